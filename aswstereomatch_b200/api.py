@@ -1,0 +1,464 @@
+"""ctypes host binding over the C ABI (include/asw/asw.h -> libasw_b200.so).
+
+Mirrors the reference's operator interface (aswStereoMatch/methods/aswMethods.h): the same
+function names, argument order, defaults and error behaviour, with numpy arrays in place of
+cv::Mat (HxWx3 uint8 BGR in, HxW float32 disparity out; invalid arguments give an empty
+array where the reference returns an empty Mat()).  There is NO CPU fallback: importing
+works without a GPU (so the symbol table can be checked), but creating a context raises
+if the CUDA library or a device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libasw_b200.so")
+
+# P.h:4-24
+DISPARITY_LEFT, DISPARITY_RIGHT = 0, 1
+(BM, SGBM, ADAPTIVE_WEIGHT, ADAPTIVE_WEIGHT_8DIRECT, ADAPTIVE_WEIGHT_GEODESIC, ADAPTIVE_WEIGHT_BILATERAL_GRID,
+ ADAPTIVE_WEIGHT_BLO1, ADAPTIVE_WEIGHT_GUIDED_FILTER, ADAPTIVE_WEIGHT_GUIDED_FILTER_2,
+ ADAPTIVE_WEIGHT_GUIDED_FILTER_3, ADAPTIVE_WEIGHT_MEDIAN, NCC) = range(12)
+
+ASW_OK, ASW_ERR_BAD_ARG, ASW_ERR_SIZE_MISMATCH, ASW_ERR_CUDA, ASW_ERR_UNSUPPORTED, ASW_ERR_NOMEM = range(6)
+_STATUS = {0: "ASW_OK", 1: "ASW_ERR_BAD_ARG", 2: "ASW_ERR_SIZE_MISMATCH", 3: "ASW_ERR_CUDA",
+           4: "ASW_ERR_UNSUPPORTED", 5: "ASW_ERR_NOMEM"}
+
+
+class AswError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"{_STATUS.get(status, status)}: {msg}")
+        self.status = status
+
+
+class U8Image(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("channels", C.c_int),
+                ("step", C.c_size_t)]
+
+
+class F32Image(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("step", C.c_size_t)]
+
+
+class MaskImage(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int), ("step", C.c_size_t)]
+
+
+# every symbol include/asw/asw.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "asw_device_count", "asw_create", "asw_destroy", "asw_last_error", "asw_version", "asw_sync", "asw_stream",
+    "asw_host_alloc", "asw_host_free", "asw_stereo_matching", "asw_adaptive_weight",
+    "asw_adaptive_weight_geodesic", "asw_adaptive_weight_bilateral_grid", "asw_adaptive_weight_blo1",
+    "asw_adaptive_weight_guidedf", "asw_adaptive_weight_guidedf_2", "asw_adaptive_weight_weighted_median",
+    "asw_capture_aggregated", "asw_cost_tad_cg", "asw_cost_sad_box", "asw_wta", "asw_guided_filter",
+    "asw_geodesic_dist", "asw_lr_check", "asw_fill_invalid", "asw_wmedian_refine", "asw_guidedf2_lr_refine",
+    "asw_batch_create", "asw_batch_destroy", "asw_batch_upload", "asw_batch_run_guidedf2_lr_refine",
+    "asw_batch_run_method", "asw_batch_download", "asw_split_local_keys", "asw_keys_alloc", "asw_keys_download",
+    "asw_keys_upload", "asw_keys_min_merge", "asw_keys_to_disparity", "asw_timer_start", "asw_timer_stop",
+    "asw_profile_enable", "asw_profile_reset", "asw_profile_count", "asw_profile_entry", "asw_launch_count",
+    "asw_flush_l2",
+]
+
+_lib = None
+
+
+def load_library():
+    """Load libasw_b200.so.  Raises (never falls back) when the CUDA extension is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, ci, cd, cf = C.c_void_p, C.c_int, C.c_double, C.c_float
+    pu8, pf32, pmask = C.POINTER(U8Image), C.POINTER(F32Image), C.POINTER(MaskImage)
+    sig = {
+        "asw_device_count": (ci, []),
+        "asw_create": (ci, [ci, C.POINTER(vp)]),
+        "asw_destroy": (None, [vp]),
+        "asw_last_error": (C.c_char_p, [vp]),
+        "asw_version": (C.c_char_p, []),
+        "asw_sync": (ci, [vp]),
+        "asw_stream": (vp, [vp]),
+        "asw_host_alloc": (vp, [C.c_size_t]),
+        "asw_host_free": (None, [vp]),
+        "asw_stereo_matching": (ci, [vp, pu8, pu8, pf32, ci, ci, ci, ci, ci]),
+        "asw_adaptive_weight": (ci, [vp, pu8, pu8, pf32, cd, cd, ci, ci, ci, ci]),
+        "asw_adaptive_weight_geodesic": (ci, [vp, pu8, pu8, pf32, ci, ci, ci, ci]),
+        "asw_adaptive_weight_bilateral_grid": (ci, [vp, pu8, pu8, pf32, ci, cd, cd, ci, ci]),
+        "asw_adaptive_weight_blo1": (ci, [vp, pu8, pu8, pf32, ci, cd, ci, ci, ci]),
+        "asw_adaptive_weight_guidedf": (ci, [vp, pu8, pu8, pf32, ci, cd, ci, ci, ci]),
+        "asw_adaptive_weight_guidedf_2": (ci, [vp, pu8, pu8, pf32, ci, cd, ci, ci, ci]),
+        "asw_adaptive_weight_weighted_median": (ci, [vp, pu8, pu8, pf32, ci, ci, cd, cd, ci, ci]),
+        "asw_capture_aggregated": (ci, [vp, vp, C.c_size_t]),
+        "asw_cost_tad_cg": (ci, [vp, pu8, pu8, vp, cd, cd, cd, ci, ci, ci]),
+        "asw_cost_sad_box": (ci, [vp, pu8, pu8, vp, ci, ci, ci, ci]),
+        "asw_wta": (ci, [vp, vp, ci, ci, ci, ci, pf32]),
+        "asw_guided_filter": (ci, [vp, pu8, pf32, ci, cd, pf32]),
+        "asw_geodesic_dist": (ci, [vp, pu8, ci, vp]),
+        "asw_lr_check": (ci, [vp, pf32, pf32, cf, pmask]),
+        "asw_fill_invalid": (ci, [vp, pf32, pmask, pf32]),
+        "asw_wmedian_refine": (ci, [vp, pu8, pf32, pmask, ci, cd, cd, pf32]),
+        "asw_guidedf2_lr_refine": (ci, [vp, pu8, pu8, pf32, cd, ci, ci, ci, cf, cd, cd, pf32, pf32, pmask]),
+        "asw_batch_create": (ci, [vp, ci, ci, ci, C.POINTER(vp)]),
+        "asw_batch_destroy": (None, [vp]),
+        "asw_batch_upload": (ci, [vp, ci, pu8, pu8]),
+        "asw_batch_run_guidedf2_lr_refine": (ci, [vp, cd, ci, ci, ci, cf, cd, cd]),
+        "asw_batch_run_method": (ci, [vp, ci, ci, ci, ci, ci]),
+        "asw_batch_download": (ci, [vp, ci, pf32]),
+        "asw_split_local_keys": (ci, [vp, pu8, pu8, ci, ci, ci, ci, ci, ci, ci, C.POINTER(vp)]),
+        "asw_keys_alloc": (ci, [vp, ci, ci, C.POINTER(vp)]),
+        "asw_keys_download": (ci, [vp, vp, ci, ci, vp]),
+        "asw_keys_upload": (ci, [vp, vp, ci, ci, vp]),
+        "asw_keys_min_merge": (ci, [vp, vp, vp, ci, ci]),
+        "asw_keys_to_disparity": (ci, [vp, vp, pf32]),
+        "asw_timer_start": (ci, [vp]),
+        "asw_timer_stop": (ci, [vp, C.POINTER(cf)]),
+        "asw_profile_enable": (ci, [vp, ci]),
+        "asw_profile_reset": (ci, [vp]),
+        "asw_profile_count": (ci, [vp]),
+        "asw_profile_entry": (ci, [vp, ci, C.POINTER(C.c_char_p), C.POINTER(cd), C.POINTER(C.c_longlong)]),
+        "asw_launch_count": (C.c_longlong, [vp]),
+        "asw_flush_l2": (ci, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _u8(a, channels=3):
+    a = np.asarray(a)
+    if a.dtype != np.uint8:
+        raise TypeError("image must be uint8")
+    if a.ndim == 2:
+        a = a[:, :, None]
+    if a.strides[2] != 1 or a.strides[1] != a.shape[2]:
+        a = np.ascontiguousarray(a)
+    return a, U8Image(a.ctypes.data, a.shape[0], a.shape[1], a.shape[2], a.strides[0])
+
+
+def _f32_in(a):
+    a = np.asarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.strides[1] != 4:
+        a = np.ascontiguousarray(a)
+    return a, F32Image(a.ctypes.data, a.shape[0], a.shape[1], a.strides[0])
+
+
+def _f32_out(H, W):
+    a = np.empty((H, W), np.float32)
+    return a, F32Image(a.ctypes.data, H, W, a.strides[0])
+
+
+def _mask_in(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, MaskImage(a.ctypes.data, a.shape[0], a.shape[1], a.strides[0])
+
+
+def _mask_out(H, W):
+    a = np.empty((H, W), np.uint8)
+    return a, MaskImage(a.ctypes.data, H, W, a.strides[0])
+
+
+class Context:
+    """One CUDA device + stream + workspaces (asw_ctx).  Not thread-safe."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.asw_create(int(device), C.byref(h))
+        if st != ASW_OK:
+            raise AswError(st, "asw_create failed: no usable CUDA device (there is no CPU fallback)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.asw_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, st):
+        if st != ASW_OK:
+            raise AswError(st, self.lib.asw_last_error(self.h).decode())
+
+    # ---- per-method entry points; strict=False mirrors the reference (empty Mat on invalid input) ----
+    def _method(self, fn, L, R, args, n_eval, agg, strict):
+        La, Ls = _u8(L)
+        Ra, Rs = _u8(R)
+        H, W = La.shape[:2]
+        out, outs = _f32_out(H, W)
+        vol = None
+        if agg:
+            vol = np.empty((n_eval, H, W), np.float32)
+            self._chk(self.lib.asw_capture_aggregated(self.h, vol.ctypes.data, vol.size))
+        st = fn(self.h, C.byref(Ls), C.byref(Rs), C.byref(outs), *args)
+        if st != ASW_OK:
+            self.lib.asw_capture_aggregated(self.h, None, 0)
+            if strict or st in (ASW_ERR_CUDA, ASW_ERR_NOMEM):
+                self._chk(st)
+            empty = np.empty((0, 0), np.float32)
+            return (empty, None) if agg else empty
+        return (out, vol) if agg else out
+
+    def stereoMatching(self, srcLeft, srcRight, disparityType, algorithmType, winSize=15, minDisparity=0,
+                       numDisparity=64, strict=False):
+        """stereoMatching (A.h:91-92); returns the disparity map the reference writes to disparityMap."""
+        return self._method(self.lib.asw_stereo_matching, srcLeft, srcRight,
+                            (int(disparityType), int(algorithmType), int(winSize), int(minDisparity),
+                             int(numDisparity)), 0, False, strict)
+
+    def computeAdaptiveWeight(self, leftImg, rightImg, gamma_c=30.0, gamma_g=2.0, dispType=DISPARITY_LEFT,
+                              winSize=7, minDisparity=186, numDisparity=144, agg=False, strict=False):
+        return self._method(self.lib.asw_adaptive_weight, leftImg, rightImg,
+                            (float(gamma_c), float(gamma_g), int(dispType), int(winSize), int(minDisparity),
+                             int(numDisparity)), numDisparity + 1, agg, strict)
+
+    def computeAdaptiveWeight_geodesic(self, leftImg, rightImg, dispType=DISPARITY_LEFT, winSize=7,
+                                       minDisparity=186, numDisparity=144, agg=False, strict=False):
+        return self._method(self.lib.asw_adaptive_weight_geodesic, leftImg, rightImg,
+                            (int(dispType), int(winSize), int(minDisparity), int(numDisparity)),
+                            numDisparity + 1, agg, strict)
+
+    def computeAdaptiveWeight_bilateralGrid(self, leftImg, rightImg, dispType=DISPARITY_LEFT, sampleRateS=10.0,
+                                            sampleRateR=10.0, minDisparity=186, numDisparity=144, agg=False,
+                                            strict=False):
+        return self._method(self.lib.asw_adaptive_weight_bilateral_grid, leftImg, rightImg,
+                            (int(dispType), float(sampleRateS), float(sampleRateR), int(minDisparity),
+                             int(numDisparity)), numDisparity + 1, agg, strict)
+
+    def computeAdaptiveWeight_BLO1(self, leftImg, rightImg, dispType=DISPARITY_LEFT, sampleRateR=10.0, winSize=35,
+                                   minDisparity=186, numDisparity=144, agg=False, strict=False):
+        return self._method(self.lib.asw_adaptive_weight_blo1, leftImg, rightImg,
+                            (int(dispType), float(sampleRateR), int(winSize), int(minDisparity), int(numDisparity)),
+                            numDisparity, agg, strict)
+
+    def computeAdaptiveWeight_GuidedF(self, leftImg, rightImg, dispType=DISPARITY_LEFT, eps=1e-8, winSize=35,
+                                      minDisparity=186, numDisparity=144, agg=False, strict=False):
+        return self._method(self.lib.asw_adaptive_weight_guidedf, leftImg, rightImg,
+                            (int(dispType), float(eps), int(winSize), int(minDisparity), int(numDisparity)),
+                            numDisparity, agg, strict)
+
+    def computeAdaptiveWeight_GuidedF_2(self, leftImg, rightImg, dispType=DISPARITY_LEFT, eps=1e-8, winSize=35,
+                                        minDisparity=186, numDisparity=144, agg=False, strict=False):
+        return self._method(self.lib.asw_adaptive_weight_guidedf_2, leftImg, rightImg,
+                            (int(dispType), float(eps), int(winSize), int(minDisparity), int(numDisparity)),
+                            numDisparity, agg, strict)
+
+    def computeAdaptiveWeight_WeightedMedian(self, leftImg, rightImg, dispType=DISPARITY_LEFT, winSize=35,
+                                             sampleRateS=10.0, sampleRateR=10.0, minDisparity=186,
+                                             numDisparity=144, agg=False, strict=False):
+        return self._method(self.lib.asw_adaptive_weight_weighted_median, leftImg, rightImg,
+                            (int(dispType), int(winSize), float(sampleRateS), float(sampleRateR),
+                             int(minDisparity), int(numDisparity)), numDisparity, agg, strict)
+
+    # ---- stage level ----
+    def computeSimilarity(self, leftImg, rightImg, regularity, thresC, thresG, dispType, minDisparity,
+                          numDisparity):
+        """computeSimilarity 7-arg (A.h:112-114): returns the [D][H][W] float volume (cost_d_imgs)."""
+        La, Ls = _u8(leftImg)
+        Ra, Rs = _u8(rightImg)
+        H, W = La.shape[:2]
+        vol = np.empty((numDisparity, H, W), np.float32)
+        self._chk(self.lib.asw_cost_tad_cg(self.h, C.byref(Ls), C.byref(Rs), vol.ctypes.data, float(regularity),
+                                           float(thresC), float(thresG), int(dispType), int(minDisparity),
+                                           int(numDisparity)))
+        return vol
+
+    def getCostSAD(self, leftImg, rightImg, dispType, winSize, minDisparity, numDisparity):
+        """getCostSAD_d for every d (A.h:157 as called at A.cpp:2524-2536)."""
+        La, Ls = _u8(leftImg)
+        Ra, Rs = _u8(rightImg)
+        H, W = La.shape[:2]
+        vol = np.empty((numDisparity, H, W), np.float32)
+        self._chk(self.lib.asw_cost_sad_box(self.h, C.byref(Ls), C.byref(Rs), vol.ctypes.data, int(dispType),
+                                            int(winSize), int(minDisparity), int(numDisparity)))
+        return vol
+
+    def wta(self, volume, minDisparity=0):
+        v = np.ascontiguousarray(volume, dtype=np.float32)
+        D, H, W = v.shape
+        out, outs = _f32_out(H, W)
+        self._chk(self.lib.asw_wta(self.h, v.ctypes.data, D, H, W, int(minDisparity), C.byref(outs)))
+        return out
+
+    def getGuidedFilter(self, guidedImg, inputP, r, eps):
+        ga, gs = _u8(guidedImg)
+        pa, ps = _f32_in(inputP)
+        out, outs = _f32_out(pa.shape[0], pa.shape[1])
+        self._chk(self.lib.asw_guided_filter(self.h, C.byref(gs), C.byref(ps), int(r), float(eps), C.byref(outs)))
+        return out
+
+    def getGeodesicDist(self, img, winSize):
+        ia, is_ = _u8(img)
+        H, W = ia.shape[:2]
+        out = np.empty((H, W, winSize, winSize), np.float32)
+        self._chk(self.lib.asw_geodesic_dist(self.h, C.byref(is_), int(winSize), out.ctypes.data))
+        return out
+
+    def lr_check(self, dl, dr, tol=0.0):
+        a, as_ = _f32_in(dl)
+        b, bs = _f32_in(dr)
+        m, ms = _mask_out(a.shape[0], a.shape[1])
+        self._chk(self.lib.asw_lr_check(self.h, C.byref(as_), C.byref(bs), float(tol), C.byref(ms)))
+        return m
+
+    def fill_invalid(self, d, valid):
+        a, as_ = _f32_in(d)
+        m, ms = _mask_in(valid)
+        out, outs = _f32_out(a.shape[0], a.shape[1])
+        self._chk(self.lib.asw_fill_invalid(self.h, C.byref(as_), C.byref(ms), C.byref(outs)))
+        return out
+
+    def wmedian_refine(self, img, filled, valid, win=9, rate_s=10.0, rate_r=10.0):
+        ia, is_ = _u8(img)
+        f, fs = _f32_in(filled)
+        m, ms = _mask_in(valid)
+        out, outs = _f32_out(f.shape[0], f.shape[1])
+        self._chk(self.lib.asw_wmedian_refine(self.h, C.byref(is_), C.byref(fs), C.byref(ms), int(win),
+                                              float(rate_s), float(rate_r), C.byref(outs)))
+        return out
+
+    def guidedf2_lr_refine(self, L, R, eps=1e-4, win=9, min_d=0, num_d=64, tol=0.0, rate_s=10.0, rate_r=10.0,
+                           parts=False):
+        La, Ls = _u8(L)
+        Ra, Rs = _u8(R)
+        H, W = La.shape[:2]
+        out, outs = _f32_out(H, W)
+        if parts:
+            dl, dls = _f32_out(H, W)
+            dr, drs = _f32_out(H, W)
+            m, ms = _mask_out(H, W)
+            self._chk(self.lib.asw_guidedf2_lr_refine(self.h, C.byref(Ls), C.byref(Rs), C.byref(outs), float(eps),
+                                                      int(win), int(min_d), int(num_d), float(tol), float(rate_s),
+                                                      float(rate_r), C.byref(dls), C.byref(drs), C.byref(ms)))
+            return out, dict(dl=dl, dr=dr, valid=m)
+        self._chk(self.lib.asw_guidedf2_lr_refine(self.h, C.byref(Ls), C.byref(Rs), C.byref(outs), float(eps),
+                                                  int(win), int(min_d), int(num_d), float(tol), float(rate_s),
+                                                  float(rate_r), None, None, None))
+        return out
+
+    # ---- disparity split ----
+    def split_local_keys(self, L, R, algorithm, disp_type, win, min_d, num_d, d_begin, d_end):
+        La, Ls = _u8(L)
+        Ra, Rs = _u8(R)
+        H, W = La.shape[:2]
+        dk = C.c_void_p()
+        self._chk(self.lib.asw_split_local_keys(self.h, C.byref(Ls), C.byref(Rs), int(algorithm), int(disp_type),
+                                                int(win), int(min_d), int(num_d), int(d_begin), int(d_end),
+                                                C.byref(dk)))
+        keys = np.empty((H, W), np.uint64)
+        self._chk(self.lib.asw_keys_download(self.h, dk, H, W, keys.ctypes.data))
+        return keys, dk
+
+    def keys_to_disparity(self, keys):
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        H, W = keys.shape
+        dk = C.c_void_p()
+        self._chk(self.lib.asw_keys_alloc(self.h, H, W, C.byref(dk)))
+        self._chk(self.lib.asw_keys_upload(self.h, keys.ctypes.data, H, W, dk))
+        out, outs = _f32_out(H, W)
+        self._chk(self.lib.asw_keys_to_disparity(self.h, dk, C.byref(outs)))
+        return out
+
+    # ---- measurement ----
+    def sync(self):
+        self._chk(self.lib.asw_sync(self.h))
+
+    def timer_start(self):
+        self._chk(self.lib.asw_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        self._chk(self.lib.asw_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, on=True):
+        self._chk(self.lib.asw_profile_enable(self.h, 1 if on else 0))
+
+    def profile_reset(self):
+        self._chk(self.lib.asw_profile_reset(self.h))
+
+    def profile(self):
+        out = {}
+        for i in range(self.lib.asw_profile_count(self.h)):
+            name = C.c_char_p()
+            ms = C.c_double()
+            n = C.c_longlong()
+            self._chk(self.lib.asw_profile_entry(self.h, i, C.byref(name), C.byref(ms), C.byref(n)))
+            out[name.value.decode()] = (ms.value, n.value)
+        return out
+
+    def launch_count(self):
+        return int(self.lib.asw_launch_count(self.h))
+
+    def flush_l2(self):
+        self._chk(self.lib.asw_flush_l2(self.h))
+
+
+class Batch:
+    """Device-resident batch of stereo pairs (config 5)."""
+
+    def __init__(self, ctx, n_pairs, H, W):
+        self.ctx = ctx
+        self.n, self.H, self.W = n_pairs, H, W
+        h = C.c_void_p()
+        ctx._chk(ctx.lib.asw_batch_create(ctx.h, n_pairs, H, W, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.asw_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, i, L, R):
+        La, Ls = _u8(L)
+        Ra, Rs = _u8(R)
+        self.ctx._chk(self.ctx.lib.asw_batch_upload(self.h, i, C.byref(Ls), C.byref(Rs)))
+
+    def run_guidedf2_lr_refine(self, eps=1e-4, win=9, min_d=0, num_d=64, tol=0.0, rate_s=10.0, rate_r=10.0):
+        self.ctx._chk(self.ctx.lib.asw_batch_run_guidedf2_lr_refine(self.h, float(eps), int(win), int(min_d),
+                                                                    int(num_d), float(tol), float(rate_s),
+                                                                    float(rate_r)))
+
+    def run_method(self, algorithm, disp_type=DISPARITY_LEFT, win=15, min_d=0, num_d=64):
+        self.ctx._chk(self.ctx.lib.asw_batch_run_method(self.h, int(algorithm), int(disp_type), int(win),
+                                                        int(min_d), int(num_d)))
+
+    def download(self, i, out=None, sync=True):
+        """D2H of pair i's map (asynchronous on the ctx stream unless sync)."""
+        if out is None:
+            out = np.empty((self.H, self.W), np.float32)
+        s = F32Image(out.ctypes.data, self.H, self.W, out.strides[0])
+        self.ctx._chk(self.ctx.lib.asw_batch_download(self.h, i, C.byref(s)))
+        if sync:
+            self.ctx.sync()
+        return out
+
+
+def pinned_empty(shape, dtype):
+    """numpy array over cudaHostAlloc'ed (pinned) memory; keeps the allocation alive via .base."""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = lib.asw_host_alloc(max(nbytes, 1))
+    if not p:
+        raise MemoryError("asw_host_alloc failed")
+    buf = (C.c_uint8 * nbytes).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    return arr

@@ -1,0 +1,164 @@
+// asw_common.cuh -- context, device buffers, launch/profiling helpers (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/asw/asw.h"
+
+#define ASW_MAX_PROFILE 48
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct ProfEntry {
+    const char* name;
+    double total_ms;
+    long long launches;
+};
+
+struct asw_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;      // asw_timer_*
+    cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;      // per-kernel profiling
+    char err[512] = {0};
+    int sm_count = 148;
+    // named workspaces (grow-only)
+    std::vector<DevBuf> bufs;
+    // profiling
+    bool profiling = false;
+    ProfEntry prof[ASW_MAX_PROFILE];
+    int n_prof = 0;
+    long long launches = 0;
+    // capture hook
+    float* capture_host = nullptr;
+    size_t capture_cap = 0;
+    // L2 flush scratch
+    DevBuf flush;
+    // pinned staging for small D2H results
+    void* pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+// workspace slots
+enum {
+    WS_IMG_L = 0, WS_IMG_R, WS_FEAT_REF, WS_FEAT_TGT, WS_GUIDE_I, WS_GUIDE_MI, WS_GUIDE_DEN,
+    WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_VOL0, WS_VOL1, WS_AB, WS_KEYS, WS_KEYS2, WS_DISP_L, WS_DISP_R,
+    WS_MASK, WS_FILLED, WS_OUT, WS_SLICE_MM, WS_GRAY_L, WS_GRAY_R, WS_GEO_L, WS_GEO_R, WS_GRID_S, WS_GRID_C,
+    WS_TABLE0, WS_TABLE1, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3, WS_COUNT
+};
+
+static inline asw_status asw_fail(asw_ctx* ctx, asw_status st, const char* fmt, const char* a = "", const char* b = "") {
+    if (ctx) snprintf(ctx->err, sizeof(ctx->err), fmt, a, b);
+    return st;
+}
+
+#define ASW_CUDA(ctx, call)                                                              \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            return asw_fail((ctx), ASW_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+        }                                                                                \
+    } while (0)
+
+#define ASW_TRY(expr)                        \
+    do {                                     \
+        asw_status s__ = (expr);             \
+        if (s__ != ASW_OK) return s__;       \
+    } while (0)
+
+// reserve a workspace slot (grow-only; contents undefined after growth)
+static inline asw_status ws_reserve(asw_ctx* ctx, int slot, size_t bytes, void** out) {
+    if ((int)ctx->bufs.size() < WS_COUNT) ctx->bufs.resize(WS_COUNT);
+    DevBuf& b = ctx->bufs[slot];
+    if (b.cap < bytes) {
+        if (b.p) {
+            ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ASW_CUDA(ctx, cudaFree(b.p));
+            b.p = nullptr; b.cap = 0;
+        }
+        size_t cap = (bytes + 255) & ~(size_t)255;
+        cudaError_t e = cudaMalloc(&b.p, cap);
+        if (e != cudaSuccess) {
+            b.p = nullptr;
+            return asw_fail(ctx, ASW_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
+        }
+        b.cap = cap;
+    }
+    *out = b.p;
+    return ASW_OK;
+}
+template <typename T>
+static inline asw_status ws_get(asw_ctx* ctx, int slot, size_t count, T** out) {
+    void* p = nullptr;
+    asw_status s = ws_reserve(ctx, slot, count * sizeof(T), &p);
+    *out = (T*)p;
+    return s;
+}
+
+// profiling-aware launch bracket: PROF_BEGIN(ctx); kernel<<<...>>>(...); PROF_END(ctx, "name");
+static inline void prof_begin(asw_ctx* ctx) {
+    if (ctx->profiling) cudaEventRecord(ctx->ev_p0, ctx->stream);
+}
+static inline asw_status prof_end(asw_ctx* ctx, const char* name) {
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return asw_fail(ctx, ASW_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(e));
+    if (ctx->profiling) {
+        cudaEventRecord(ctx->ev_p1, ctx->stream);
+        cudaEventSynchronize(ctx->ev_p1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev_p0, ctx->ev_p1);
+        int i = 0;
+        for (; i < ctx->n_prof; i++)
+            if (strcmp(ctx->prof[i].name, name) == 0) break;
+        if (i == ctx->n_prof && ctx->n_prof < ASW_MAX_PROFILE) {
+            ctx->prof[i].name = name; ctx->prof[i].total_ms = 0; ctx->prof[i].launches = 0;
+            ctx->n_prof++;
+        }
+        if (i < ctx->n_prof) { ctx->prof[i].total_ms += ms; ctx->prof[i].launches++; }
+    }
+    return ASW_OK;
+}
+#define LAUNCH(ctx, name, ...)            \
+    do {                                  \
+        prof_begin(ctx);                  \
+        __VA_ARGS__;                      \
+        ASW_TRY(prof_end(ctx, name));     \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+// cv::borderInterpolate: delta = 0 BORDER_REFLECT, delta = 1 BORDER_REFLECT_101
+__device__ __forceinline__ int border_idx(int p, int len, int delta) {
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        if (p < 0) p = -p - 1 + delta;
+        else p = len - 1 - (p - len) - delta;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// total order on float bits such that unsigned compare == float compare; NaN -> 0xFFFFFFFF
+__device__ __forceinline__ uint32_t orderable_u32(float f) {
+    if (f != f) return 0xFFFFFFFFu;
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+// 64-bit WTA key: strict-< / lowest-d-wins / NaN-never-wins under unsigned min
+__device__ __forceinline__ unsigned long long wta_key(float cost, int d) {
+    return ((unsigned long long)orderable_u32(cost) << 32) | (unsigned)d;
+}
+#define WTA_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull

@@ -1,0 +1,434 @@
+// asw_lib.cu -- C ABI (include/asw/asw.h) over the sm_100a kernels.  Single translation unit.
+// Host orchestration only: argument checks mirroring the reference's early-outs, H2D / D2H,
+// workspace management, kernel launches.  No CPU compute path: every stage is a CUDA kernel.
+#include "asw_common.cuh"
+#include "k_prep.cuh"
+#include "k_cost.cuh"
+#include "k_guided.cuh"
+#include "k_refine.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+// =================================================================================================
+// context
+// =================================================================================================
+extern "C" int asw_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+extern "C" const char* asw_version(void) { return "aswstereomatch_b200 0.1 (sm_100a)"; }
+
+extern "C" asw_status asw_create(int device, asw_ctx** out) {
+    if (!out) return ASW_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return ASW_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return ASW_ERR_CUDA;
+    asw_ctx* ctx = new asw_ctx();
+    ctx->device = device;
+    ctx->bufs.resize(WS_COUNT);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_t0) != cudaSuccess || cudaEventCreate(&ctx->ev_t1) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev_p0) != cudaSuccess || cudaEventCreate(&ctx->ev_p1) != cudaSuccess) {
+        delete ctx;
+        return ASW_ERR_CUDA;
+    }
+    *out = ctx;
+    return ASW_OK;
+}
+extern "C" void asw_destroy(asw_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& b : ctx->bufs) if (b.p) cudaFree(b.p);
+    if (ctx->flush.p) cudaFree(ctx->flush.p);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
+    cudaEventDestroy(ctx->ev_p0); cudaEventDestroy(ctx->ev_p1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+extern "C" const char* asw_last_error(const asw_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+extern "C" asw_status asw_sync(asw_ctx* ctx) {
+    if (!ctx) return ASW_ERR_BAD_ARG;
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ASW_OK;
+}
+extern "C" void* asw_stream(asw_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" void* asw_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) return nullptr;
+    return p;
+}
+extern "C" void asw_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" asw_status asw_timer_start(asw_ctx* ctx) {
+    if (!ctx) return ASW_ERR_BAD_ARG;
+    ASW_CUDA(ctx, cudaEventRecord(ctx->ev_t0, ctx->stream));
+    return ASW_OK;
+}
+extern "C" asw_status asw_timer_stop(asw_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return ASW_ERR_BAD_ARG;
+    ASW_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
+    ASW_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
+    ASW_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));
+    return ASW_OK;
+}
+extern "C" asw_status asw_profile_enable(asw_ctx* ctx, int on) {
+    if (!ctx) return ASW_ERR_BAD_ARG;
+    ctx->profiling = on != 0;
+    return ASW_OK;
+}
+extern "C" asw_status asw_profile_reset(asw_ctx* ctx) {
+    if (!ctx) return ASW_ERR_BAD_ARG;
+    ctx->n_prof = 0;
+    ctx->launches = 0;
+    return ASW_OK;
+}
+extern "C" int asw_profile_count(asw_ctx* ctx) { return ctx ? ctx->n_prof : 0; }
+extern "C" asw_status asw_profile_entry(asw_ctx* ctx, int i, const char** name, double* total_ms, long long* launches) {
+    if (!ctx || i < 0 || i >= ctx->n_prof) return ASW_ERR_BAD_ARG;
+    if (name) *name = ctx->prof[i].name;
+    if (total_ms) *total_ms = ctx->prof[i].total_ms;
+    if (launches) *launches = ctx->prof[i].launches;
+    return ASW_OK;
+}
+extern "C" long long asw_launch_count(asw_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+__global__ void k_flush_l2(uint4* __restrict__ p, size_t n, uint32_t v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = make_uint4(v, v, v, v);
+}
+extern "C" asw_status asw_flush_l2(asw_ctx* ctx) {
+    if (!ctx) return ASW_ERR_BAD_ARG;
+    ASW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)256 << 20;   // 256 MiB > 126 MB L2
+    if (!ctx->flush.p) {
+        ASW_CUDA(ctx, cudaMalloc(&ctx->flush.p, bytes));
+        ctx->flush.cap = bytes;
+    }
+    static uint32_t tick = 0;
+    k_flush_l2<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>((uint4*)ctx->flush.p, bytes / 16, ++tick);
+    ASW_CUDA(ctx, cudaGetLastError());
+    return ASW_OK;
+}
+extern "C" asw_status asw_capture_aggregated(asw_ctx* ctx, float* host_volume, size_t capacity_floats) {
+    if (!ctx) return ASW_ERR_BAD_ARG;
+    ctx->capture_host = host_volume;
+    ctx->capture_cap = host_volume ? capacity_floats : 0;
+    return ASW_OK;
+}
+
+// =================================================================================================
+// host <-> device helpers
+// =================================================================================================
+static asw_status check_u8(asw_ctx* ctx, const asw_u8_image* im, int channels) {
+    if (!im || !im->data || im->rows <= 0 || im->cols <= 0) return asw_fail(ctx, ASW_ERR_BAD_ARG, "empty image%s%s");
+    if (im->channels != channels) return asw_fail(ctx, ASW_ERR_BAD_ARG, "unexpected channel count%s%s");
+    if (im->step < (size_t)im->cols * channels) return asw_fail(ctx, ASW_ERR_BAD_ARG, "bad step%s%s");
+    return ASW_OK;
+}
+static asw_status check_f32(asw_ctx* ctx, const asw_f32_image* im) {
+    if (!im || !im->data || im->rows <= 0 || im->cols <= 0 || im->step < (size_t)im->cols * 4)
+        return asw_fail(ctx, ASW_ERR_BAD_ARG, "bad float image%s%s");
+    return ASW_OK;
+}
+static asw_status check_mask(asw_ctx* ctx, const asw_mask_image* im) {
+    if (!im || !im->data || im->rows <= 0 || im->cols <= 0 || im->step < (size_t)im->cols)
+        return asw_fail(ctx, ASW_ERR_BAD_ARG, "bad mask image%s%s");
+    return ASW_OK;
+}
+static asw_status check_pair(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, const asw_f32_image* disp) {
+    if (!ctx) return ASW_ERR_BAD_ARG;
+    ASW_TRY(check_u8(ctx, L, 3));
+    ASW_TRY(check_u8(ctx, R, 3));
+    if (L->rows != R->rows || L->cols != R->cols) return asw_fail(ctx, ASW_ERR_SIZE_MISMATCH, "left/right sizes differ%s%s");
+    if (disp) {
+        ASW_TRY(check_f32(ctx, disp));
+        if (disp->rows != L->rows || disp->cols != L->cols)
+            return asw_fail(ctx, ASW_ERR_SIZE_MISMATCH, "disparity map size differs from the images%s%s");
+    }
+    return ASW_OK;
+}
+static asw_status upload_u8(asw_ctx* ctx, const asw_u8_image* im, uint8_t* dst) {
+    size_t rowb = (size_t)im->cols * im->channels;
+    ASW_CUDA(ctx, cudaMemcpy2DAsync(dst, rowb, im->data, im->step, rowb, im->rows, cudaMemcpyHostToDevice, ctx->stream));
+    return ASW_OK;
+}
+static asw_status upload_f32(asw_ctx* ctx, const asw_f32_image* im, float* dst) {
+    size_t rowb = (size_t)im->cols * 4;
+    ASW_CUDA(ctx, cudaMemcpy2DAsync(dst, rowb, im->data, im->step, rowb, im->rows, cudaMemcpyHostToDevice, ctx->stream));
+    return ASW_OK;
+}
+static asw_status upload_mask(asw_ctx* ctx, const asw_mask_image* im, uint8_t* dst) {
+    ASW_CUDA(ctx, cudaMemcpy2DAsync(dst, im->cols, im->data, im->step, im->cols, im->rows, cudaMemcpyHostToDevice, ctx->stream));
+    return ASW_OK;
+}
+static asw_status download_f32(asw_ctx* ctx, const float* src, asw_f32_image* im) {
+    size_t rowb = (size_t)im->cols * 4;
+    ASW_CUDA(ctx, cudaMemcpy2DAsync(im->data, im->step, src, rowb, rowb, im->rows, cudaMemcpyDeviceToHost, ctx->stream));
+    return ASW_OK;
+}
+static asw_status download_mask(asw_ctx* ctx, const uint8_t* src, asw_mask_image* im) {
+    ASW_CUDA(ctx, cudaMemcpy2DAsync(im->data, im->step, src, im->cols, im->cols, im->rows, cudaMemcpyDeviceToHost, ctx->stream));
+    return ASW_OK;
+}
+static asw_status upload_pair(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, uint8_t** dL, uint8_t** dR) {
+    size_t n = (size_t)L->rows * L->cols * 3;
+    ASW_TRY(ws_get(ctx, WS_IMG_L, n, dL));
+    ASW_TRY(ws_get(ctx, WS_IMG_R, n, dR));
+    ASW_TRY(upload_u8(ctx, L, *dL));
+    ASW_TRY(upload_u8(ctx, R, *dR));
+    return ASW_OK;
+}
+// copy the aggregated volume to the capture buffer (if armed) and disarm
+static asw_status finish_capture(asw_ctx* ctx, const float* dev_agg, size_t count) {
+    if (!ctx->capture_host) return ASW_OK;
+    float* dst = ctx->capture_host;
+    size_t cap = ctx->capture_cap;
+    ctx->capture_host = nullptr; ctx->capture_cap = 0;
+    if (cap < count) return asw_fail(ctx, ASW_ERR_BAD_ARG, "capture buffer too small%s%s");
+    ASW_CUDA(ctx, cudaMemcpyAsync(dst, dev_agg, count * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ASW_OK;
+}
+static asw_status init_keys(asw_ctx* ctx, unsigned long long* keys, size_t n) {
+    LAUNCH(ctx, "fill_u64", (k_fill_u64<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(keys, n, WTA_KEY_EMPTY)));
+    return ASW_OK;
+}
+static asw_status keys_to_disp(asw_ctx* ctx, const unsigned long long* keys, size_t n, float* disp) {
+    LAUNCH(ctx, "keys_to_disp", (k_keys_to_disp<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(keys, n, disp)));
+    return ASW_OK;
+}
+
+// =================================================================================================
+// device-level pipelines (inputs and outputs resident in HBM)
+// =================================================================================================
+struct ViewGeom {
+    const uint8_t* ref; const uint8_t* tgt;   // tightly packed BGR on device
+    int H, W, max_off, pad_l, pad_r, Wp, x0_base, x0_step;
+};
+// LEFT: pad the right image on the left by max_off, crop at max_off - offset (A.cpp:442, 455)
+// RIGHT: pad the left image on the right, crop at offset (A.cpp:491, 503)
+static ViewGeom make_view(const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type, int min_d, int num_d) {
+    ViewGeom v;
+    v.H = H; v.W = W;
+    v.max_off = min_d + num_d - 1;
+    if (disp_type == ASW_DISPARITY_LEFT) {
+        v.ref = dL; v.tgt = dR; v.pad_l = v.max_off; v.pad_r = 0;
+        v.x0_base = v.max_off - min_d; v.x0_step = -1;
+    } else {
+        v.ref = dR; v.tgt = dL; v.pad_l = 0; v.pad_r = v.max_off;
+        v.x0_base = min_d; v.x0_step = 1;
+    }
+    v.Wp = W + v.max_off;
+    return v;
+}
+
+__global__ void k_init_slice_mm(uint32_t* mm, int D) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < D) { mm[2 * i] = 0xFFFFFFFFu; mm[2 * i + 1] = 0u; }
+}
+__global__ void k_init_mm_u8(int* mm) { mm[0] = 255; mm[1] = 0; }
+
+// guidance moments for a C-channel u8 guide: planes I (C), mean_I (C), den (C) + packed records for C == 3
+struct GuidePrep { float* I; float* mI; float* den; float4 *Gi, *Gm, *Gd; };
+static asw_status prep_guide(asw_ctx* ctx, const uint8_t* guide, int H, int W, int C, int r, double eps, GuidePrep* gp) {
+    size_t n = (size_t)H * W;
+    float *planes, *boxed;
+    int* mm;
+    ASW_TRY(ws_get(ctx, WS_TMP0, n * 2 * C, &planes));
+    ASW_TRY(ws_get(ctx, WS_TMP1, n * 2 * C, &boxed));
+    ASW_TRY(ws_get(ctx, WS_MISC0, (size_t)64, &mm));
+    gp->Gi = gp->Gm = gp->Gd = nullptr;
+    if (C == 3) {
+        ASW_TRY(ws_get(ctx, WS_GUIDE_I, n, &gp->Gi));
+        ASW_TRY(ws_get(ctx, WS_GUIDE_MI, n, &gp->Gm));
+        ASW_TRY(ws_get(ctx, WS_GUIDE_DEN, n, &gp->Gd));
+    }
+    LAUNCH(ctx, "init_mm", (k_init_mm_u8<<<1, 1, 0, ctx->stream>>>(mm)));
+    LAUNCH(ctx, "minmax_u8", (k_minmax_u8<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(guide, n * C, mm)));
+    LAUNCH(ctx, "guide_normalize", (k_guide_normalize<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(guide, n, C, mm, planes, gp->Gi)));
+    ASW_TRY(launch_box_f32(ctx, planes, boxed, H, W, r, 2 * C, n));
+    LAUNCH(ctx, "guide_finish", (k_guide_finish<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(boxed, n, C, (float)eps, gp->Gm, gp->Gd)));
+    gp->I = planes; gp->mI = boxed; gp->den = boxed + n * C;
+    return ASW_OK;
+}
+
+static size_t gf_smem_bytes(int k) {
+    int IW = GF_TW + k - 1, IH = GF_TH + k - 1;
+    return ((size_t)IH * (IW | 1) + (size_t)IH * GF_HP) * sizeof(float4);
+}
+static int gf_chunk_slices(size_t n) {
+    // keep one chunk's a/b planes (16 B per DE) inside the 126 MB L2 so pass 2 reads them from L2
+    size_t budget = (size_t)64 << 20;
+    const char* e = getenv("ASW_GF_CHUNK_MB");
+    if (e && atoi(e) > 0) budget = (size_t)atoi(e) << 20;
+    size_t s = budget / (n * 16);
+    if (s < 1) s = 1;
+    return (int)s;
+}
+
+// GuidedF_2 for one view, fast path.  keys must be initialised by the caller (allows d-range splits).
+// d_lo/d_hi: slice index range [d_lo, d_hi) evaluated (labels = min_d + index).
+static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type,
+                                    double eps, int win, int min_d, int num_d, int d_lo, int d_hi,
+                                    unsigned long long* keys, float* agg_dev) {
+    size_t n = (size_t)H * W;
+    ViewGeom v = make_view(dL, dR, H, W, disp_type, min_d, num_d);
+    Feat *fref, *ftgt;
+    ASW_TRY(ws_get(ctx, WS_FEAT_REF, n, &fref));
+    ASW_TRY(ws_get(ctx, WS_FEAT_TGT, (size_t)H * v.Wp, &ftgt));
+    LAUNCH(ctx, "features", (k_features<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(v.ref, H, W, 0, 0, fref)));
+    LAUNCH(ctx, "features", (k_features<<<dim3(cdiv(v.Wp, 128), H), 128, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, ftgt)));
+    GuidePrep gp;
+    ASW_TRY(prep_guide(ctx, v.ref, H, W, 3, win, eps, &gp));                        // A.cpp:3004 / 3019
+    uint32_t* slice_mm;
+    ASW_TRY(ws_get(ctx, WS_SLICE_MM, (size_t)2 * num_d, &slice_mm));
+    LAUNCH(ctx, "init_slice_mm", (k_init_slice_mm<<<cdiv(num_d, 128), 128, 0, ctx->stream>>>(slice_mm, num_d)));
+    TadParams tp = make_tad_params(0.4, 10, 50);                                     // A.cpp:2990
+    const int DC = 4;
+    int chunk = gf_chunk_slices(n);
+    chunk = ((chunk + DC - 1) / DC) * DC;
+    int span = d_hi - d_lo;
+    if (chunk > span) chunk = ((span + DC - 1) / DC) * DC;
+    float4* ab;
+    ASW_TRY(ws_get(ctx, WS_AB, n * (size_t)chunk, &ab));
+    size_t smem = gf_smem_bytes(win);
+    if (smem > 220 * 1024) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "guided-filter window too large for the tiled kernels%s%s");
+    cudaFuncSetAttribute(k_gf_ab<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_gf_q<DC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 tiles(cdiv(W, GF_TW), cdiv(H, GF_TH), 1);
+    for (int c0 = d_lo; c0 < d_hi; c0 += chunk) {
+        int cn = (d_hi - c0 < chunk) ? d_hi - c0 : chunk;
+        GfGeom g;
+        g.H = H; g.W = W; g.Wp = v.Wp; g.k = win; g.a = win / 2;
+        g.x0_base = v.x0_base + v.x0_step * c0; g.x0_step = v.x0_step; g.D = cn;
+        dim3 grid(tiles.x, tiles.y, cdiv(cn, DC));
+        LAUNCH(ctx, "gf_ab", (k_gf_ab<DC><<<grid, GF_THREADS, smem, ctx->stream>>>(fref, ftgt, gp.Gi, gp.Gm, gp.Gd, g, tp, ab, slice_mm + 2 * c0)));
+        LAUNCH(ctx, "gf_q", (k_gf_q<DC><<<grid, GF_THREADS, smem, ctx->stream>>>(ab, gp.Gi, g, tp.c0, slice_mm + 2 * c0, min_d + c0, keys,
+                                                                              agg_dev ? agg_dev + (size_t)(c0 - d_lo) * n : nullptr)));
+    }
+    return ASW_OK;
+}
+
+static asw_status dev_guidedf2(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type,
+                               double eps, int win, int min_d, int num_d, float* disp_dev, float* agg_dev) {
+    size_t n = (size_t)H * W;
+    unsigned long long* keys;
+    ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
+    ASW_TRY(init_keys(ctx, keys, n));
+    ASW_TRY(dev_guidedf2_keys(ctx, dL, dR, H, W, disp_type, eps, win, min_d, num_d, 0, num_d, keys, agg_dev));
+    return keys_to_disp(ctx, keys, n, disp_dev);
+}
+
+// generic guided filter of one slice: cost (device, n floats) -> q (device); guide prepared by prep_guide
+static asw_status dev_gf_generic_slice(asw_ctx* ctx, const GuidePrep& gp, const float* cost, int H, int W, int C, int r, float* q) {
+    size_t n = (size_t)H * W;
+    float *planes, *boxed;
+    uint32_t* mm;
+    ASW_TRY(ws_get(ctx, WS_TMP2, n * (1 + C), &planes));
+    ASW_TRY(ws_get(ctx, WS_TMP3, n * (1 + C), &boxed));
+    ASW_TRY(ws_get(ctx, WS_MISC1, (size_t)64, &mm));
+    LAUNCH(ctx, "init_slice_mm", (k_init_slice_mm<<<1, 32, 0, ctx->stream>>>(mm, 1)));
+    LAUNCH(ctx, "minmax_f32", (k_minmax_f32_slices<<<dim3(ctx->sm_count * 2, 1), 256, 0, ctx->stream>>>(cost, n, mm)));
+    unsigned nb = (unsigned)((n + 255) / 256);
+    LAUNCH(ctx, "gfg_products", (k_gfg_products<<<nb, 256, 0, ctx->stream>>>(cost, mm, gp.I, n, C, planes)));
+    ASW_TRY(launch_box_f32(ctx, planes, boxed, H, W, r, 1 + C, n));
+    LAUNCH(ctx, "gfg_ab", (k_gfg_ab<<<nb, 256, 0, ctx->stream>>>(boxed, gp.mI, gp.den, n, C)));
+    ASW_TRY(launch_box_f32(ctx, boxed, planes, H, W, r, 1 + C, n));
+    LAUNCH(ctx, "gfg_q", (k_gfg_q<<<nb, 256, 0, ctx->stream>>>(planes, gp.I, n, C, q)));
+    return ASW_OK;
+}
+
+// gray + SAD box cost volume on device (A.cpp:2442-2503 for every d), vol [num_d][n]
+static asw_status dev_cost_sad_box(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type,
+                                   int win, int min_d, int num_d, float* vol, uint8_t** gray_ref_out, uint8_t** gray_tgt_out) {
+    size_t n = (size_t)H * W;
+    ViewGeom v = make_view(dL, dR, H, W, disp_type, min_d, num_d);
+    uint8_t *gref, *gtgt;
+    ASW_TRY(ws_get(ctx, WS_GRAY_L, n, &gref));
+    ASW_TRY(ws_get(ctx, WS_GRAY_R, (size_t)H * v.Wp, &gtgt));
+    LAUNCH(ctx, "bgr2gray", (k_bgr2gray_pad<<<dim3(cdiv(W, 256), H), 256, 0, ctx->stream>>>(v.ref, H, W, 0, 0, gref)));
+    LAUNCH(ctx, "bgr2gray", (k_bgr2gray_pad<<<dim3(cdiv(v.Wp, 256), H), 256, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, gtgt)));
+    float* ad;
+    ASW_TRY(ws_get(ctx, WS_VOL1, n * num_d, &ad));
+    LAUNCH(ctx, "gray_absdiff", (k_gray_absdiff<<<dim3(cdiv(W, 256), H, num_d), 256, 0, ctx->stream>>>(gref, gtgt, H, W, v.Wp, v.x0_base, v.x0_step, ad)));
+    ASW_TRY(launch_box_f32(ctx, ad, vol, H, W, win, num_d, n));
+    if (gray_ref_out) *gray_ref_out = gref;
+    if (gray_tgt_out) *gray_tgt_out = gtgt;
+    return ASW_OK;
+}
+
+// GuidedF (6-channel guidance, SAD cost), A.cpp:2867-2963
+static asw_status dev_guidedf(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type, double eps,
+                              int win, int min_d, int num_d, float* disp_dev, float* agg_dev) {
+    size_t n = (size_t)H * W;
+    float* cost;
+    ASW_TRY(ws_get(ctx, WS_VOL0, n * num_d, &cost));
+    ASW_TRY(dev_cost_sad_box(ctx, dL, dR, H, W, disp_type, win, min_d, num_d, cost, nullptr, nullptr));
+    ViewGeom v = make_view(dL, dR, H, W, disp_type, min_d, num_d);
+    // padded target BGR image for the 6-channel guide (A.cpp:2877-2878)
+    uint8_t *tpad, *guide6;
+    ASW_TRY(ws_get(ctx, WS_MISC2, (size_t)H * v.Wp * 3, &tpad));
+    ASW_TRY(ws_get(ctx, WS_MISC3, n * 6, &guide6));
+    LAUNCH(ctx, "pad_bgr", (k_pad_cols_bgr<<<dim3(cdiv(v.Wp, 128), H), 128, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, tpad)));
+    float* q = agg_dev;
+    if (!q) ASW_TRY(ws_get(ctx, WS_VOL1, n * num_d, &q));   // the |L-R| planes in WS_VOL1 are dead after dev_cost_sad_box
+    for (int i = 0; i < num_d; i++) {
+        // LEFT: Rect(numDisparity - i - 1, ..) (A.cpp:2909); RIGHT: Rect(i + minDisparity, ..) (A.cpp:2926)
+        int x0 = disp_type == ASW_DISPARITY_LEFT ? num_d - i - 1 : i + min_d;
+        LAUNCH(ctx, "merge_guide6", (k_merge_guide6<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(
+                                        v.ref, tpad, H, W, v.Wp, x0, disp_type == ASW_DISPARITY_LEFT ? 1 : 0, guide6)));
+        GuidePrep gp;
+        ASW_TRY(prep_guide(ctx, guide6, H, W, 6, win, eps, &gp));
+        ASW_TRY(dev_gf_generic_slice(ctx, gp, cost + (size_t)i * n, H, W, 6, win, q + (size_t)i * n));
+    }
+    unsigned long long* keys;
+    ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
+    ASW_TRY(init_keys(ctx, keys, n));
+    LAUNCH(ctx, "wta_keys", (k_wta_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(q, num_d, n, min_d, keys)));
+    return keys_to_disp(ctx, keys, n, disp_dev);
+}
+
+// stage 4 on device
+static asw_status dev_lr_refine(asw_ctx* ctx, const uint8_t* dL, const float* dl, const float* dr, int H, int W, float tol,
+                                int win, double rate_s, double rate_r, uint8_t* valid, float* filled, float* out) {
+    dim3 grid(cdiv(W, 128), H);
+    LAUNCH(ctx, "lr_check", (k_lr_check<<<grid, 128, 0, ctx->stream>>>(dl, dr, H, W, tol, valid)));
+    LAUNCH(ctx, "fill_invalid", (k_fill_invalid<<<grid, 128, 0, ctx->stream>>>(dl, valid, H, W, filled)));
+    double alpha_r = (1.0 / rate_r) * (-1);
+    float alpha_s = (float)((1.0 / rate_s) * (-1));
+    LAUNCH(ctx, "wmedian_refine", (k_wmedian_refine<<<dim3(cdiv(W, 32), H), 32, 0, ctx->stream>>>(dL, filled, valid, H, W, win, alpha_r, alpha_s, out)));
+    return ASW_OK;
+}
+
+static asw_status dev_guidedf2_lr_refine(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double eps, int win,
+                                         int min_d, int num_d, float tol, double rate_s, double rate_r, float* out,
+                                         float** dl_out, float** dr_out, uint8_t** valid_out) {
+    size_t n = (size_t)H * W;
+    float *dl, *dr, *filled;
+    uint8_t* valid;
+    ASW_TRY(ws_get(ctx, WS_DISP_L, n, &dl));
+    ASW_TRY(ws_get(ctx, WS_DISP_R, n, &dr));
+    ASW_TRY(ws_get(ctx, WS_FILLED, n, &filled));
+    ASW_TRY(ws_get(ctx, WS_MASK, n, &valid));
+    ASW_TRY(dev_guidedf2(ctx, dL, dR, H, W, ASW_DISPARITY_LEFT, eps, win, min_d, num_d, dl, nullptr));
+    ASW_TRY(dev_guidedf2(ctx, dL, dR, H, W, ASW_DISPARITY_RIGHT, eps, win, min_d, num_d, dr, nullptr));
+    ASW_TRY(dev_lr_refine(ctx, dL, dl, dr, H, W, tol, win, rate_s, rate_r, valid, filled, out));
+    if (dl_out) *dl_out = dl;
+    if (dr_out) *dr_out = dr;
+    if (valid_out) *valid_out = valid;
+    return ASW_OK;
+}
+
+#include "k_traditional.cuh"
+#include "k_geodesic.cuh"
+#include "k_grid.cuh"
+#include "k_blo1.cuh"
+#include "k_wmedian.cuh"
+#include "asw_methods.inl"

@@ -1,0 +1,102 @@
+// k_cost.cuh -- stage 1 raw costs: TAD colour+gradient (A.cpp:415-487) and box-SAD (A.cpp:2442-2503),
+// and the stand-alone WTA (A.cpp:3032-3048).
+#pragma once
+#include "k_prep.cuh"
+
+struct TadParams {
+    double reg, reg_r;     // regularity, 1 - regularity            (A.cpp:435)
+    float thr_c;           // colour threshold                       (A.cpp:462)
+    float add_c;           // 255 * (float)(thresC/255): scaleAdd on u8 (SURVEY B-2)
+    float thr_g;           // gradient threshold                     (A.cpp:475)
+    float g_hi, g_lo;      // 254*thrG, 255*thrG                     (A.cpp:474-482)
+    float c0;              // smallest possible cost: blend(0, 255*thrG)
+};
+
+static inline TadParams make_tad_params(double regularity, double thres_c, double thres_g) {
+    TadParams p;
+    p.reg = regularity;
+    p.reg_r = 1 - regularity;
+    p.thr_c = (float)thres_c;
+    p.add_c = 255.0f * (float)(thres_c / 255.0);
+    p.thr_g = (float)thres_g;
+    p.g_hi = 254.0f * p.thr_g;
+    p.g_lo = 255.0f * p.thr_g;
+    p.c0 = (float)__builtin_fma(0.0, p.reg_r, (double)p.g_lo * p.reg);
+    return p;
+}
+
+// cv::addWeighted on CV_32F (OpenCV 4.13): double scalars, (float)fma(a, alpha, b*beta)
+__device__ __forceinline__ float add_weighted_f32(float a, double alpha, float b, double beta) {
+    return (float)fma((double)a, alpha, __dmul_rn((double)b, beta));
+}
+
+// One disparity evaluation of computeSimilarity's 3-channel LEFT branch (A.cpp:455-484).
+__device__ __forceinline__ float tad_cost(const Feat& a, const Feat& b, const TadParams& p) {
+    uint32_t ad = __vabsdiffu4(a.bgr, b.bgr);                       // absdiff per channel (A.cpp:455)
+    int c0 = ad & 0xFF, c1 = (ad >> 8) & 0xFF, c2 = (ad >> 16) & 0xFF;
+    int s = min(c0 + c1, 255) + c2;                                 // (c0+c1) saturates, then +c2
+    int color = ((s + 1) * 43691) >> 17;                            // round(s/3): addWeighted(1/3,1/3) u8
+    float cc = 0.0f;
+    if ((float)color > p.thr_c)                                     // A.cpp:461-465 (inverted truncation)
+        cc = fminf(rintf((float)color + p.add_c), 255.0f);
+    int ga0 = (int16_t)(a.g01 & 0xFFFF), ga1 = (int16_t)(a.g01 >> 16), ga2 = (int16_t)(a.g2 & 0xFFFF);
+    int gb0 = (int16_t)(b.g01 & 0xFFFF), gb1 = (int16_t)(b.g01 >> 16), gb2 = (int16_t)(b.g2 & 0xFFFF);
+    float g0 = (float)abs(ga0 - gb0), g1 = (float)abs(ga1 - gb1), g2 = (float)abs(ga2 - gb2);
+    float gm1 = __fadd_rn(g0, g1);
+    float G = add_weighted_f32(gm1, 1.0 / 3, g2, 1.0 / 3);         // A.cpp:473
+    float gc = (G > p.thr_g) ? __fadd_rn(p.g_hi, G) : p.g_lo;       // A.cpp:474-482
+    return add_weighted_f32(cc, p.reg_r, gc, p.reg);                // A.cpp:484
+}
+
+// Raw TAD C+G volume [D][H][W]; x0_base + x0_step*di = column offset of the target crop
+// (LEFT: max_off - offset, RIGHT: offset).
+__global__ void k_cost_tad_volume(const Feat* __restrict__ ref, const Feat* __restrict__ tgt, int H, int W,
+                                  int Wp, int x0_base, int x0_step, TadParams p, float* __restrict__ vol) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y, di = blockIdx.z;
+    if (x >= W) return;
+    int x0 = x0_base + x0_step * di;
+    Feat a = ref[(size_t)y * W + x];
+    Feat b = tgt[(size_t)y * Wp + x0 + x];
+    vol[((size_t)di * H + y) * W + x] = tad_cost(a, b, p);
+}
+
+// gray absolute difference as float, one slice per blockIdx.z (A.cpp:2477-2478)
+__global__ void k_gray_absdiff(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, int H, int W,
+                               int Wp, int x0_base, int x0_step, float* __restrict__ vol) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y, di = blockIdx.z;
+    if (x >= W) return;
+    int x0 = x0_base + x0_step * di;
+    int v = (int)ref[(size_t)y * W + x] - (int)tgt[(size_t)y * Wp + x0 + x];
+    vol[((size_t)di * H + y) * W + x] = (float)abs(v);
+}
+
+// WTA over a materialised volume -> 64-bit keys (strict <, ascending d, NaN/inf never win)
+__global__ void k_wta_keys(const float* __restrict__ vol, int D, size_t n, int d_first,
+                           unsigned long long* __restrict__ keys) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long best = WTA_KEY_EMPTY;
+    for (int d = 0; d < D; d++) {
+        unsigned long long k = wta_key(vol[(size_t)d * n + i], d_first + d);
+        best = min(best, k);
+    }
+    keys[i] = min(keys[i], best);
+}
+__global__ void k_fill_u64(unsigned long long* __restrict__ p, size_t n, unsigned long long v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+// keys -> float disparity; a cost of +inf or NaN never beats DBL_MAX in the reference: sentinel 0
+__global__ void k_keys_to_disp(const unsigned long long* __restrict__ keys, size_t n, float* __restrict__ disp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long k = keys[i];
+    uint32_t hi = (uint32_t)(k >> 32);
+    disp[i] = (hi >= 0xFF800000u) ? 0.0f : (float)(uint32_t)(k & 0xFFFFFFFFu);
+}
+__global__ void k_keys_min_merge(unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = min(a[i], b[i]);
+}

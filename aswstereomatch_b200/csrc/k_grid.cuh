@@ -1,0 +1,3 @@
+// k_grid.cuh -- placeholder
+#pragma once
+static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_s, double rate_r, int min_d, int num_d, float* disp_dev, float* agg_dev) { return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "not built yet%s%s"); }

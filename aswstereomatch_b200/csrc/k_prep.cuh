@@ -1,0 +1,171 @@
+// k_prep.cuh -- image preparation kernels shared by the methods:
+//   * feature records (BGR + Scharr-x gradient) for the TAD C+G cost (A.cpp:442-450)
+//   * BGR2GRAY (OpenCV >= 4.2 fixed point), column REFLECT padding
+//   * generic double-accumulated box filter (cv::boxFilter 32F semantics, SURVEY B-9)
+//   * min/max reductions
+#pragma once
+#include "asw_common.cuh"
+
+// One 16-byte record per pixel: x = B | G<<8 | R<<16, y = gB (lo16) | gG (hi16), z = gR (lo16).
+// Gradients are exact integers in [-4080, 4080] (16 * 255) so int16 holds them.
+struct __align__(16) Feat {
+    uint32_t bgr;
+    uint32_t g01;
+    uint32_t g2;
+    uint32_t pad;
+};
+
+// Build records for an image padded on the column axis with BORDER_REFLECT (pad_l / pad_r columns);
+// the gradient is filter2D([-3 0 3; -10 0 10; -3 0 3]) of the PADDED image with BORDER_REFLECT_101
+// (A.cpp:446-450 applies filter2D to right_border).
+__global__ void k_features(const uint8_t* __restrict__ img, int H, int W, int pad_l, int pad_r,
+                           Feat* __restrict__ out) {
+    int Wp = W + pad_l + pad_r;
+    int xp = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (xp >= Wp) return;
+    int ys[3] = {border_idx(y - 1, H, 1), y, border_idx(y + 1, H, 1)};
+    int xs[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        int xq = border_idx(xp - 1 + i, Wp, 1);       // REFLECT_101 inside the padded image
+        xs[i] = border_idx(xq - pad_l, W, 0);         // padded column -> source column (REFLECT)
+    }
+    int g[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        int v = 0;
+        const int wgt[3] = {3, 10, 3};
+#pragma unroll
+        for (int r = 0; r < 3; r++) {
+            const uint8_t* row = img + (size_t)ys[r] * W * 3;
+            v += wgt[r] * ((int)row[xs[2] * 3 + c] - (int)row[xs[0] * 3 + c]);
+        }
+        g[c] = v;
+    }
+    const uint8_t* px = img + ((size_t)y * W + xs[1]) * 3;
+    Feat f;
+    f.bgr = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16);
+    f.g01 = ((uint32_t)(uint16_t)(int16_t)g[0]) | ((uint32_t)(uint16_t)(int16_t)g[1] << 16);
+    f.g2 = (uint32_t)(uint16_t)(int16_t)g[2];
+    f.pad = 0;
+    out[(size_t)y * Wp + xp] = f;
+}
+
+// cvtColor(BGR2GRAY) u8: (3735 B + 19235 G + 9798 R + 2^14) >> 15, with optional REFLECT column padding
+__global__ void k_bgr2gray_pad(const uint8_t* __restrict__ img, int H, int W, int pad_l, int pad_r,
+                               uint8_t* __restrict__ out) {
+    int Wp = W + pad_l + pad_r;
+    int xp = blockIdx.x * blockDim.x + threadIdx.x;
+    int y = blockIdx.y;
+    if (xp >= Wp) return;
+    int x = border_idx(xp - pad_l, W, 0);
+    const uint8_t* px = img + ((size_t)y * W + x) * 3;
+    out[(size_t)y * Wp + xp] = (uint8_t)((3735 * px[0] + 19235 * px[1] + 9798 * px[2] + (1 << 14)) >> 15);
+}
+
+// min / max of a u8 buffer -> mm[0] = min, mm[1] = max (ints, pre-initialised to 255 / 0)
+__global__ void k_minmax_u8(const uint8_t* __restrict__ src, size_t n, int* __restrict__ mm) {
+    int mn = 255, mx = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        int v = src[i];
+        mn = min(mn, v); mx = max(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[0], mn); atomicMax(&mm[1], mx); }
+}
+
+// per-slice min / max of a float volume [D][n]; mm[2*d] = min bits, mm[2*d+1] = max bits using the
+// orderable-uint encoding (works for any sign).  mm pre-initialised to 0xFFFFFFFF / 0.
+__global__ void k_minmax_f32_slices(const float* __restrict__ vol, size_t n, uint32_t* __restrict__ mm) {
+    int d = blockIdx.y;
+    const float* s = vol + (size_t)d * n;
+    uint32_t mn = 0xFFFFFFFFu, mx = 0u;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float v = s[i];
+        if (v == v) { uint32_t o = orderable_u32(v); mn = min(mn, o); mx = max(mx, o); }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[2 * d], mn); atomicMax(&mm[2 * d + 1], mx); }
+}
+__device__ __forceinline__ float from_orderable(uint32_t o) {
+    uint32_t b = (o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o;
+    return __uint_as_float(b);
+}
+
+// cv::normalize(NORM_MINMAX, 0..1, CV_32F) scalars (SURVEY B-10): sf = (float)(1/(max-min)),
+// hf = 0f - (float)(min * sf)
+__device__ __forceinline__ void minmax_scale_shift(double mn, double mx, float* sf, float* hf) {
+    double scale = (mx - mn > 2.220446049250313e-16) ? 1.0 / (mx - mn) : 0.0;
+    *sf = (float)scale;
+    *hf = 0.0f - (float)(mn * (double)(*sf));
+}
+
+// Generic box filter, one plane per blockIdx.z: cv::boxFilter(32F -> 32F, normalised, anchor k/2,
+// BORDER_REFLECT_101) with double accumulation (direct separable sums; OpenCV uses running double
+// sums, the two agree to the last float ulp except on rare pixels).  Tile 32x8 outputs per block.
+template <int TW, int TH>
+__global__ void k_box_f32(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int k,
+                          size_t plane_stride) {
+    extern __shared__ double sm_box[];
+    int a = k / 2;
+    int IW = TW + k - 1, IH = TH + k - 1;
+    double* tile = sm_box;                  // [IH][IW]
+    double* hs = sm_box + (size_t)IH * IW;  // [IH][TW]
+    const float* s = src + (size_t)blockIdx.z * plane_stride;
+    float* o = dst + (size_t)blockIdx.z * plane_stride;
+    int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    int tid = threadIdx.y * blockDim.x + threadIdx.x, nt = blockDim.x * blockDim.y;
+    for (int i = tid; i < IH * IW; i += nt) {
+        int r = i / IW, c = i % IW;
+        int sy = border_idx(y0 - a + r, H, 1), sx = border_idx(x0 - a + c, W, 1);
+        tile[i] = (double)s[(size_t)sy * W + sx];
+    }
+    __syncthreads();
+    for (int i = tid; i < IH * TW; i += nt) {
+        int r = i / TW, c = i % TW;
+        double acc = 0;
+        for (int j = 0; j < k; j++) acc += tile[r * IW + c + j];
+        hs[i] = acc;
+    }
+    __syncthreads();
+    double scale = 1.0 / ((double)k * k);
+    for (int i = tid; i < TH * TW; i += nt) {
+        int r = i / TW, c = i % TW;
+        int x = x0 + c, y = y0 + r;
+        if (x < W && y < H) {
+            double acc = 0;
+            for (int j = 0; j < k; j++) acc += hs[(r + j) * TW + c];
+            o[(size_t)y * W + x] = (float)(acc * scale);
+        }
+    }
+}
+
+static inline asw_status launch_box_f32(asw_ctx* ctx, const float* src, float* dst, int H, int W, int k,
+                                        int planes, size_t plane_stride) {
+    const int TW = 32, TH = 8;
+    size_t smem = ((size_t)(TH + k - 1) * (TW + k - 1) + (size_t)(TH + k - 1) * TW) * sizeof(double);
+    if (smem > 200 * 1024) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "box window too large%s%s");
+    cudaFuncSetAttribute(k_box_f32<TW, TH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    dim3 grid(cdiv(W, TW), cdiv(H, TH), planes), block(32, 8);
+    LAUNCH(ctx, "box_f32", (k_box_f32<TW, TH><<<grid, block, smem, ctx->stream>>>(src, dst, H, W, k, plane_stride)));
+    return ASW_OK;
+}
+
+// copyMakeBorder(img, 0, 0, pad_l, pad_r, BORDER_REFLECT) for BGR u8
+__global__ void k_pad_cols_bgr(const uint8_t* __restrict__ img, int H, int W, int pad_l, int pad_r,
+                               uint8_t* __restrict__ out) {
+    int Wp = W + pad_l + pad_r;
+    int xp = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (xp >= Wp) return;
+    int x = border_idx(xp - pad_l, W, 0);
+    const uint8_t* s = img + ((size_t)y * W + x) * 3;
+    uint8_t* o = out + ((size_t)y * Wp + xp) * 3;
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2];
+}

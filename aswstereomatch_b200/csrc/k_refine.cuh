@@ -1,0 +1,107 @@
+// k_refine.cuh -- stage 4: LR consistency check, invalid fill, weighted-median refinement.
+// NOT in the reference: our specification, re-using the reference's weight formulas
+// (computeColorWeightGau A.cpp:3139-3205, computeSpaceWeightGau A.cpp:3207-3226) and its median
+// selection rule (A.cpp:3276-3304).  Mask / fill / selection are integer-exact against the oracle.
+#pragma once
+#include "k_cost.cuh"
+
+// valid = |dL(y,x) - dR(y, max(0, x - (int)dL))| <= tol
+__global__ void k_lr_check(const float* __restrict__ dl, const float* __restrict__ dr, int H, int W, float tol,
+                           uint8_t* __restrict__ valid) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    float d = dl[(size_t)y * W + x];
+    int xr = max(0, x - (int)d);
+    valid[(size_t)y * W + x] = fabsf(d - dr[(size_t)y * W + xr]) <= tol ? 1 : 0;
+}
+
+// invalid pixel <- min(nearest valid to the left, nearest valid to the right) on the same row
+__global__ void k_fill_invalid(const float* __restrict__ d, const uint8_t* __restrict__ valid, int H, int W,
+                               float* __restrict__ out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    const float* row = d + (size_t)y * W;
+    const uint8_t* v = valid + (size_t)y * W;
+    float r = row[x];
+    if (!v[x]) {
+        int xl = x - 1; while (xl >= 0 && !v[xl]) xl--;
+        int xr = x + 1; while (xr < W && !v[xr]) xr++;
+        if (xl >= 0 && xr < W) r = fminf(row[xl], row[xr]);
+        else if (xl >= 0) r = row[xl];
+        else if (xr < W) r = row[xr];
+    }
+    out[(size_t)y * W + x] = r;
+}
+
+// exp(-(|dB|+|dG|+|dR|)/rateR) with the float lowering of A.cpp:3177-3179:
+// (w0 + w1 + w2) / rateR * (-1) -> addWeighted(w0+w1, alpha, w2, alpha), alpha = (1/rateR)*(-1)
+__device__ __forceinline__ float wm_color_weight(const uint8_t* c, const uint8_t* q, double alpha) {
+    float d0 = (float)abs((int)q[0] - (int)c[0]), d1 = (float)abs((int)q[1] - (int)c[1]);
+    float d2 = (float)abs((int)q[2] - (int)c[2]);
+    float m1 = __fadd_rn(d0, d1);
+    float arg = (float)fma((double)m1, alpha, __dmul_rn((double)d2, alpha));
+    return (float)exp((double)arg);
+}
+
+// One thread per invalid pixel.  Window on the REFLECT-padded (A.cpp:3156) filled map.
+// Selection (A.cpp:3276-3304): stable ascending sort by value (ties keep window row-major order),
+// weights accumulated in double in that order; at the first element whose partial sum exceeds
+// total/2 return the PREVIOUS element's value (the first element's own value if it is the first).
+__global__ void k_wmedian_refine(const uint8_t* __restrict__ img, const float* __restrict__ filled,
+                                 const uint8_t* __restrict__ valid, int H, int W, int win, double alpha_r,
+                                 float alpha_s, float* __restrict__ out) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    size_t p = (size_t)y * W + x;
+    if (valid[p]) { out[p] = filled[p]; return; }
+    const int h = win / 2;
+    const uint8_t* c = img + p * 3;
+    // weight of window element (wy, wx): colour * spatial (float product, A.cpp:3273 order)
+    auto weight = [&](int wy, int wx, int sy, int sx) -> float {
+        float wc = wm_color_weight(c, img + ((size_t)sy * W + sx) * 3, alpha_r);
+        float dist2 = __fadd_rn((float)((wx - h) * (wx - h)), (float)((wy - h) * (wy - h)));
+        float wd = (float)exp((double)__fmul_rn(dist2, alpha_s));                 // A.cpp:3219-3225
+        return __fmul_rn(wc, wd);
+    };
+    double total = 0;
+    for (int wy = 0; wy < win; wy++) {
+        int sy = border_idx(y - h + wy, H, 0);
+        for (int wx = 0; wx < win; wx++) {
+            int sx = border_idx(x - h + wx, W, 0);
+            total += (double)weight(wy, wx, sy, sx);
+        }
+    }
+    const double half = total / 2;
+    double partial = 0;
+    float cur = -INFINITY, prev_val = 0.0f, result = filled[p];
+    bool first = true, done = false;
+    while (!done) {
+        // next distinct value above cur
+        float nxt = INFINITY; bool found = false;
+        for (int wy = 0; wy < win; wy++) {
+            int sy = border_idx(y - h + wy, H, 0);
+            for (int wx = 0; wx < win; wx++) {
+                float v = filled[(size_t)sy * W + border_idx(x - h + wx, W, 0)];
+                if (v > cur && v <= nxt) { nxt = v; found = true; }
+            }
+        }
+        if (!found) break;
+        for (int wy = 0; wy < win && !done; wy++) {
+            int sy = border_idx(y - h + wy, H, 0);
+            for (int wx = 0; wx < win; wx++) {
+                int sx = border_idx(x - h + wx, W, 0);
+                if (filled[(size_t)sy * W + sx] != nxt) continue;
+                partial += (double)weight(wy, wx, sy, sx);
+                if (partial > half) {
+                    result = first ? nxt : prev_val;
+                    done = true;
+                    break;
+                }
+                first = false;
+                prev_val = nxt;
+            }
+        }
+        cur = nxt;
+    }
+    out[p] = result;
+}

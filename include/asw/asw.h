@@ -1,0 +1,188 @@
+/*
+ * asw.h -- C ABI of the B200-native aswStereoMatch dense-matching hot path.
+ *
+ * Drop-in boundary for ZhangYY12345/aswStereoMatch's method entry points
+ * (aswStereoMatch/methods/aswMethods.h, cited below as A.h:<line>, bodies in
+ * aswMethods.cpp = A.cpp, enums in parametersStereo.h = P.h).  The reference
+ * exposes free C++ functions over cv::Mat; this header exposes the same calls
+ * over plain pointers and sizes so that any host (the C++ shim in
+ * aswMethods_compat.h, ctypes, cgo, JNI ...) can bind them.  No OpenCV, torch or
+ * CUDA types appear in a signature.
+ *
+ * Image convention = cv::Mat: row-major, `step` bytes per row, colour images are
+ * BGR interleaved CV_8UC3 (channels == 3).  All image pointers are HOST pointers
+ * owned by the caller; inputs are never modified (the reference takes cv::Mat by
+ * value and only re-seats its own headers, A.cpp:2272, A.cpp:1847).  Disparity
+ * maps are CV_32FC1 (integral values in [minDisparity, minDisparity+D_eval-1]).
+ *
+ * One asw_ctx = one CUDA device + one stream + its workspaces.  A ctx is not
+ * thread-safe; distinct ctxs are.  Every computation runs in hand-written sm_100a
+ * CUDA kernels; there is no CPU fallback: without a usable device asw_create fails
+ * with ASW_ERR_CUDA.
+ */
+#ifndef ASW_ASW_H
+#define ASW_ASW_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums: integer values identical to P.h:4-24 ---- */
+enum { ASW_DISPARITY_LEFT = 0, ASW_DISPARITY_RIGHT = 1 };
+enum {
+    ASW_ALG_BM = 0, ASW_ALG_SGBM = 1, ASW_ALG_ADAPTIVE_WEIGHT = 2, ASW_ALG_ADAPTIVE_WEIGHT_8DIRECT = 3,
+    ASW_ALG_ADAPTIVE_WEIGHT_GEODESIC = 4, ASW_ALG_ADAPTIVE_WEIGHT_BILATERAL_GRID = 5,
+    ASW_ALG_ADAPTIVE_WEIGHT_BLO1 = 6, ASW_ALG_ADAPTIVE_WEIGHT_GUIDED_FILTER = 7,
+    ASW_ALG_ADAPTIVE_WEIGHT_GUIDED_FILTER_2 = 8, ASW_ALG_ADAPTIVE_WEIGHT_GUIDED_FILTER_3 = 9,
+    ASW_ALG_ADAPTIVE_WEIGHT_MEDIAN = 10, ASW_ALG_NCC = 11
+};
+
+typedef enum {
+    ASW_OK = 0,
+    ASW_ERR_BAD_ARG = 1,        /* null pointer, even window, bad channels: reference returns Mat() */
+    ASW_ERR_SIZE_MISMATCH = 2,  /* left/right (or map) sizes differ */
+    ASW_ERR_CUDA = 3,           /* CUDA runtime / launch failure, or no device */
+    ASW_ERR_UNSUPPORTED = 4,    /* reference behaviour undefined (throws / UB) or out of scope */
+    ASW_ERR_NOMEM = 5
+} asw_status;
+
+typedef struct { const uint8_t* data; int rows, cols, channels; size_t step; } asw_u8_image;
+typedef struct { float* data; int rows, cols; size_t step; } asw_f32_image;
+typedef struct { uint8_t* data; int rows, cols; size_t step; } asw_mask_image;
+
+typedef struct asw_ctx asw_ctx;
+
+/* ---- lifetime ---- */
+int asw_device_count(void);
+asw_status asw_create(int device, asw_ctx** out);
+void asw_destroy(asw_ctx* ctx);
+const char* asw_last_error(const asw_ctx* ctx);
+const char* asw_version(void);
+asw_status asw_sync(asw_ctx* ctx);
+void* asw_stream(asw_ctx* ctx);                       /* the ctx's cudaStream_t */
+
+/* pinned host memory for callers that want full PCIe bandwidth */
+void* asw_host_alloc(size_t bytes);
+void asw_host_free(void* p);
+
+/* ---- dispatcher: stereoMatching (A.h:91-92, A.cpp:46-88) with the dispatcher's literals ---- */
+asw_status asw_stereo_matching(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                               asw_f32_image* disparity, int disparity_type, int algorithm_type,
+                               int win_size, int min_disparity, int num_disparity);
+
+/* ---- per-method entry points (same argument order and meaning as A.h) ---- */
+/* computeAdaptiveWeight (A.h:133-134, A.cpp:1016-1156) */
+asw_status asw_adaptive_weight(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                               asw_f32_image* disparity, double gamma_c, double gamma_g, int disp_type,
+                               int win_size, int min_disparity, int num_disparity);
+/* computeAdaptiveWeight_geodesic (A.h:141-142, A.cpp:1436-1534) */
+asw_status asw_adaptive_weight_geodesic(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                                        asw_f32_image* disparity, int disp_type, int win_size,
+                                        int min_disparity, int num_disparity);
+/* computeAdaptiveWeight_bilateralGrid (A.h:153-155, A.cpp:2253-2430) */
+asw_status asw_adaptive_weight_bilateral_grid(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                                              asw_f32_image* disparity, int disp_type, double sample_rate_s,
+                                              double sample_rate_r, int min_disparity, int num_disparity);
+/* computeAdaptiveWeight_BLO1 (A.h:158-160, A.cpp:2505-2725) */
+asw_status asw_adaptive_weight_blo1(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                                    asw_f32_image* disparity, int disp_type, double sample_rate_r,
+                                    int win_size, int min_disparity, int num_disparity);
+/* computeAdaptiveWeight_GuidedF (A.h:164-166, A.cpp:2867-2963) */
+asw_status asw_adaptive_weight_guidedf(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                                       asw_f32_image* disparity, int disp_type, double eps, int win_size,
+                                       int min_disparity, int num_disparity);
+/* computeAdaptiveWeight_GuidedF_2 (A.h:167-169, A.cpp:2976-3050) */
+asw_status asw_adaptive_weight_guidedf_2(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                                         asw_f32_image* disparity, int disp_type, double eps, int win_size,
+                                         int min_disparity, int num_disparity);
+/* computeAdaptiveWeight_WeightedMedian (A.h:176-179, A.cpp:3228-3383) */
+asw_status asw_adaptive_weight_weighted_median(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                                               asw_f32_image* disparity, int disp_type, int win_size,
+                                               double sample_rate_s, double sample_rate_r,
+                                               int min_disparity, int num_disparity);
+
+/* When set (non-NULL), the next per-method call also copies its aggregated cost volume,
+ * [D_eval][rows][cols] float, to `host_volume` (capacity in floats).  Cleared after one call.
+ * Parity-test hook for "aggregated float costs within 1e-4". */
+asw_status asw_capture_aggregated(asw_ctx* ctx, float* host_volume, size_t capacity_floats);
+
+/* ---- stage level ---- */
+/* computeSimilarity 7-arg (A.h:112-114, A.cpp:415-487): volume [num_disparity][rows][cols] */
+asw_status asw_cost_tad_cg(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                           float* host_volume, double regularity, double thres_c, double thres_g,
+                           int disp_type, int min_disparity, int num_disparity);
+/* getCostSAD_d for every d (A.h:157, A.cpp:2442-2503 as called at A.cpp:2524-2536) */
+asw_status asw_cost_sad_box(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                            float* host_volume, int disp_type, int win_size, int min_disparity,
+                            int num_disparity);
+/* the inlined WTA blocks (A.cpp:3032-3048 ...): strict <, ascending d, NaN never wins, untouched = 0 */
+asw_status asw_wta(asw_ctx* ctx, const float* host_volume, int num_slices, int rows, int cols,
+                   int min_disparity, asw_f32_image* disparity);
+/* getGuidedFilter (A.h:163, A.cpp:2766-2854); guide channels 3 or 6 */
+asw_status asw_guided_filter(asw_ctx* ctx, const asw_u8_image* guide, const asw_f32_image* input_p,
+                             int r, double eps, asw_f32_image* out);
+/* geodesic distance windows getGeodesicDist (A.h:140, A.cpp:1392-1424): [rows][cols][win*win] */
+asw_status asw_geodesic_dist(asw_ctx* ctx, const asw_u8_image* img, int win_size, float* host_dist);
+
+/* ---- stage 4 (not in the reference; specification in DESIGN.md / SURVEY 8 a-14) ---- */
+asw_status asw_lr_check(asw_ctx* ctx, const asw_f32_image* disp_left, const asw_f32_image* disp_right,
+                        float tol, asw_mask_image* valid);
+asw_status asw_fill_invalid(asw_ctx* ctx, const asw_f32_image* disp, const asw_mask_image* valid,
+                            asw_f32_image* out);
+asw_status asw_wmedian_refine(asw_ctx* ctx, const asw_u8_image* img, const asw_f32_image* filled,
+                              const asw_mask_image* valid, int win_size, double rate_s, double rate_r,
+                              asw_f32_image* out);
+/* full frame of configs 2/5: GuidedF_2 left + right view, LR check, fill, weighted-median refine.
+ * Optional outputs (may be NULL): raw left/right maps and the validity mask. */
+asw_status asw_guidedf2_lr_refine(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                                  asw_f32_image* refined, double eps, int win_size, int min_disparity,
+                                  int num_disparity, float lr_tol, double rate_s, double rate_r,
+                                  asw_f32_image* raw_left, asw_f32_image* raw_right, asw_mask_image* valid);
+
+/* ---- device-resident batches (config 5; inputs live in HBM between upload and run) ---- */
+typedef struct asw_batch asw_batch;
+asw_status asw_batch_create(asw_ctx* ctx, int n_pairs, int rows, int cols, asw_batch** out);
+void asw_batch_destroy(asw_batch* b);
+asw_status asw_batch_upload(asw_batch* b, int index, const asw_u8_image* left, const asw_u8_image* right);
+/* asynchronous on the ctx stream: every pair through asw_guidedf2_lr_refine's pipeline */
+asw_status asw_batch_run_guidedf2_lr_refine(asw_batch* b, double eps, int win_size, int min_disparity,
+                                            int num_disparity, float lr_tol, double rate_s, double rate_r);
+/* asynchronous: every pair through one method of the dispatcher (left view only) */
+asw_status asw_batch_run_method(asw_batch* b, int algorithm_type, int disp_type, int win_size,
+                                int min_disparity, int num_disparity);
+asw_status asw_batch_download(asw_batch* b, int index, asw_f32_image* disparity);
+
+/* ---- disparity-range split of one pair (multi-GPU) ----
+ * Each rank evaluates candidates [d_begin, d_end) and gets per-pixel 64-bit keys
+ * (orderable(cost) << 32 | d) in a device buffer; a MIN all-reduce over ranks (NCCL via
+ * torch.distributed, or asw_keys_min_merge for peer buffers) then asw_keys_to_disparity
+ * reproduces strict-< / lowest-d / NaN-never-wins exactly. */
+asw_status asw_split_local_keys(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                                int algorithm_type, int disp_type, int win_size, int min_disparity,
+                                int num_disparity, int d_begin, int d_end, void** device_keys);
+/* a rows x cols key buffer in the ctx workspace, initialised to "empty" (all ones) */
+asw_status asw_keys_alloc(asw_ctx* ctx, int rows, int cols, void** device_keys);
+asw_status asw_keys_download(asw_ctx* ctx, const void* device_keys, int rows, int cols, uint64_t* host_keys);
+asw_status asw_keys_upload(asw_ctx* ctx, const uint64_t* host_keys, int rows, int cols, void* device_keys);
+asw_status asw_keys_min_merge(asw_ctx* ctx, void* device_keys_inout, const void* device_keys_other,
+                              int rows, int cols);
+asw_status asw_keys_to_disparity(asw_ctx* ctx, const void* device_keys, asw_f32_image* disparity);
+
+/* ---- measurement hooks (CUDA events on the ctx stream) ---- */
+asw_status asw_timer_start(asw_ctx* ctx);
+asw_status asw_timer_stop(asw_ctx* ctx, float* elapsed_ms);      /* synchronises the stream */
+asw_status asw_profile_enable(asw_ctx* ctx, int on);              /* per-kernel event timing */
+asw_status asw_profile_reset(asw_ctx* ctx);
+int asw_profile_count(asw_ctx* ctx);
+asw_status asw_profile_entry(asw_ctx* ctx, int index, const char** kernel_name, double* total_ms,
+                             long long* launches);
+long long asw_launch_count(asw_ctx* ctx);                         /* kernels launched since create/reset */
+asw_status asw_flush_l2(asw_ctx* ctx);                            /* writes a >L2-sized scratch buffer */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ASW_ASW_H */

@@ -1,0 +1,151 @@
+"""GPU parity: TAD C+G cost, WTA, guided-filter ASW (configs 2 and 5) and stage 4, through the C ABI,
+against the CPU oracle on identical seeded inputs.  Tolerances are north_star's: integer / index stages
+bit-exact given the same cost volume; aggregated float costs within 1e-4 relative (relative to the slice
+max |cost|); final disparity maps agree on >= 99.9 % of pixels."""
+import numpy as np
+import pytest
+
+import aswstereomatch_b200 as asw
+from aswstereomatch_b200.synth import make_pair
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4
+AGREE = 0.999
+
+
+def rel_err(a, b):
+    """max over slices of |a-b| / max|b| of that slice"""
+    a = a.reshape(a.shape[0], -1).astype(np.float64)
+    b = b.reshape(b.shape[0], -1).astype(np.float64)
+    s = np.maximum(np.abs(b).max(axis=1, keepdims=True), 1e-30)
+    return float((np.abs(a - b) / s).max())
+
+
+@pytest.mark.parametrize("H,W,D,seed", [(40, 56, 8, 7), (96, 130, 16, 1), (61, 75, 5, 2)])
+@pytest.mark.parametrize("disp_type", [0, 1])
+def test_cost_tad_cg_bit_exact(ctx, H, W, D, seed, disp_type):
+    L, R, _ = make_pair(H, W, D, seed)
+    got = ctx.computeSimilarity(L, R, 0.4, 10, 50, disp_type, 0, D)
+    ref = orc.cost_tad_cg(L, R, 0, D, disp_type)
+    assert np.array_equal(got, ref)
+
+
+def test_cost_tad_cg_golden(ctx):
+    g = np.load("tests/golden/cv2_stages_40x56_d8.npz")
+    got = ctx.computeSimilarity(g["L"], g["R"], 0.4, 10, 50, 0, 0, 8)
+    assert np.array_equal(got, g["cost_tad_cg"])
+
+
+def test_cost_nonzero_min_disparity(ctx):
+    L, R, _ = make_pair(48, 80, 12, 4)
+    got = ctx.computeSimilarity(L, R, 0.4, 10, 50, 0, 3, 6)
+    ref = orc.cost_tad_cg(L, R, 3, 6, 0)
+    assert np.array_equal(got, ref)
+
+
+def test_cost_sad_box(ctx):
+    L, R, _ = make_pair(48, 70, 8, 5)
+    got = ctx.getCostSAD(L, R, 0, 7, 0, 8)
+    ref = orc.cost_sad_box(L, R, 0, 8, 7)
+    assert rel_err(got, ref) <= 1e-6
+
+
+def test_wta_bit_exact_with_ties_and_nan(ctx):
+    rng = np.random.default_rng(0)
+    vol = rng.integers(0, 4, (9, 33, 47)).astype(np.float32)     # many exact ties
+    vol[:, 0, 0] = np.nan                                         # never wins -> sentinel 0
+    vol[3, 1, 1] = np.nan
+    vol[:, 2, 2] = np.inf
+    got = ctx.wta(vol, 5)
+    ref = orc.wta(vol, 5)
+    assert np.array_equal(got, ref)
+    assert got[0, 0] == 0.0 and got[2, 2] == 0.0
+
+
+def test_guided_filter_stage_golden(ctx):
+    g = np.load("tests/golden/cv2_stages_40x56_d8.npz")
+    got = ctx.getGuidedFilter(g["L"], g["cost_tad_cg"][3], 5, 1e-4)
+    assert np.abs(got - g["gf_slice3_r5"]).max() <= REL_TOL
+
+
+@pytest.mark.parametrize("H,W,D,win,eps,seed", [(40, 56, 8, 5, 1e-4, 7), (96, 128, 16, 9, 1e-4, 3),
+                                                 (75, 101, 12, 9, 1e-6, 9), (64, 64, 7, 15, 1e-4, 11)])
+def test_guidedf2_left(ctx, H, W, D, win, eps, seed):
+    L, R, _ = make_pair(H, W, D, seed)
+    d, q = ctx.computeAdaptiveWeight_GuidedF_2(L, R, 0, eps, win, 0, D, agg=True, strict=True)
+    d_ref, q_ref = orc.asw_guidedf2(L, R, 0, eps, win, 0, D, agg=True)
+    assert rel_err(q, q_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+    # WTA is bit-exact given the same (GPU) volume
+    assert np.array_equal(d, orc.wta(q, 0))
+
+
+def test_guidedf2_golden(ctx):
+    g = np.load("tests/golden/cv2_stages_40x56_d8.npz")
+    d, q = ctx.computeAdaptiveWeight_GuidedF_2(g["L"], g["R"], 0, 1e-4, 5, 0, 8, agg=True, strict=True)
+    assert rel_err(q, g["guidedf2_q"]) <= REL_TOL
+    assert (d == g["guidedf2_disp"]).mean() >= AGREE
+
+
+def test_guidedf2_config2_full_size(ctx):
+    """config 2: 450x375, D=64, r=9, eps=1e-4, LR check + weighted-median refine"""
+    L, R, gt = make_pair(375, 450, 64, 2)
+    out, parts = ctx.guidedf2_lr_refine(L, R, 1e-4, 9, 0, 64, parts=True)
+    ref, rparts = orc.guidedf2_lr_refine(L, R, 1e-4, 9, 0, 64)
+    assert (parts["dl"] == rparts["dl"]).mean() >= AGREE
+    assert (parts["dr"] == rparts["dr"]).mean() >= AGREE
+    # integer-exact stage 4 given the same maps
+    v = orc.lr_check(parts["dl"], parts["dr"], 0.0)
+    assert np.array_equal(parts["valid"], v)
+    f = orc.fill_invalid(parts["dl"], v)
+    assert np.array_equal(out, orc.wmedian_refine(L, f, v, 9, 10, 10))
+    assert (out == ref).mean() >= 0.995     # refine propagates the <=0.1 % raw differences
+    assert np.mean(np.abs(out - gt) <= 1) > 0.9
+
+
+def test_stage4_pieces_bit_exact(ctx):
+    rng = np.random.default_rng(5)
+    L, R, _ = make_pair(60, 90, 16, 6)
+    dl = rng.integers(0, 16, (60, 90)).astype(np.float32)
+    dr = rng.integers(0, 16, (60, 90)).astype(np.float32)
+    v = ctx.lr_check(dl, dr, 1.0)
+    assert np.array_equal(v, orc.lr_check(dl, dr, 1.0))
+    v[7, :] = 0          # a row with no valid pixel
+    v[:, 0] = 0
+    f = ctx.fill_invalid(dl, v)
+    assert np.array_equal(f, orc.fill_invalid(dl, v))
+    for win in (5, 9):
+        out = ctx.wmedian_refine(L, f, v, win, 10, 10)
+        assert np.array_equal(out, orc.wmedian_refine(L, f, v, win, 10, 10))
+
+
+def test_guidedf_v1_six_channel(ctx):
+    L, R, _ = make_pair(48, 64, 8, 13)
+    d, q = ctx.computeAdaptiveWeight_GuidedF(L, R, 0, 1e-4, 7, 0, 8, agg=True, strict=True)
+    d_ref, q_ref = orc.asw_guidedf(L, R, 0, 1e-4, 7, 0, 8, agg=True)
+    assert rel_err(q, q_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+
+
+def test_error_behaviour(ctx):
+    L, R, _ = make_pair(32, 40, 4, 1)
+    # even window -> the reference returns an empty Mat (A.cpp:2458-2462)
+    assert ctx.computeAdaptiveWeight_GuidedF(L, R, 0, 1e-4, 8, 0, 4).size == 0
+    # size mismatch
+    assert ctx.computeAdaptiveWeight_GuidedF_2(L, R[:, :-1], 0, 1e-4, 9, 0, 4).size == 0
+    with pytest.raises(asw.AswError):
+        ctx.computeAdaptiveWeight_GuidedF_2(L, R, 1, 1e-4, 9, 0, 4, strict=True)   # RIGHT throws in the reference
+
+
+def test_batch_resident_matches_single(ctx):
+    pairs = [make_pair(64, 96, 16, 100 + i)[:2] for i in range(3)]
+    b = asw.Batch(ctx, 3, 64, 96)
+    for i, (L, R) in enumerate(pairs):
+        b.upload(i, L, R)
+    b.run_guidedf2_lr_refine(1e-4, 9, 0, 16)
+    for i, (L, R) in enumerate(pairs):
+        assert np.array_equal(b.download(i), ctx.guidedf2_lr_refine(L, R, 1e-4, 9, 0, 16))
+    ctx.sync()
+    b.close()
