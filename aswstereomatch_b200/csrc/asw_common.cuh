@@ -52,7 +52,7 @@ enum {
     WS_IMG_L = 0, WS_IMG_R, WS_FEAT_REF, WS_FEAT_TGT, WS_GUIDE_I, WS_GUIDE_MI, WS_GUIDE_DEN,
     WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_VOL0, WS_VOL1, WS_AB, WS_KEYS, WS_KEYS2, WS_DISP_L, WS_DISP_R,
     WS_MASK, WS_FILLED, WS_OUT, WS_SLICE_MM, WS_GRAY_L, WS_GRAY_R, WS_GEO_L, WS_GEO_R, WS_GRID_S, WS_GRID_C,
-    WS_TABLE0, WS_TABLE1, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3, WS_COUNT
+    WS_TABLE0, WS_TABLE1, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3, WS_CAPTURE, WS_COUNT
 };
 
 static inline asw_status asw_fail(asw_ctx* ctx, asw_status st, const char* fmt, const char* a = "", const char* b = "") {
@@ -157,8 +157,17 @@ __device__ __forceinline__ uint32_t orderable_u32(float f) {
     uint32_t b = __float_as_uint(f);
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
-// 64-bit WTA key: strict-< / lowest-d-wins / NaN-never-wins under unsigned min
-__device__ __forceinline__ unsigned long long wta_key(float cost, int d) {
-    return ((unsigned long long)orderable_u32(cost) << 32) | (unsigned)d;
+__device__ __forceinline__ unsigned long long orderable_u64(double f) {
+    if (f != f) return 0xFFFFFFFFFFFFFFFFull;
+    unsigned long long b = (unsigned long long)__double_as_longlong(f);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
 }
+// 64-bit WTA key: top 48 bits = orderable double cost (sign, exponent, 36 mantissa bits: float costs are
+// represented exactly), low 16 bits = disparity label.  Unsigned min over keys == the reference's WTA
+// (A.cpp:3032-3048): strict <, ascending d so the lowest d wins ties; NaN and +inf never beat DBL_MAX.
+__device__ __forceinline__ unsigned long long wta_key_d(double cost, int d) {
+    return (orderable_u64(cost) & 0xFFFFFFFFFFFF0000ull) | (unsigned long long)(d & 0xFFFF);
+}
+__device__ __forceinline__ unsigned long long wta_key(float cost, int d) { return wta_key_d((double)cost, d); }
 #define WTA_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull
+#define WTA_KEY_INF_TOP 0xFFF0000000000000ull   /* orderable(+inf) */

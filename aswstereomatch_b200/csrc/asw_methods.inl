@@ -233,7 +233,7 @@ static asw_status run_method_host(asw_ctx* ctx, const MethodArgs& m, const asw_u
     ASW_TRY(upload_pair(ctx, L, R, &dL, &dR));
     ASW_TRY(ws_get(ctx, WS_OUT, n, &out));
     size_t agg_count = n * (size_t)method_n_eval(m);
-    if (ctx->capture_host) ASW_TRY(ws_get(ctx, WS_VOL0, agg_count, &agg));
+    if (ctx->capture_host) ASW_TRY(ws_get(ctx, WS_CAPTURE, agg_count, &agg));
     asw_status st = dev_run_method(ctx, m, dL, dR, H, W, out, agg);
     if (st != ASW_OK) { ctx->capture_host = nullptr; return st; }
     ASW_TRY(download_f32(ctx, out, disp));

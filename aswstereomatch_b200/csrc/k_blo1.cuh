@@ -1,3 +1,214 @@
-// k_blo1.cuh -- placeholder
+// k_blo1.cuh -- O(1)-bilateral ASW, computeAdaptiveWeight_BLO1 (A.cpp:2505-2725), LEFT, minDisparity = 0.
+//
+// Reference: for every intensity level k (0, step, 2 step, ..., 255; step = int(256*sampleRateR)) and every d:
+//   M_d = |L-k| * |R_d-k| ; J_{k,d} = box(M_d * c_d) ; N_k = box(M_{D-1})  (LAST d only, A.cpp:2588) ;
+//   JB_{k,d} = J_{k,d} / N_k ; then per pixel with I = L(p): cost = JB_{I,d} if I is a level, otherwise
+//   (I-lo)*JB_{lo,d} + (hi-I)*JB_{hi,d} (weights swapped and un-normalised, A.cpp:2666-2667) ; WTA.
+// The reference materialises all 86 x D planes (40 GB at 1280x720x128).  Here one CTA owns a 64x32 tile
+// of one disparity, keeps the L / R_d / c_d tiles (+ window halo) in shared memory and loops only over the
+// levels that some pixel of the tile actually consumes (a pixel consumes <= 2 levels), running the box
+// filter as separable sliding sums in shared memory; nothing per-level ever reaches HBM.  N_k is
+// d-independent and is computed once per level with exact integer sums.
 #pragma once
-static asw_status dev_blo1(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_r, int win, int min_d, int num_d, float* disp_dev, float* agg_dev) { return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "not built yet%s%s"); }
+#include "k_cost.cuh"
+
+#define BLO_TW 64
+#define BLO_TH 32
+#define BLO_THREADS 256
+#define BLO_MAXLEV 257
+
+struct BloGeom {
+    int H, W, Wp, win, h, D;
+    int x0_base, x0_step;        // padded target crop column for slice di: x0_base + x0_step * di
+    int step, nl;                // level step, number of levels
+    int last255;                 // 1 if the last level (255) is not a multiple of step
+};
+__device__ __forceinline__ int blo_level_value(const BloGeom& g, int li) {
+    return (li == g.nl - 1 && g.last255) ? 255 : li * g.step;
+}
+
+// N_k = box(|L-k| * |R_{D-1}-k|), exact: integer window sums, (float)(sum * (1/win^2)) as cv::boxFilter.
+// grid: (tiles_x, tiles_y, nl)
+__global__ void __launch_bounds__(BLO_THREADS)
+k_blo1_norm(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, BloGeom g, float* __restrict__ Nk) {
+    extern __shared__ int sm_blo_i[];
+    const int win = g.win, h = g.h;
+    const int IW = BLO_TW + win - 1, IH = BLO_TH + win - 1, PP = IW | 1, HP = BLO_TW + 1;
+    int* M = sm_blo_i;                       // [IH][PP]
+    int* Hs = sm_blo_i + IH * PP;            // [IH][HP]
+    const int tid = threadIdx.x, x0t = blockIdx.x * BLO_TW, y0t = blockIdx.y * BLO_TH;
+    const int k = blo_level_value(g, blockIdx.z);
+    const int xoff = g.x0_base + g.x0_step * (g.D - 1);        // the last disparity's crop (A.cpp:2588)
+    for (int i = tid; i < IH * IW; i += BLO_THREADS) {
+        int r = i / IW, c = i - r * IW;
+        int sy = border_idx(y0t - h + r, g.H, 1), sx = border_idx(x0t - h + c, g.W, 1);
+        int l = lg[(size_t)sy * g.W + sx], rr = rpad[(size_t)sy * g.Wp + xoff + sx];
+        M[r * PP + c] = abs(l - k) * abs(rr - k);
+    }
+    __syncthreads();
+    for (int i = tid; i < IH * (BLO_TW / 8); i += BLO_THREADS) {
+        int seg = i / IH, r = i - seg * IH;
+        const int* src = M + r * PP + seg * 8;
+        int s = 0;
+        for (int j = 0; j < win; j++) s += src[j];
+        int* dst = Hs + r * HP + seg * 8;
+        dst[0] = s;
+#pragma unroll
+        for (int o = 1; o < 8; o++) { s += src[o - 1 + win] - src[o - 1]; dst[o] = s; }
+    }
+    __syncthreads();
+    {
+        const int col = tid % BLO_TW, rseg = tid / BLO_TW, x = x0t + col;
+        const int* src = Hs + (rseg * 8) * HP + col;
+        int s = 0;
+        for (int j = 0; j < win; j++) s += src[j * HP];
+        const double scale = 1.0 / ((double)win * win);
+#pragma unroll
+        for (int o = 0; o < 8; o++) {
+            if (o > 0) s += src[(o - 1 + win) * HP] - src[(o - 1) * HP];
+            int y = y0t + rseg * 8 + o;
+            if (x < g.W && y < g.H) Nk[(size_t)blockIdx.z * g.H * g.W + (size_t)y * g.W + x] = (float)((double)s * scale);
+        }
+    }
+}
+
+// grid: (tiles_x, tiles_y, D)
+__global__ void __launch_bounds__(BLO_THREADS)
+k_blo1_aggregate(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, const float* __restrict__ cost,
+                 const float* __restrict__ Nk, BloGeom g, int d_label0, unsigned long long* __restrict__ keys,
+                 float* __restrict__ agg) {
+    extern __shared__ float sm_blo_f[];
+    const int win = g.win, h = g.h;
+    const int IW = BLO_TW + win - 1, IH = BLO_TH + win - 1, PP = IW | 1, HP = BLO_TW + 1;
+    float* P = sm_blo_f;                                  // [IH][PP]   M * c for the current level
+    float* Hs = P + IH * PP;                              // [IH][HP]
+    float* Ct = Hs + IH * HP;                             // [IH][PP]   c_d tile
+    uint8_t* Lt = (uint8_t*)(Ct + IH * PP);               // [IH][PP]
+    uint8_t* Rt = Lt + IH * PP;                           // [IH][PP]
+    __shared__ uint32_t need[(BLO_MAXLEV + 31) / 32];
+    const int tid = threadIdx.x, x0t = blockIdx.x * BLO_TW, y0t = blockIdx.y * BLO_TH;
+    const int di = blockIdx.z;
+    const int xoff = g.x0_base + g.x0_step * di;
+    const size_t n = (size_t)g.H * g.W;
+    const float* cd = cost + (size_t)di * n;
+    if (tid < (BLO_MAXLEV + 31) / 32) need[tid] = 0;
+    for (int i = tid; i < IH * IW; i += BLO_THREADS) {
+        int r = i / IW, c = i - r * IW;
+        int sy = border_idx(y0t - h + r, g.H, 1), sx = border_idx(x0t - h + c, g.W, 1);   // boxFilter REFLECT_101
+        Lt[r * PP + c] = lg[(size_t)sy * g.W + sx];
+        Rt[r * PP + c] = rpad[(size_t)sy * g.Wp + xoff + sx];
+        Ct[r * PP + c] = cd[(size_t)sy * g.W + sx];
+    }
+    __syncthreads();
+    // the 8 pixels this thread owns: (col, rseg*8 + o); their consumed levels
+    const int col = tid % BLO_TW, rseg = tid / BLO_TW, x = x0t + col;
+    int I8[8], lo_li[8], hi_li[8];
+    float part_lo[8], part_hi[8];
+#pragma unroll
+    for (int o = 0; o < 8; o++) {
+        int y = y0t + rseg * 8 + o;
+        bool in = x < g.W && y < g.H;
+        int I = Lt[(h + rseg * 8 + o) * PP + h + col];
+        I8[o] = I;
+        part_lo[o] = 0.0f; part_hi[o] = 0.0f;
+        bool is_level = (I % g.step == 0) || I == 255;          // discretInten membership (A.cpp:2656)
+        if (is_level) {
+            lo_li[o] = (I == 255 && g.last255) ? g.nl - 1 : I / g.step;
+            hi_li[o] = -1;
+        } else {
+            int lo = I / g.step * g.step, hi = lo + g.step;      // A.cpp:2658-2663
+            lo_li[o] = I / g.step;
+            hi_li[o] = hi > 255 ? g.nl - 1 : lo_li[o] + 1;
+        }
+        if (!in) { lo_li[o] = -1; hi_li[o] = -1; }
+        if (lo_li[o] >= 0) atomicOr(&need[lo_li[o] >> 5], 1u << (lo_li[o] & 31));
+        if (hi_li[o] >= 0) atomicOr(&need[hi_li[o] >> 5], 1u << (hi_li[o] & 31));
+    }
+    __syncthreads();
+    const float inv = 1.0f / (float)(win * win);
+    for (int li = 0; li < g.nl; li++) {
+        if (!((need[li >> 5] >> (li & 31)) & 1u)) continue;      // block-uniform
+        const int k = blo_level_value(g, li);
+        for (int i = tid; i < IH * IW; i += BLO_THREADS) {
+            int r = i / IW, c = i - r * IW, a = r * PP + c;
+            float m = (float)(abs((int)Lt[a] - k) * abs((int)Rt[a] - k));     // A.cpp:2571-2580
+            P[a] = __fmul_rn(m, Ct[a]);                                        // A.cpp:2583
+        }
+        __syncthreads();
+        for (int i = tid; i < IH * (BLO_TW / 8); i += BLO_THREADS) {
+            int seg = i / IH, r = i - seg * IH;
+            const float* src = P + r * PP + seg * 8;
+            float s = 0.0f;
+            for (int j = 0; j < win; j++) s += src[j];
+            float* dst = Hs + r * HP + seg * 8;
+            dst[0] = s;
+#pragma unroll
+            for (int o = 1; o < 8; o++) { s += src[o - 1 + win] - src[o - 1]; dst[o] = s; }
+        }
+        __syncthreads();
+        {
+            const float* src = Hs + (rseg * 8) * HP + col;
+            float s = 0.0f;
+            for (int j = 0; j < win; j++) s += src[j * HP];
+#pragma unroll
+            for (int o = 0; o < 8; o++) {
+                if (o > 0) s += src[(o - 1 + win) * HP] - src[(o - 1) * HP];
+                if (lo_li[o] == li || hi_li[o] == li) {
+                    int y = y0t + rseg * 8 + o;
+                    float nk = __ldg(&Nk[(size_t)li * n + (size_t)y * g.W + x]);
+                    float jb = __fdiv_rn(s * inv, nk);                          // A.cpp:2594
+                    if (hi_li[o] < 0) part_lo[o] = jb;                          // I is a level: cost = JB_{I,d}
+                    else if (lo_li[o] == li) part_lo[o] = __fmul_rn((float)(I8[o] - k), jb);    // (I - lo) * JB_lo
+                    else part_hi[o] = __fmul_rn((float)(k - I8[o]), jb);        // (hi - I) * JB_hi
+                }
+            }
+        }
+        // the next level's P writes do not touch Hs; its h-sum pass starts only after the next barrier
+    }
+#pragma unroll
+    for (int o = 0; o < 8; o++) {
+        int y = y0t + rseg * 8 + o;
+        if (x < g.W && y < g.H) {
+            float c = hi_li[o] < 0 ? part_lo[o] : __fadd_rn(part_lo[o], part_hi[o]);   // A.cpp:2666-2667
+            size_t p = (size_t)y * g.W + x;
+            if (agg) agg[(size_t)di * n + p] = c;
+            atomicMin(&keys[p], wta_key(c, d_label0 + di));
+        }
+    }
+}
+
+static asw_status dev_blo1(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_r, int win,
+                           int min_d, int num_d, float* disp_dev, float* agg_dev) {
+    size_t n = (size_t)H * W;
+    BloGeom g;
+    g.step = (int)(256 * rate_r);                                  // A.cpp:2549
+    if (g.step <= 0) return asw_fail(ctx, ASW_ERR_BAD_ARG, "sampleRateR too small: the level step is 0%s%s");
+    g.nl = 0;
+    for (int i = 0; i < 256; i += g.step) g.nl++;                  // A.cpp:2550-2555
+    g.last255 = ((g.nl - 1) * g.step != 255) ? 1 : 0;              // A.cpp:2556-2559
+    if (g.last255) g.nl++;
+    float* cost;
+    uint8_t *gref, *gtgt;
+    ASW_TRY(ws_get(ctx, WS_VOL0, n * num_d, &cost));
+    if (agg_dev == cost) return asw_fail(ctx, ASW_ERR_BAD_ARG, "internal: capture buffer aliases the cost volume%s%s");
+    ASW_TRY(dev_cost_sad_box(ctx, dL, dR, H, W, ASW_DISPARITY_LEFT, win, min_d, num_d, cost, &gref, &gtgt));   // A.cpp:2531-2536
+    ViewGeom v = make_view(dL, dR, H, W, ASW_DISPARITY_LEFT, min_d, num_d);
+    g.H = H; g.W = W; g.Wp = v.Wp; g.win = win; g.h = win / 2; g.D = num_d;
+    g.x0_base = v.x0_base; g.x0_step = v.x0_step;
+    float* Nk;
+    ASW_TRY(ws_get(ctx, WS_TMP0, n * g.nl, &Nk));
+    int IW = BLO_TW + win - 1, IH = BLO_TH + win - 1, PP = IW | 1, HP = BLO_TW + 1;
+    size_t smem_n = ((size_t)IH * PP + (size_t)IH * HP) * sizeof(int);
+    size_t smem_a = ((size_t)IH * PP * 2 + (size_t)IH * HP) * sizeof(float) + (size_t)IH * PP * 2;
+    if (smem_a > 220 * 1024) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "BLO1 window too large for the tiled kernel%s%s");
+    cudaFuncSetAttribute(k_blo1_norm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_n);
+    cudaFuncSetAttribute(k_blo1_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
+    dim3 tiles(cdiv(W, BLO_TW), cdiv(H, BLO_TH));
+    LAUNCH(ctx, "blo1_norm", (k_blo1_norm<<<dim3(tiles.x, tiles.y, g.nl), BLO_THREADS, smem_n, ctx->stream>>>(gref, gtgt, g, Nk)));
+    unsigned long long* keys;
+    ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
+    ASW_TRY(init_keys(ctx, keys, n));
+    LAUNCH(ctx, "blo1_aggregate", (k_blo1_aggregate<<<dim3(tiles.x, tiles.y, num_d), BLO_THREADS, smem_a, ctx->stream>>>(
+                                      gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)));
+    return keys_to_disp(ctx, keys, n, disp_dev);
+}

@@ -93,8 +93,7 @@ __global__ void k_keys_to_disp(const unsigned long long* __restrict__ keys, size
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned long long k = keys[i];
-    uint32_t hi = (uint32_t)(k >> 32);
-    disp[i] = (hi >= 0xFF800000u) ? 0.0f : (float)(uint32_t)(k & 0xFFFFFFFFu);
+    disp[i] = (k >= WTA_KEY_INF_TOP) ? 0.0f : (float)(uint32_t)(k & 0xFFFFull);
 }
 __global__ void k_keys_min_merge(unsigned long long* __restrict__ a, const unsigned long long* __restrict__ b, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -1,3 +1,181 @@
-// k_grid.cuh -- placeholder
+// k_grid.cuh -- bilateral-grid ASW (createBilGrid nested-map overload A.cpp:1831-2185, quadrlinear_blGrid
+// A.cpp:2227-2251, computeAdaptiveWeight_bilateralGrid A.cpp:2253-2430).  LEFT only (the RIGHT branch reads
+// at(j, width) out of bounds, A.cpp:1923).
+//
+// Per candidate disparity (D+1 of them) a dense 4-D grid [x][y][z][w] of (double sum, int count):
+//   K11 k_grid_splat   : key = (cvRound(x/sS), cvRound(y/sS), cvRound(L/sR), cvRound(R(max(0,x-d))/sR)),
+//                        sum += |L-R| (integer valued -> order independent, exact), count += 1
+//   K12 k_grid_pass    : the four IN-PLACE, ascending-index (recursive) 5-tap passes w, z, y, x with the
+//                        reference's edge rules; counts truncated to int after every pass; fp64, same
+//                        expression order, no FMA contraction (the library is built with -fmad=false)
+//   K13 k_grid_slice   : corners at ceil(index) +- 1 (A.cpp:2295-2327), out-of-grid keys read 0, 4-linear
+//                        interpolation in the reference's order, cost = quad(sum)/quad(count) (NaN never wins)
+// Several candidates are processed per launch (blockIdx.z / grid batches) to fill the 148 SMs.
 #pragma once
-static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_s, double rate_r, int min_d, int num_d, float* disp_dev, float* agg_dev) { return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "not built yet%s%s"); }
+#include "k_cost.cuh"
+
+struct GridDims {
+    int nx, ny, nz, nw;          // last indices (inclusive): cells = (nx+1)(ny+1)(nz+1)(nw+1)
+    double rate_s, rate_r;
+    size_t cells;
+};
+__device__ __forceinline__ size_t gidx(const GridDims& g, int x, int y, int z, int w) {
+    return (((size_t)x * (g.ny + 1) + y) * (g.nz + 1) + z) * (g.nw + 1) + w;
+}
+// cvRound = round half to even (lrint in the default rounding mode); cvCeil = ceil
+__device__ __forceinline__ int cv_round(double v) { return __double2int_rn(v); }
+__device__ __forceinline__ int cv_ceil(double v) { return __double2int_ru(v); }
+
+// one candidate per blockIdx.z
+__global__ void k_grid_splat(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, int H, int W, int d_first,
+                             GridDims g, double* __restrict__ S, int* __restrict__ C) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    int d = d_first + blockIdx.z;
+    float lf = (float)lg[(size_t)y * W + x];
+    float rf = (float)rg[(size_t)y * W + max(0, x - d)];
+    int kx = cv_round((double)x / g.rate_s), ky = cv_round((double)y / g.rate_s);
+    int kz = cv_round((double)lf / g.rate_r), kw = cv_round((double)rf / g.rate_r);
+    size_t id = (size_t)blockIdx.z * g.cells + gidx(g, kx, ky, kz, kw);
+    atomicAdd(&S[id], fabs((double)(lf - rf)));        // A.cpp:1897-1912
+    atomicAdd(&C[id], 1);
+}
+
+// one recursive in-place 5-tap pass along a strided line of n+1 cells (A.cpp:1936-2183)
+__device__ __forceinline__ void grid_pass_line(double* __restrict__ s, int* __restrict__ c, size_t stride, int n) {
+    // rolling registers: m2, m1 = already-updated v[i-2], v[i-1]; c0 = v[i]; p1, p2 = original v[i+1], v[i+2]
+    double sm2 = 0, sm1 = 0, s0 = s[0], sp1 = s[stride], sp2 = s[2 * stride];
+    double cm2 = 0, cm1 = 0, c0 = (double)c[0], cp1 = (double)c[stride], cp2 = (double)c[2 * stride];
+    for (int i = 0; i <= n; i++) {
+        double ns, nc;
+        if (i == 0) {
+            ns = 0.6 * s0 + 0.3 * sp1 + 0.1 * sp2;
+            nc = 0.6 * c0 + 0.3 * cp1 + 0.1 * cp2;
+        } else if (i == 1) {
+            ns = 0.2 * sm1 + 0.5 * s0 + 0.2 * sp1 + 0.1 * sp2;
+            nc = 0.2 * cm1 + 0.5 * c0 + 0.2 * cp1 + 0.1 * cp2;
+        } else if (i == n - 1) {
+            ns = 0.1 * sm2 + 0.2 * sm1 + 0.5 * s0 + 0.2 * sp1;
+            nc = 0.1 * cm2 + 0.2 * cm1 + 0.5 * c0 + 0.2 * cp1;
+        } else if (i == n) {
+            ns = 0.1 * sm2 + 0.3 * sm1 + 0.6 * s0;
+            nc = 0.1 * cm2 + 0.3 * cm1 + 0.6 * c0;
+        } else {
+            ns = 0.0625 * sm2 + 0.25 * sm1 + 0.375 * s0 + 0.25 * sp1 + 0.0625 * sp2;
+            nc = 0.0625 * cm2 + 0.25 * cm1 + 0.375 * c0 + 0.25 * cp1 + 0.0625 * cp2;
+        }
+        int nci = (int)nc;                              // pair<double,double> -> pair<double,int>: truncation
+        s[(size_t)i * stride] = ns;
+        c[(size_t)i * stride] = nci;
+        sm2 = sm1; sm1 = ns; s0 = sp1; sp1 = sp2;
+        cm2 = cm1; cm1 = (double)nci; c0 = cp1; cp1 = cp2;
+        if (i + 3 <= n) { sp2 = s[(size_t)(i + 3) * stride]; cp2 = (double)c[(size_t)(i + 3) * stride]; }
+        else { sp2 = 0; cp2 = 0; }
+    }
+}
+
+// axis: 0 = w, 1 = z, 2 = y, 3 = x.  One thread per line; thread index ordered so that adjacent threads
+// touch adjacent memory where the axis allows it (y and x passes are fully coalesced).
+__global__ void k_grid_pass(double* __restrict__ S, int* __restrict__ C, GridDims g, int axis, int n_grids) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int X = g.nx + 1, Y = g.ny + 1, Z = g.nz + 1, Wd = g.nw + 1;
+    size_t lines;
+    if (axis == 0) lines = (size_t)X * Y * Z;
+    else if (axis == 1) lines = (size_t)X * Y * Wd;
+    else if (axis == 2) lines = (size_t)X * Z * Wd;
+    else lines = (size_t)Y * Z * Wd;
+    if (t >= lines * n_grids) return;
+    size_t gi = t / lines, l = t - gi * lines;
+    double* s = S + gi * g.cells;
+    int* c = C + gi * g.cells;
+    size_t base, stride; int n;
+    if (axis == 0) { base = l * Wd; stride = 1; n = g.nw; }                                   // (x,y,z) fixed
+    else if (axis == 1) { size_t xy = l / Wd; int w = (int)(l - xy * Wd); base = xy * Z * Wd + w; stride = Wd; n = g.nz; }
+    else if (axis == 2) { size_t x = l / ((size_t)Z * Wd); size_t zw = l - x * Z * Wd; base = x * Y * Z * Wd + zw; stride = (size_t)Z * Wd; n = g.ny; }
+    else { base = l; stride = (size_t)Y * Z * Wd; n = g.nx; }
+    grid_pass_line(s + base, c + base, stride, n);
+}
+
+__global__ void k_grid_slice(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, int H, int W, int d_first,
+                             int cand_first, GridDims g, const double* __restrict__ S, const int* __restrict__ C,
+                             unsigned long long* __restrict__ keys, float* __restrict__ agg) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    int d = d_first + blockIdx.z;
+    const double* s = S + (size_t)blockIdx.z * g.cells;
+    const int* c = C + (size_t)blockIdx.z * g.cells;
+    double x_ = (double)x / g.rate_s, y_ = (double)y / g.rate_s;                              // A.cpp:2290-2293
+    double cl = (double)lg[(size_t)y * W + x] / g.rate_r;
+    double cr = (double)rg[(size_t)y * W + max(0, x - d)] / g.rate_r;
+    int X = cv_ceil(x_), Y = cv_ceil(y_), Z = cv_ceil(cl), Q = cv_ceil(cr);
+    double fx = X - x_, fy = Y - y_, fz = Z - cl, fw = Q - cr;
+    double val[2];
+#pragma unroll
+    for (int t = 0; t < 2; t++) {
+        double v[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            int gx = X + ((k & 8) ? 1 : -1), gy = Y + ((k & 4) ? 1 : -1);
+            int gz = Z + ((k & 2) ? 1 : -1), gq = Q + ((k & 1) ? 1 : -1);
+            bool in = gx >= 0 && gx <= g.nx && gy >= 0 && gy <= g.ny && gz >= 0 && gz <= g.nz && gq >= 0 && gq <= g.nw;
+            size_t id = in ? gidx(g, gx, gy, gz, gq) : 0;
+            v[k] = in ? (t == 0 ? s[id] : (double)c[id]) : 0.0;         // map default-insert reads (0.0, 0)
+        }
+        double a[8], b[4], c2[2];
+#pragma unroll
+        for (int k = 0; k < 8; k++) a[k] = v[2 * k] * (1 - fw) + v[2 * k + 1] * fw;          // A.cpp:2233-2250
+#pragma unroll
+        for (int k = 0; k < 4; k++) b[k] = a[2 * k] * (1 - fz) + a[2 * k + 1] * fz;
+#pragma unroll
+        for (int k = 0; k < 2; k++) c2[k] = b[2 * k] * (1 - fy) + b[2 * k + 1] * fy;
+        val[t] = c2[0] * (1 - fx) + c2[1] * fx;
+    }
+    double E = val[0] / val[1];                                                                // A.cpp:2348
+    size_t p = (size_t)y * W + x;
+    if (agg) agg[(size_t)(cand_first + blockIdx.z) * H * W + p] = (float)E;
+    atomicMin(&keys[p], wta_key_d(E, d));
+}
+
+static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_s,
+                                     double rate_r, int min_d, int num_d, float* disp_dev, float* agg_dev) {
+    if (rate_s <= 0) rate_s = 16;                                  // A.cpp:1835-1843
+    if (rate_r <= 0) rate_r = 0.07;
+    size_t n = (size_t)H * W;
+    GridDims g;
+    g.rate_s = rate_s; g.rate_r = rate_r;
+    g.nz = (int)lrint(255.0 / rate_r); g.nw = g.nz;                // A.cpp:1866-1871 (cvRound)
+    g.nx = (int)lrint((W - 1) / rate_s); g.ny = (int)lrint((H - 1) / rate_s);
+    if (g.nx < 3 || g.ny < 3 || g.nz < 3 || g.nw < 3)
+        return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "bilateral grid needs at least 4 cells per axis%s%s");
+    g.cells = (size_t)(g.nx + 1) * (g.ny + 1) * (g.nz + 1) * (g.nw + 1);
+    uint8_t *gl, *gr;
+    ASW_TRY(ws_get(ctx, WS_GRAY_L, n, &gl));
+    ASW_TRY(ws_get(ctx, WS_GRAY_R, n, &gr));
+    LAUNCH(ctx, "bgr2gray", (k_bgr2gray_pad<<<dim3(cdiv(W, 256), H), 256, 0, ctx->stream>>>(dL, H, W, 0, 0, gl)));   // A.cpp:2270-2277
+    LAUNCH(ctx, "bgr2gray", (k_bgr2gray_pad<<<dim3(cdiv(W, 256), H), 256, 0, ctx->stream>>>(dR, H, W, 0, 0, gr)));
+    int n_cand = num_d + 1;                                         // A.cpp:2258, 2279
+    // batch candidates so that a launch has enough lines to fill the GPU, within a memory budget
+    size_t per = g.cells * 12;
+    int batch = (int)(((size_t)1536 << 20) / per);
+    if (batch < 1) batch = 1;
+    if (batch > n_cand) batch = n_cand;
+    if (batch > 32) batch = 32;
+    double* S; int* C;
+    ASW_TRY(ws_get(ctx, WS_GRID_S, g.cells * batch, &S));
+    ASW_TRY(ws_get(ctx, WS_GRID_C, g.cells * batch, &C));
+    unsigned long long* keys;
+    ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
+    ASW_TRY(init_keys(ctx, keys, n));
+    for (int c0 = 0; c0 < n_cand; c0 += batch) {
+        int nb = n_cand - c0 < batch ? n_cand - c0 : batch;
+        ASW_CUDA(ctx, cudaMemsetAsync(S, 0, g.cells * nb * sizeof(double), ctx->stream));      // A.cpp:1874-1892
+        ASW_CUDA(ctx, cudaMemsetAsync(C, 0, g.cells * nb * sizeof(int), ctx->stream));
+        LAUNCH(ctx, "grid_splat", (k_grid_splat<<<dim3(cdiv(W, 128), H, nb), 128, 0, ctx->stream>>>(gl, gr, H, W, min_d + c0, g, S, C)));
+        for (int axis = 0; axis < 4; axis++) {
+            size_t lines = g.cells / (size_t)((axis == 0 ? g.nw : axis == 1 ? g.nz : axis == 2 ? g.ny : g.nx) + 1) * nb;
+            LAUNCH(ctx, "grid_pass", (k_grid_pass<<<(unsigned)((lines + 127) / 128), 128, 0, ctx->stream>>>(S, C, g, axis, nb)));
+        }
+        LAUNCH(ctx, "grid_slice", (k_grid_slice<<<dim3(cdiv(W, 128), H, nb), 128, 0, ctx->stream>>>(gl, gr, H, W, min_d + c0, c0, g, S, C, keys, agg_dev)));
+    }
+    return keys_to_disp(ctx, keys, n, disp_dev);
+}

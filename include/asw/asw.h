@@ -157,7 +157,7 @@ asw_status asw_batch_download(asw_batch* b, int index, asw_f32_image* disparity)
 
 /* ---- disparity-range split of one pair (multi-GPU) ----
  * Each rank evaluates candidates [d_begin, d_end) and gets per-pixel 64-bit keys
- * (orderable(cost) << 32 | d) in a device buffer; a MIN all-reduce over ranks (NCCL via
+ * (48-bit orderable(cost) << 16 | d) in a device buffer; a MIN all-reduce over ranks (NCCL via
  * torch.distributed, or asw_keys_min_merge for peer buffers) then asw_keys_to_disparity
  * reproduces strict-< / lowest-d / NaN-never-wins exactly. */
 asw_status asw_split_local_keys(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,

@@ -1,0 +1,127 @@
+"""GPU parity of the four loop-heavy ASW variants (traditional, geodesic, bilateral grid, BLO(1)) and the
+dispatcher, through the C ABI, against the CPU oracle.  Same tolerances as test_gpu_guided.py."""
+import numpy as np
+import pytest
+
+import aswstereomatch_b200 as asw
+from aswstereomatch_b200.synth import make_pair
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4
+AGREE = 0.999
+
+
+def rel_err(a, b, mask=None):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    ok = np.isfinite(b) if mask is None else mask
+    assert np.array_equal(np.isfinite(a), np.isfinite(b))
+    if not ok.any():
+        return 0.0
+    s = np.maximum(np.abs(np.where(ok, b, 0)).reshape(b.shape[0], -1).max(axis=1), 1e-30)[:, None, None]
+    return float((np.abs(np.where(ok, a - b, 0)) / s).max())
+
+
+@pytest.mark.parametrize("H,W,D,win,disp_type,seed", [(40, 56, 6, 5, 0, 1), (48, 64, 8, 9, 0, 2), (36, 50, 5, 7, 1, 3),
+                                                       (64, 80, 16, 35, 0, 4)])
+def test_traditional(ctx, H, W, D, win, disp_type, seed):
+    L, R, _ = make_pair(H, W, D, seed)
+    d, e = ctx.computeAdaptiveWeight(L, R, 30, 20, disp_type, win, 0, D, agg=True, strict=True)
+    d_ref, e_ref = orc.asw_traditional(L, R, 30, 20, disp_type, win, 0, D, agg=True)
+    assert e.shape == (D + 1, H, W)                       # D+1 candidates (A.cpp:1021, 1074)
+    assert rel_err(e, e_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+    assert np.array_equal(d, orc.wta(e, 0)) or (d == orc.wta(e, 0)).mean() >= 0.9999
+
+
+def test_traditional_nonzero_min_disparity(ctx):
+    L, R, _ = make_pair(40, 64, 12, 8)
+    d = ctx.computeAdaptiveWeight(L, R, 30, 20, 0, 7, 3, 6, strict=True)
+    d_ref = orc.asw_traditional(L, R, 30, 20, 0, 7, 3, 6)
+    assert (d == d_ref).mean() >= AGREE
+    assert d.min() >= 3 and d.max() <= 9
+
+
+@pytest.mark.parametrize("H,W,win,seed", [(24, 30, 5, 1), (30, 41, 9, 2), (20, 26, 35, 3)])
+def test_geodesic_distance_bit_exact(ctx, H, W, win, seed):
+    L, _, _ = make_pair(H, W, 4, seed)
+    got = ctx.getGeodesicDist(L, win)
+    ref = orc.geodesic_dist(L, win)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("H,W,D,win,disp_type,seed", [(40, 56, 6, 5, 0, 1), (44, 60, 8, 9, 0, 2), (36, 50, 5, 7, 1, 3),
+                                                       (48, 64, 8, 35, 0, 4)])
+def test_geodesic(ctx, H, W, D, win, disp_type, seed):
+    L, R, _ = make_pair(H, W, D, seed)
+    d, e = ctx.computeAdaptiveWeight_geodesic(L, R, disp_type, win, 0, D, agg=True, strict=True)
+    d_ref, e_ref = orc.asw_geodesic(L, R, disp_type, win, 0, D, agg=True)
+    assert rel_err(e, e_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+
+
+@pytest.mark.parametrize("H,W,D,sS,sR,seed", [(48, 64, 8, 10, 10, 1), (120, 160, 8, 10, 10, 2), (60, 90, 6, 7, 12, 3)])
+def test_bilateral_grid(ctx, H, W, D, sS, sR, seed):
+    L, R, _ = make_pair(H, W, D, seed)
+    d, e = ctx.computeAdaptiveWeight_bilateralGrid(L, R, 0, sS, sR, 0, D, agg=True, strict=True)
+    d_ref, e_ref = orc.asw_bilateral_grid(L, R, 0, sS, sR, 0, D, agg=True)
+    # fp64 with the reference's expression order: NaN / inf pattern identical, finite costs equal to float rounding
+    assert np.array_equal(np.isnan(e), np.isnan(e_ref))
+    fin = np.isfinite(e_ref)
+    assert np.array_equal(np.isfinite(e), fin)
+    assert np.array_equal(e[fin], e_ref[fin])
+    assert np.array_equal(d, d_ref)
+
+
+@pytest.mark.parametrize("H,W,D,win,seed", [(40, 56, 8, 7, 7), (64, 96, 12, 9, 2), (70, 100, 8, 35, 3)])
+def test_blo1(ctx, H, W, D, win, seed):
+    L, R, _ = make_pair(H, W, D, seed)
+    d, q = ctx.computeAdaptiveWeight_BLO1(L, R, 0, 0.015, win, 0, D, agg=True, strict=True)
+    d_ref, q_ref = orc.asw_blo1(L, R, 0, 0.015, win, 0, D, agg=True)
+    assert rel_err(q, q_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+
+
+def test_blo1_golden(ctx):
+    g = np.load("tests/golden/cv2_stages_40x56_d8.npz")
+    d, q = ctx.computeAdaptiveWeight_BLO1(g["L"], g["R"], 0, 0.015, 7, 0, 8, agg=True, strict=True)
+    assert rel_err(q, g["blo1_q"]) <= REL_TOL
+    assert (d == g["blo1_disp"]).mean() >= AGREE
+
+
+def test_blo1_coarse_levels(ctx):
+    """a level step that does not divide 255 exercises the appended 255 level (A.cpp:2556-2559)"""
+    L, R, _ = make_pair(40, 56, 6, 5)
+    d, q = ctx.computeAdaptiveWeight_BLO1(L, R, 0, 0.05, 5, 0, 6, agg=True, strict=True)
+    d_ref, q_ref = orc.asw_blo1(L, R, 0, 0.05, 5, 0, 6, agg=True)
+    assert rel_err(q, q_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+
+
+@pytest.mark.parametrize("alg", [asw.ADAPTIVE_WEIGHT, asw.ADAPTIVE_WEIGHT_GEODESIC, asw.ADAPTIVE_WEIGHT_BILATERAL_GRID,
+                                 asw.ADAPTIVE_WEIGHT_BLO1, asw.ADAPTIVE_WEIGHT_GUIDED_FILTER,
+                                 asw.ADAPTIVE_WEIGHT_GUIDED_FILTER_2])
+def test_dispatcher_literals(ctx, alg):
+    """stereoMatching (A.cpp:46-88) with its hard-coded hyper-parameters"""
+    L, R, _ = make_pair(48, 64, 8, 21)
+    d = ctx.stereoMatching(L, R, asw.DISPARITY_LEFT, alg, 9, 0, 8, strict=True)
+    d_ref = orc.stereo_matching(L, R, 0, alg, 9, 0, 8)
+    assert (d == d_ref).mean() >= AGREE
+
+
+def test_dispatcher_out_of_scope(ctx):
+    L, R, _ = make_pair(32, 40, 4, 1)
+    for alg in (asw.BM, asw.SGBM, asw.ADAPTIVE_WEIGHT_8DIRECT, asw.ADAPTIVE_WEIGHT_GUIDED_FILTER_3, asw.NCC):
+        assert ctx.stereoMatching(L, R, 0, alg, 9, 0, 4).size == 0
+        with pytest.raises(asw.AswError):
+            ctx.stereoMatching(L, R, 0, alg, 9, 0, 4, strict=True)
+
+
+def test_method_error_behaviour(ctx):
+    L, R, _ = make_pair(32, 40, 4, 1)
+    assert ctx.computeAdaptiveWeight_geodesic(L, R, 0, 8, 0, 4).size == 0          # even window (A.cpp:1440-1443)
+    assert ctx.computeAdaptiveWeight_BLO1(L, R, 0, 0.015, 8, 0, 4).size == 0       # even window (A.cpp:2458-2462)
+    assert ctx.computeAdaptiveWeight_bilateralGrid(L, R, 1, 10, 10, 0, 4).size == 0  # RIGHT is out of bounds in the reference
+    assert ctx.computeAdaptiveWeight(L, R[:-1], 30, 20, 0, 7, 0, 4).size == 0      # size mismatch
