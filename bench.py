@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the dense-matching hot path (BASELINE.json metric: MDE/s, ms/frame).
+
+Workload (config.workload): BASELINE config 5 -- a batch of 1920x1080 synthetic stereo pairs, 256 disparities,
+guided-filter ASW (GuidedF_2, r = 9, eps = 1e-4) for the left AND right view + LR check + weighted-median
+refinement; pairs are sharded over ranks with no collective (weak scaling: every rank owns --pairs pairs).
+One "step" = one pass of that pipeline over the rank's batch.
+
+  value : whole-job MDE/s with the inputs already resident in HBM (CUDA events on the library's stream,
+          barrier + synchronize on both sides, max over ranks)
+  e2e   : the same metric through the C-ABI batch calls with HOST (pinned) buffers: per step every pair is
+          copied host->device, processed, and its refined map copied device->host inside the timed region
+  roofline / cpu_baseline : see DESIGN.md section "Measurement"
+
+`--impl reference` times the reference's CPU behaviour (the oracle port, all host threads) on a bounded
+sample of the same workload and prints the same line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, D = 1080, 1920, 256
+WIN, EPS = 9, 1e-4
+VIEWS = 2
+# algorithmic bytes per disparity evaluation (SURVEY 8d, 3-pass model = 52 B/DE), split over our two kernels:
+#   gf_ab (model passes A+B: write p 4 + read L,R 6 + read p 4 + read I 3 + write a,b 16) = 33 B/DE
+#   gf_q  (model pass  C : read a,b 16 + read I 3)                                         = 19 B/DE
+ALG_BYTES = {"gf_ab": 33.0, "gf_q": 19.0}
+WORKLOAD = ("cfg5: batch of 1920x1080 synthetic pairs, 256 disparities, GuidedF_2 (r=9, eps=1e-4) left+right view "
+            "+ LR check + weighted-median refine, pair-sharded")
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        v = float(json.load(open(p))["hbm_gbs"])
+        return v, "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(sample_hw=(1080, 1920), sample_d=128, threads=None):
+    """oracle (CPU port of the reference) on a bounded sample of the workload: one pair, both views + LR + refine"""
+    from aswstereomatch_b200.synth import make_pair
+    from oracle import orc
+    if threads:
+        orc.set_num_threads(threads)
+    h, w = sample_hw
+    L, R, _ = make_pair(h, w, sample_d, 1000)
+    t0 = time.perf_counter()
+    orc.guidedf2_lr_refine(L, R, EPS, WIN, 0, sample_d)
+    dt = time.perf_counter() - t0
+    mde = h * w * sample_d * VIEWS / 1e6
+    return {"value": mde / dt, "unit": "MDE/s", "cores": orc.num_threads(), "kind": "port",
+            "sample": f"1 pair {w}x{h}, D={sample_d}, r={WIN}, eps={EPS}, 2 views + LR + refine ({dt:.1f} s; "
+                      f"oracle/asw_oracle.c, OpenMP over slices/rows)"}, dt
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation (oracle port; the reference itself needs OpenCV
+    4.1.0 C++ and cannot be built here) on a bounded sample per step."""
+    if rank != 0:
+        return
+    from aswstereomatch_b200.synth import make_pair
+    from oracle import orc
+    orc.build()
+    h, w, d = 540, 960, 128
+    L, R, _ = make_pair(h, w, d, 1000)
+    for _ in range(args.warmup):
+        orc.guidedf2_lr_refine(L, R, EPS, WIN, 0, d)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.guidedf2_lr_refine(L, R, EPS, WIN, 0, d)
+    dt = time.perf_counter() - t0
+    mde_step = h * w * d * VIEWS / 1e6
+    val = mde_step * args.steps / dt
+    sample = f"per step: 1 pair {w}x{h}, D={d}, r={WIN}, eps={EPS}, 2 views + LR + refine (bounded sample of cfg5)"
+    line = {"impl": "reference", "metric": "MDE/s", "value": val, "unit": "MDE/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "MDE/s", "cores": orc.num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "MDE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--pairs", type=int, default=64, help="pairs per GPU per step (cfg5: 64)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import aswstereomatch_b200 as asw
+    from aswstereomatch_b200.synth import make_batch
+    ctx = asw.Context(local_rank)          # raises without the CUDA library / a device: no CPU fallback
+    P = args.pairs
+    Ls, Rs = make_batch(P, H, W, D, seed0=1000 + 10000 * rank, distinct=min(P, 4))
+    # pinned host buffers (inputs and results) for the end-to-end leg
+    hL = asw.pinned_empty((P, H, W, 3), np.uint8)
+    hR = asw.pinned_empty((P, H, W, 3), np.uint8)
+    hD = asw.pinned_empty((P, H, W), np.float32)
+    for i in range(P):
+        hL[i] = Ls[i]; hR[i] = Rs[i]
+    del Ls, Rs
+    batch = asw.Batch(ctx, P, H, W)
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step_resident():
+        batch.run_guidedf2_lr_refine(EPS, WIN, 0, D)
+
+    def step_e2e():
+        for i in range(P):
+            batch.upload(i, hL[i], hR[i])
+        batch.run_guidedf2_lr_refine(EPS, WIN, 0, D)
+        for i in range(P):
+            batch.download(i, hD[i], sync=False)
+
+    def timed(fn, steps):
+        barrier()
+        ctx.timer_start()
+        for _ in range(steps):
+            fn()
+        ms = ctx.timer_stop()          # records the stop event and synchronises the stream
+        barrier()
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    # inputs resident in HBM before the timed region of the `value` leg
+    for i in range(P):
+        batch.upload(i, hL[i], hR[i])
+    for _ in range(args.warmup):
+        step_resident()
+    ctx.sync()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    n0 = ctx.launch_count()
+    ms_res = timed(step_resident, args.steps)
+    launches = ctx.launch_count() - n0
+    clk = clocks.stop() if rank == 0 else None
+
+    # per-kernel launch durations, measured live with CUDA events on the launching stream (one extra step)
+    ctx.profile_enable(True); ctx.profile_reset()
+    step_resident(); ctx.sync()
+    prof = ctx.profile()
+    ctx.profile_enable(False)
+
+    # end-to-end leg (host buffers; H2D + D2H inside the timed region)
+    step_e2e(); ctx.sync()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # sanity: the last e2e result is a plausible disparity map (guards against timing a no-op)
+    ok = bool(np.isfinite(hD[0]).all() and hD[0].max() <= D - 1 and hD[0].std() > 0)
+
+    if rank == 0:
+        mde_step = H * W * D * VIEWS * P * world / 1e6
+        value = mde_step / (ms_res / args.steps) * 1e3
+        e2e = mde_step / (ms_e2e / args.steps) * 1e3
+        peak, peak_src = measured_peak()
+        dom = max(prof.items(), key=lambda kv: kv[1][0])
+        name, (tot_ms, n_l) = dom
+        de_per_launch = H * W * D * VIEWS * P / n_l            # each gf_ab / gf_q launch covers one slice chunk
+        alg = ALG_BYTES.get(name)
+        achieved = alg * de_per_launch / (tot_ms / n_l * 1e-3) / 1e9 if alg else None
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tr[name]["dram_bytes_per_de"] * de_per_launch
+        except Exception:
+            pass
+        total_prof = sum(v[0] for v in prof.values())
+        line = {
+            "metric": "MDE/s", "value": value, "unit": "MDE/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_res / args.steps, "ms_per_frame": ms_res / args.steps / P, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_per_gpu": P, "image": [W, H], "disparities": D, "views": VIEWS,
+                       "l2": "inputs larger than L2: every step streams 0.8 GB of images and >10 GB of per-slice "
+                             "intermediates per GPU through the 126 MB L2", "result_check": ok},
+            "clocks": clk,
+            "e2e": {"value": e2e, "unit": "MDE/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(hL.nbytes + hR.nbytes), "d2h_bytes_per_step": int(hD.nbytes)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                         "avg_launch_ms": tot_ms / n_l, "share_of_step": tot_ms / total_prof,
+                         "alg_bytes_per_de": alg, "de_per_launch": de_per_launch},
+            "kernels_ms_per_step": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]},
+        }
+        if not args.no_cpu_baseline:
+            try:
+                from oracle import orc
+                orc.build()
+                line["cpu_baseline"], _ = cpu_baseline()
+            except Exception as e:          # the baseline is reported, never required for the GPU numbers
+                line["cpu_baseline"] = {"value": None, "unit": "MDE/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    batch.close()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
