@@ -9,6 +9,7 @@ if the CUDA library or a device is missing.
 """
 import ctypes as C
 import os
+import weakref
 
 import numpy as np
 
@@ -175,9 +176,12 @@ class Context:
             raise AswError(st, "asw_create failed: no usable CUDA device (there is no CPU fallback)")
         self.h = h
         self.device = device
+        self._children = weakref.WeakSet()     # batches must be destroyed before their context
 
     def close(self):
         if getattr(self, "h", None):
+            for b in list(self._children):
+                b.close()
             self.lib.asw_destroy(self.h)
             self.h = None
 
@@ -414,10 +418,13 @@ class Batch:
         h = C.c_void_p()
         ctx._chk(ctx.lib.asw_batch_create(ctx.h, n_pairs, H, W, C.byref(h)))
         self.h = h
+        ctx._children.add(self)
 
     def close(self):
+        # finalisers of a garbage cycle run in arbitrary order: never touch a batch whose context is gone
         if getattr(self, "h", None):
-            self.ctx.lib.asw_batch_destroy(self.h)
+            if getattr(self.ctx, "h", None):
+                self.ctx.lib.asw_batch_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -312,14 +312,15 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
         g.H = H; g.W = W; g.Wp = v.Wp; g.k = win; g.a = win / 2; g.TW = GFF_IW + 1 - win; g.TH = GFF_IH + 1 - win;
         g.x0_step = v.x0_step;
         size_t smem = ((size_t)GFF_IH * GFF_PP + (size_t)GFF_IH * (g.TW + 1)) * sizeof(float4);
-        cudaFuncSetAttribute(k_gff_ab<DC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        size_t smem_ab = smem + (size_t)g.TW * g.TH * 3 * sizeof(float2);     // + (mean_I, 1/den) of the output tile
+        cudaFuncSetAttribute(k_gff_ab<DC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ab);
         cudaFuncSetAttribute(k_gff_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         int tx = cdiv(W, g.TW), ty = cdiv(H, g.TH);
         for (int c0 = d_lo; c0 < d_hi; c0 += chunk) {
             int cn = (d_hi - c0 < chunk) ? d_hi - c0 : chunk;
             g.x0_base = v.x0_base + v.x0_step * c0; g.D = cn;
-            LAUNCH(ctx, "gf_ab", (k_gff_ab<DC1><<<dim3(tx, ty, cdiv(cn, DC1)), GFF_THREADS, smem, ctx->stream>>>(
-                                     fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0)));
+            LAUNCH(ctx, "gf_ab", (k_gff_ab<DC1><<<dim3(tx, ty, cdiv(cn, DC1)), GFF_THREADS, smem_ab, ctx->stream>>>(
+                                     fref, ftgt, gp.Gi, gp.Gm, grd, g, make_tad_fast(tp), tp.c0, ab, slice_mm + 2 * c0)));
             // pass 2: as many slices per CTA as still leaves >= 4 CTAs per SM (fewer key atomics per pixel)
             int dc2 = cn;
             while (dc2 > 8 && (long long)tx * ty * cdiv(cn, dc2) < (long long)ctx->sm_count * 4) dc2 = (dc2 + 1) / 2;

@@ -48,6 +48,29 @@ __device__ __forceinline__ float tad_cost(const Feat& a, const Feat& b, const Ta
     return add_weighted_f32(cc, p.reg_r, gc, p.reg);                // A.cpp:484
 }
 
+// fp32-only variant used inside the fused guided-filter kernels.  Returns c' = cost - c0 directly:
+//   cost - c0 = regR*Cc + reg*(Gc - 255*T_G) = regR*Cc + reg*max(G - T_G, 0)        (A.cpp:474-484)
+// The colour part Cc is the same exact integer; G = (g0+g1+g2)/3 and the blend are evaluated in fp32 instead
+// of OpenCV's double (differences <= 1 float ulp of the ~5100-offset cost, i.e. ~1e-7 of the slice range --
+// three orders of magnitude inside the 1e-4 budget) and no float<->double conversions hit the XU pipe.
+struct TadFast { float thr_c, add_c, thr_g, reg_r, reg; };
+static inline TadFast make_tad_fast(const TadParams& p) {
+    TadFast f; f.thr_c = p.thr_c; f.add_c = p.add_c; f.thr_g = p.thr_g; f.reg_r = (float)p.reg_r; f.reg = (float)p.reg;
+    return f;
+}
+__device__ __forceinline__ float tad_cost_prime(uint32_t a_bgr, uint32_t a_g01, uint32_t a_g2, const Feat& b, const TadFast& p) {
+    uint32_t ad = __vabsdiffu4(a_bgr, b.bgr);
+    int c0 = ad & 0xFF, c1 = (ad >> 8) & 0xFF, c2 = (ad >> 16) & 0xFF;
+    int s = min(c0 + c1, 255) + c2;
+    int color = ((s + 1) * 43691) >> 17;
+    float cc = ((float)color > p.thr_c) ? fminf(rintf((float)color + p.add_c), 255.0f) : 0.0f;
+    int ga0 = (int16_t)(a_g01 & 0xFFFF), ga1 = (int16_t)(a_g01 >> 16), ga2 = (int16_t)(a_g2 & 0xFFFF);
+    int gb0 = (int16_t)(b.g01 & 0xFFFF), gb1 = (int16_t)(b.g01 >> 16), gb2 = (int16_t)(b.g2 & 0xFFFF);
+    int S = abs(ga0 - gb0) + abs(ga1 - gb1) + abs(ga2 - gb2);
+    float G = (float)S * 0.33333334f;
+    return fmaf(p.reg_r, cc, p.reg * fmaxf(G - p.thr_g, 0.0f));
+}
+
 // Raw TAD C+G volume [D][H][W]; x0_base + x0_step*di = column offset of the target crop
 // (LEFT: max_off - offset, RIGHT: offset).
 __global__ void k_cost_tad_volume(const Feat* __restrict__ ref, const Feat* __restrict__ tgt, int H, int W,

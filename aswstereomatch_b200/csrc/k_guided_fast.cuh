@@ -1,16 +1,22 @@
 // k_guided_fast.cuh -- tuned guided-filter kernels for windows k <= 13 (configs 2 and 5 use k = 9).
 //
-// Same algorithm and arithmetic as k_gf_ab / k_gf_q in k_guided.cuh (which remain the generic path for
-// larger windows); what changes is the mapping onto the SM:
+// Same algorithm as k_gf_ab / k_gf_q in k_guided.cuh (which remain the generic path for larger windows);
+// what changes is the mapping onto the SM:
 //   * the input tile is fixed at 36 rows x 64 columns (outputs TH x TW = (37-k) x (65-k)); 9 warps, warp w
 //     owns input rows 4w..4w+3, lane l owns input columns l and l+32 -> every thread owns the same 8 tile
 //     positions for every disparity, no div/mod or border arithmetic in the loop
-//   * everything that does not depend on the disparity (reference-side feature record, normalised guidance,
-//     reflected addresses) is loaded ONCE per CTA into registers and reused for all DC slices of the chunk;
-//     per disparity evaluation the only global load of pass 1 is one 16-byte target feature record
-//   * the slice min/max is reduced per CTA (one atomic pair per CTA and slice instead of one per warp)
+//   * everything that does not depend on the disparity is loaded ONCE per CTA and reused for all DC slices
+//     of the chunk: reference-side feature records + normalised guidance + reflected addresses in
+//     registers, (mean_I, 1/(var_I+eps)) of the output pixels in shared memory.  Per disparity evaluation the
+//     only global traffic of pass 1 is one 16-byte target feature record in and one 16-byte (a,b) record out
+//   * c' = cost - c0 is evaluated in fp32 (tad_cost_prime) -- no float<->double conversions on the XU pipe
+//   * box sums run on Blackwell's packed fp32x2 pipe (FADD2 / FFMA2 via __fadd2_rn / __ffma2_rn): a float4
+//     window update costs 4 instructions instead of 8
+//   * the slice min/max is reduced per CTA (one atomic pair per CTA and slice)
 //   * a = cov * (1/den) with 1/den precomputed per pixel instead of three IEEE divisions per evaluation
-//   * sliding k-sums on float4 in shared memory, odd pitches -> conflict-free LDS.128 / STS.128
+//   * odd shared-memory pitches -> conflict-free LDS.128 / STS.128 for both the row- and column-strided phases
+// Plane order inside the float4 records of pass 1 is (I0 c', I1 c', I2 c', c') so that channel pairs line up
+// with the packed instructions.
 #pragma once
 #include "k_guided.cuh"
 
@@ -25,6 +31,20 @@ struct GffGeom {
     int x0_base, x0_step, D;
 };
 
+// packed fp32x2 helpers (sm_100a FADD2 / FFMA2 / FMUL2)
+__device__ __forceinline__ float4 p4add(float4 a, float4 b) {
+    float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y));
+    float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+// s - old + nw
+__device__ __forceinline__ float4 p4slide(float4 s, float4 old, float4 nw) {
+    const float2 m1 = make_float2(-1.0f, -1.0f);
+    float2 lo = __fadd2_rn(__ffma2_rn(make_float2(old.x, old.y), m1, make_float2(s.x, s.y)), make_float2(nw.x, nw.y));
+    float2 hi = __fadd2_rn(__ffma2_rn(make_float2(old.z, old.w), m1, make_float2(s.z, s.w)), make_float2(nw.z, nw.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
 __device__ __forceinline__ void gff_hsum(const float4* __restrict__ P, float4* __restrict__ Hs, int tid, int k, int TW, int HP) {
     // item = (row r, run of 8 outputs); consecutive threads -> consecutive rows (odd pitches: no bank conflicts)
     const int nrun = (TW + 7) >> 3;
@@ -34,12 +54,12 @@ __device__ __forceinline__ void gff_hsum(const float4* __restrict__ P, float4* _
         float4* dst = Hs + r * HP + run * 8;
         int len = min(8, TW - run * 8);
         float4 s = src[0];
-        for (int j = 1; j < k; j++) s = f4add(s, src[j]);
+        for (int j = 1; j < k; j++) s = p4add(s, src[j]);
         dst[0] = s;
 #pragma unroll
         for (int o = 1; o < 8; o++) {
             if (o < len) {
-                s = f4add(f4sub(s, src[o - 1]), src[o - 1 + k]);
+                s = p4slide(s, src[o - 1], src[o - 1 + k]);
                 dst[o] = s;
             }
         }
@@ -50,20 +70,31 @@ __device__ __forceinline__ void gff_hsum(const float4* __restrict__ P, float4* _
 template <int DC>
 __global__ void __launch_bounds__(GFF_THREADS, 2)
 k_gff_ab(const Feat* __restrict__ ref, const Feat* __restrict__ tgt, const float4* __restrict__ Gi,
-         const float4* __restrict__ Gm, const float4* __restrict__ Grd /* 1/den */, GffGeom g, TadParams tp,
+         const float4* __restrict__ Gm, const float4* __restrict__ Grd /* 1/den */, GffGeom g, TadFast tp, float c0,
          float4* __restrict__ ab, uint32_t* __restrict__ slice_mm) {
     extern __shared__ float4 sm_gff[];
+    const int k = g.k, TW = g.TW, TH = g.TH, HP = TW + 1;
     float4* P = sm_gff;                                  // [36][65]
     float4* Hs = sm_gff + GFF_IH * GFF_PP;               // [36][TW+1]
+    float2* GM = (float2*)(Hs + GFF_IH * HP);            // [TH*TW][3] float2: (m0,m1) (m2,rd0) (rd1,rd2)
     __shared__ float red_min[9], red_max[9];
     __shared__ int rowidx[GFF_IH], colidx[GFF_IW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k = g.k, TW = g.TW, TH = g.TH, HP = TW + 1;
     const int x0t = blockIdx.x * TW, y0t = blockIdx.y * TH;
     if (tid < GFF_IH) rowidx[tid] = border_idx(y0t - g.a + tid, g.H, 1);
     else if (tid < GFF_IH + GFF_IW) colidx[tid - GFF_IH] = border_idx(x0t - g.a + tid - GFF_IH, g.W, 1);
+    // guidance moments of the output pixels -> shared memory (disparity independent)
+    for (int i = tid; i < TH * TW; i += GFF_THREADS) {
+        int r = i / TW, c = i - r * TW;
+        int y = min(y0t + r, g.H - 1), x = min(x0t + c, g.W - 1);
+        float4 m = __ldg(&Gm[(size_t)y * g.W + x]);
+        float4 rd = __ldg(&Grd[(size_t)y * g.W + x]);
+        GM[i * 3 + 0] = make_float2(m.x, m.y);
+        GM[i * 3 + 1] = make_float2(m.z, rd.x);
+        GM[i * 3 + 2] = make_float2(rd.y, rd.z);
+    }
     __syncthreads();
-    // ---- disparity-independent prologue: 8 owned positions ----
+    // ---- disparity-independent prologue: 8 owned input positions ----
     uint32_t f_bgr[8], f_g01[8], f_g2[8];
     float I0[8], I1[8], I2[8];
     int toff[8];
@@ -81,28 +112,32 @@ k_gff_ab(const Feat* __restrict__ ref, const Feat* __restrict__ tgt, const float
     const int col = tid % TW, rrun = tid / TW;
     const int nrr = (TH + 7) >> 3;
     const bool c_active = rrun < nrr;
-    const int c_len = c_active ? min(8, TH - rrun * 8) : 0;
     const int x = x0t + col;
+    int c_len = c_active ? min(8, TH - rrun * 8) : 0;
+    c_len = min(c_len, g.H - (y0t + rrun * 8));          // rows below the image are not written
+    if (x >= g.W) c_len = 0;
+    const int pix0 = (y0t + rrun * 8) * g.W + x;
     const float inv = 1.0f / (float)(k * k);
     const int d_begin = blockIdx.z * DC;
+    const size_t n = (size_t)g.H * g.W;
 
     for (int dd = 0; dd < DC; dd++) {
         const int di = d_begin + dd;
         if (di >= g.D) break;
         const int xoff = g.x0_base + g.x0_step * di;
-        // ---- phase A ----
+        // ---- phase A: c' and its products with the guidance, pre-scaled by 1/k^2 ----
         float cmin = 3.0e38f, cmax = -3.0e38f;
         Feat fb[8];
 #pragma unroll
         for (int e = 0; e < 8; e++) fb[e] = tgt[toff[e] + xoff];
 #pragma unroll
         for (int e = 0; e < 8; e++) {
-            Feat fa; fa.bgr = f_bgr[e]; fa.g01 = f_g01[e]; fa.g2 = f_g2[e]; fa.pad = 0;
-            float cst = tad_cost(fa, fb[e], tp);
-            cmin = fminf(cmin, cst); cmax = fmaxf(cmax, cst);
-            float cp = __fsub_rn(cst, tp.c0);
+            float cp = tad_cost_prime(f_bgr[e], f_g01[e], f_g2[e], fb[e], tp);     // c' = cost - c0
+            cmin = fminf(cmin, cp); cmax = fmaxf(cmax, cp);
+            float cs = cp * inv;
+            float2 p01 = __fmul2_rn(make_float2(I0[e], I1[e]), make_float2(cs, cs));
             int r = warp * 4 + (e >> 1), c = lane + ((e & 1) << 5);
-            P[r * GFF_PP + c] = make_float4(cp, __fmul_rn(I0[e], cp), __fmul_rn(I1[e], cp), __fmul_rn(I2[e], cp));
+            P[r * GFF_PP + c] = make_float4(p01.x, p01.y, I2[e] * cs, cs);
         }
         for (int o = 16; o > 0; o >>= 1) {
             cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
@@ -114,33 +149,33 @@ k_gff_ab(const Feat* __restrict__ ref, const Feat* __restrict__ tgt, const float
             float mn = red_min[0], mx = red_max[0];
 #pragma unroll
             for (int w = 1; w < 9; w++) { mn = fminf(mn, red_min[w]); mx = fmaxf(mx, red_max[w]); }
-            atomicMin(&slice_mm[2 * di], orderable_u32(mn));
-            atomicMax(&slice_mm[2 * di + 1], orderable_u32(mx));
+            atomicMin(&slice_mm[2 * di], orderable_u32(__fadd_rn(c0, mn)));      // slice min / max of the raw cost
+            atomicMax(&slice_mm[2 * di + 1], orderable_u32(__fadd_rn(c0, mx)));
         }
-        // ---- phase B ----
+        // ---- phase B: horizontal window sums ----
         gff_hsum(P, Hs, tid, k, TW, HP);
         __syncthreads();
-        // ---- phase C ----
-        if (c_active) {
+        // ---- phase C: vertical window sums -> mean_p, corr_Ip -> a, b ----
+        if (c_len > 0) {
             const float4* src = Hs + (rrun * 8) * HP + col;
+            const float2* gm = GM + ((rrun * 8) * TW + col) * 3;
+            float4* out = ab + (size_t)di * n + pix0;
             float4 s = src[0];
-            for (int j = 1; j < k; j++) s = f4add(s, src[j * HP]);
+            for (int j = 1; j < k; j++) s = p4add(s, src[j * HP]);
 #pragma unroll
             for (int o = 0; o < 8; o++) {
                 if (o < c_len) {
-                    if (o > 0) s = f4add(f4sub(s, src[(o - 1) * HP]), src[(o - 1 + k) * HP]);
-                    int y = y0t + rrun * 8 + o;
-                    if (x < g.W && y < g.H) {
-                        size_t pix = (size_t)y * g.W + x;
-                        float4 m = __ldg(&Gm[pix]);
-                        float4 rd = __ldg(&Grd[pix]);
-                        float mP = s.x * inv;
-                        float a0 = __fmul_rn(__fsub_rn(s.y * inv, __fmul_rn(m.x, mP)), rd.x);   // A.cpp:2805-2846
-                        float a1 = __fmul_rn(__fsub_rn(s.z * inv, __fmul_rn(m.y, mP)), rd.y);
-                        float a2 = __fmul_rn(__fsub_rn(s.w * inv, __fmul_rn(m.z, mP)), rd.z);
-                        float dot = __fadd_rn(__fadd_rn(__fmul_rn(a0, m.x), __fmul_rn(a1, m.y)), __fmul_rn(a2, m.z));
-                        ab[(size_t)di * g.H * g.W + pix] = make_float4(a0, a1, a2, __fsub_rn(mP, dot));   // A.cpp:2847
-                    }
+                    if (o > 0) s = p4slide(s, src[(o - 1) * HP], src[(o - 1 + k) * HP]);
+                    float2 m01 = gm[o * TW * 3 + 0], m2r0 = gm[o * TW * 3 + 1], r12 = gm[o * TW * 3 + 2];
+                    float mP = s.w;                                                         // box(c')
+                    const float2 m1 = make_float2(-1.0f, -1.0f);
+                    // cov = corr_Ip - mean_I * mean_p ; a = cov / (var + eps)                (A.cpp:2805-2846)
+                    float2 cov01 = __ffma2_rn(__fmul2_rn(m01, make_float2(mP, mP)), m1, make_float2(s.x, s.y));
+                    float2 a01 = __fmul2_rn(cov01, make_float2(m2r0.y, r12.x));
+                    float a2 = __fmul_rn(__fsub_rn(s.z, __fmul_rn(m2r0.x, mP)), r12.y);
+                    float2 am = __fmul2_rn(a01, m01);
+                    float dot = __fadd_rn(__fadd_rn(am.x, am.y), __fmul_rn(a2, m2r0.x));
+                    __stcs(out + o * g.W, make_float4(a01.x, a01.y, a2, __fsub_rn(mP, dot)));  // A.cpp:2847
                 }
             }
         }
@@ -169,18 +204,20 @@ k_gff_q(const float4* __restrict__ ab, const float4* __restrict__ Gi, GffGeom g,
     for (int e = 0; e < 8; e++) off[e] = rowidx[warp * 4 + (e >> 1)] * g.W + colidx[lane + ((e & 1) << 5)];
     const int col = tid % TW, rrun = tid / TW;
     const int nrr = (TH + 7) >> 3;
-    const bool c_active = rrun < nrr;
-    const int c_len = c_active ? min(8, TH - rrun * 8) : 0;
     const int x = x0t + col;
+    int c_len = (rrun < nrr) ? min(8, TH - rrun * 8) : 0;
+    c_len = min(c_len, g.H - (y0t + rrun * 8));
+    if (x >= g.W) c_len = 0;
+    const int pix0 = (y0t + rrun * 8) * g.W + x;
     const float inv = 1.0f / (float)(k * k);
     const size_t n = (size_t)g.H * g.W;
     unsigned long long best[8];
-    float4 Ipix[8];
+    float4 Ipix[8];                                      // guidance of the owned output pixels, pre-scaled by 1/k^2
 #pragma unroll
     for (int o = 0; o < 8; o++) {
         best[o] = WTA_KEY_EMPTY;
-        int y = y0t + rrun * 8 + o;
-        Ipix[o] = (c_active && o < c_len && x < g.W && y < g.H) ? __ldg(&Gi[(size_t)y * g.W + x]) : make_float4(0, 0, 0, 0);
+        float4 I = (o < c_len) ? __ldg(&Gi[pix0 + o * g.W]) : make_float4(0, 0, 0, 0);
+        Ipix[o] = make_float4(I.x * inv, I.y * inv, I.z * inv, inv);
     }
     const int d_begin = blockIdx.z * dc;
     for (int dd = 0; dd < dc; dd++) {
@@ -189,40 +226,37 @@ k_gff_q(const float4* __restrict__ ab, const float4* __restrict__ Gi, GffGeom g,
         const float4* abd = ab + (size_t)di * n;
         float4 v[8];
 #pragma unroll
-        for (int e = 0; e < 8; e++) v[e] = abd[off[e]];
+        for (int e = 0; e < 8; e++) v[e] = __ldcs(&abd[off[e]]);
 #pragma unroll
         for (int e = 0; e < 8; e++) P[(warp * 4 + (e >> 1)) * GFF_PP + lane + ((e & 1) << 5)] = v[e];
+        // per-slice affine of cv::normalize (A.cpp:2775): q = sf * q' + (c0 * sf + hf)
         float sf, hf;
         minmax_scale_shift((double)from_orderable(slice_mm[2 * di]), (double)from_orderable(slice_mm[2 * di + 1]), &sf, &hf);
         float h2 = (float)fma((double)c0, (double)sf, (double)hf);
         __syncthreads();
         gff_hsum(P, Hs, tid, k, TW, HP);
         __syncthreads();
-        if (c_active) {
+        if (c_len > 0) {
             const float4* src = Hs + (rrun * 8) * HP + col;
             float4 s = src[0];
-            for (int j = 1; j < k; j++) s = f4add(s, src[j * HP]);
+            for (int j = 1; j < k; j++) s = p4add(s, src[j * HP]);
 #pragma unroll
             for (int o = 0; o < 8; o++) {
                 if (o < c_len) {
-                    if (o > 0) s = f4add(f4sub(s, src[(o - 1) * HP]), src[(o - 1 + k) * HP]);
+                    if (o > 0) s = p4slide(s, src[(o - 1) * HP], src[(o - 1 + k) * HP]);
                     float4 I = Ipix[o];
-                    float dot = __fadd_rn(__fadd_rn(__fmul_rn(s.x * inv, I.x), __fmul_rn(s.y * inv, I.y)), __fmul_rn(s.z * inv, I.z));
-                    float q = fmaf(__fadd_rn(dot, s.w * inv), sf, h2);                    // A.cpp:2852 + slice affine
-                    int y = y0t + rrun * 8 + o;
-                    if (agg && x < g.W && y < g.H) agg[(size_t)di * n + (size_t)y * g.W + x] = q;
+                    float2 t = __fmul2_rn(make_float2(s.x, s.y), make_float2(I.x, I.y));
+                    float dot = __fadd_rn(__fadd_rn(t.x, t.y), __fmul_rn(s.z, I.z));          // abar . I (A.cpp:2852)
+                    float q = fmaf(__fadd_rn(dot, s.w * I.w), sf, h2);                          // + bbar, slice affine
+                    if (agg) agg[(size_t)di * n + pix0 + o * g.W] = q;
                     best[o] = min(best[o], wta_key(q, d_first_label + di));
                 }
             }
         }
     }
-    if (c_active) {
 #pragma unroll
-        for (int o = 0; o < 8; o++) {
-            int y = y0t + rrun * 8 + o;
-            if (o < c_len && x < g.W && y < g.H) atomicMin(&keys[(size_t)y * g.W + x], best[o]);
-        }
-    }
+    for (int o = 0; o < 8; o++)
+        if (o < c_len) atomicMin(&keys[pix0 + o * g.W], best[o]);
 }
 
 __global__ void k_reciprocal4(const float4* __restrict__ in, size_t n, float4* __restrict__ out) {

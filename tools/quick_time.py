@@ -50,3 +50,5 @@ tot = sum(v[0] for v in ctx.profile().values())
 for k, (ms, n) in sorted(ctx.profile().items(), key=lambda kv: -kv[1][0]):
     print(f"  {k:20s} {ms:9.3f} ms  {n:5d} launches  {100 * ms / tot:5.1f}%")
 print("  total", tot)
+b.close()
+ctx.close()
