@@ -374,6 +374,19 @@ class Context:
         self._chk(self.lib.asw_keys_to_disparity(self.h, dk, C.byref(outs)))
         return out
 
+    def keys_device_merge(self, keys_a_host, dk_other):
+        """upload keys_a into a fresh device key buffer, MIN-merge the device buffer dk_other into it on the GPU
+        (asw_keys_min_merge, the peer-buffer variant of the exchange) and return the resulting disparity map"""
+        keys_a_host = np.ascontiguousarray(keys_a_host, dtype=np.uint64)
+        H, W = keys_a_host.shape
+        dk = C.c_void_p()
+        self._chk(self.lib.asw_keys_alloc(self.h, H, W, C.byref(dk)))
+        self._chk(self.lib.asw_keys_upload(self.h, keys_a_host.ctypes.data, H, W, dk))
+        self._chk(self.lib.asw_keys_min_merge(self.h, dk, dk_other, H, W))
+        out, outs = _f32_out(H, W)
+        self._chk(self.lib.asw_keys_to_disparity(self.h, dk, C.byref(outs)))
+        return out
+
     # ---- measurement ----
     def sync(self):
         self._chk(self.lib.asw_sync(self.h))

@@ -139,6 +139,25 @@ def test_error_behaviour(ctx):
         ctx.computeAdaptiveWeight_GuidedF_2(L, R, 1, 1e-4, 9, 0, 4, strict=True)   # RIGHT throws in the reference
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_disparity_split_equals_unsplit(ctx, world):
+    """ranks evaluate disjoint disparity ranges, a MIN over the 64-bit keys gives the unsplit map.
+    The ranks are emulated sequentially on one GPU; the exchange itself is covered by the gloo test."""
+    from aswstereomatch_b200 import sharding
+    L, R, _ = make_pair(72, 100, 21, 31)
+    full = ctx.stereoMatching(L, R, 0, asw.ADAPTIVE_WEIGHT_GUIDED_FILTER_2, 9, 0, 21, strict=True)
+    merged = None
+    last_dk = None
+    for r in range(world):
+        lo, hi = sharding.split_range(21, r, world)
+        keys, dk = ctx.split_local_keys(L, R, asw.ADAPTIVE_WEIGHT_GUIDED_FILTER_2, 0, 9, 0, 21, lo, hi)
+        if r < world - 1:
+            merged = keys if merged is None else np.minimum(merged, keys)
+        last_dk = dk
+    assert np.array_equal(ctx.keys_device_merge(merged, last_dk), full)          # device-side merge of the last rank
+    assert np.array_equal(ctx.keys_to_disparity(np.minimum(merged, keys)), full) # host-side merge
+
+
 def test_batch_resident_matches_single(ctx):
     pairs = [make_pair(64, 96, 16, 100 + i)[:2] for i in range(3)]
     b = asw.Batch(ctx, 3, 64, 96)

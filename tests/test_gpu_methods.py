@@ -125,3 +125,22 @@ def test_method_error_behaviour(ctx):
     assert ctx.computeAdaptiveWeight_BLO1(L, R, 0, 0.015, 8, 0, 4).size == 0       # even window (A.cpp:2458-2462)
     assert ctx.computeAdaptiveWeight_bilateralGrid(L, R, 1, 10, 10, 0, 4).size == 0  # RIGHT is out of bounds in the reference
     assert ctx.computeAdaptiveWeight(L, R[:-1], 30, 20, 0, 7, 0, 4).size == 0      # size mismatch
+
+
+@pytest.mark.parametrize("H,W,D,win,seed", [(32, 44, 6, 5, 1), (40, 56, 8, 9, 2)])
+def test_weighted_median_method(ctx, H, W, D, win, seed):
+    """computeAdaptiveWeight_WeightedMedian (A.cpp:3228-3383): medians are selected values of the cost volume"""
+    L, R, _ = make_pair(H, W, D, seed)
+    d, q = ctx.computeAdaptiveWeight_WeightedMedian(L, R, 0, win, 10, 10, 0, D, agg=True, strict=True)
+    d_ref, q_ref = orc.asw_weighted_median(L, R, 0, win, 10, 10, 0, D, agg=True)
+    assert (q == q_ref).mean() >= 0.999           # a selection: equal except where a crossing flips on a weight ulp
+    assert rel_err(q, q_ref) <= 0.05
+    assert (d == d_ref).mean() >= AGREE
+
+
+def test_weighted_median_dispatcher_and_limits(ctx):
+    L, R, _ = make_pair(32, 44, 6, 3)
+    d = ctx.stereoMatching(L, R, 0, asw.ADAPTIVE_WEIGHT_MEDIAN, 7, 0, 6, strict=True)
+    assert (d == orc.stereo_matching(L, R, 0, asw.ADAPTIVE_WEIGHT_MEDIAN, 7, 0, 6)).mean() >= AGREE
+    assert ctx.computeAdaptiveWeight_WeightedMedian(L, R, 0, 8, 10, 10, 0, 6).size == 0      # even window (A.cpp:3238-3241)
+    assert ctx.computeAdaptiveWeight_WeightedMedian(L, R, 1, 7, 10, 10, 0, 6).size == 0      # RIGHT: UB in the reference
