@@ -92,7 +92,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(sample_hw=(1080, 1920), sample_d=128, threads=None):
+def cpu_baseline(sample_hw=(1080, 1920), sample_d=256, threads=None):
     """oracle (CPU port of the reference) on a bounded sample of the workload: one pair, both views + LR + refine"""
     from aswstereomatch_b200.synth import make_pair
     from oracle import orc
