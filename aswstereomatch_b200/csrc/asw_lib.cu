@@ -292,8 +292,8 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
     ASW_TRY(ws_get(ctx, WS_SLICE_MM, (size_t)2 * num_d, &slice_mm));
     LAUNCH(ctx, "init_slice_mm", (k_init_slice_mm<<<cdiv(num_d, 128), 128, 0, ctx->stream>>>(slice_mm, num_d)));
     TadParams tp = make_tad_params(0.4, 10, 50);                                     // A.cpp:2990
-    if (win <= GFF_MAXK && !getenv("ASW_GF_GENERIC")) {
-        // tuned kernels (k_guided_fast.cuh): fixed 36x64 input tile, register-resident reference-side data
+    if ((win == 5 || win == 7 || win == 9) && !getenv("ASW_GF_GENERIC")) {
+        // tuned kernels (k_guided_fast.cuh): fixed 32x64 input tile, register-resident reference-side data
         const int DC1 = 8;
         float4* grd;
         ASW_TRY(ws_get(ctx, WS_GUIDE_RDEN, n, &grd));
@@ -309,24 +309,14 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
         float4* ab;
         ASW_TRY(ws_get(ctx, WS_AB, n * (size_t)chunk, &ab));
         GffGeom g;
-        g.H = H; g.W = W; g.Wp = v.Wp; g.k = win; g.a = win / 2; g.TW = GFF_IW + 1 - win; g.TH = GFF_IH + 1 - win;
-        g.x0_step = v.x0_step;
-        size_t smem = ((size_t)GFF_IH * GFF_PP + (size_t)GFF_IH * (g.TW + 1)) * sizeof(float4);
-        size_t smem_ab = smem + (size_t)g.TW * g.TH * 3 * sizeof(float2);     // + (mean_I, 1/den) of the output tile
-        cudaFuncSetAttribute(k_gff_ab<DC1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ab);
-        cudaFuncSetAttribute(k_gff_q, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int tx = cdiv(W, g.TW), ty = cdiv(H, g.TH);
+        g.H = H; g.W = W; g.Wp = v.Wp; g.a = win / 2; g.x0_step = v.x0_step; g.D = 0;
         for (int c0 = d_lo; c0 < d_hi; c0 += chunk) {
             int cn = (d_hi - c0 < chunk) ? d_hi - c0 : chunk;
-            g.x0_base = v.x0_base + v.x0_step * c0; g.D = cn;
-            LAUNCH(ctx, "gf_ab", (k_gff_ab<DC1><<<dim3(tx, ty, cdiv(cn, DC1)), GFF_THREADS, smem_ab, ctx->stream>>>(
-                                     fref, ftgt, gp.Gi, gp.Gm, grd, g, make_tad_fast(tp), tp.c0, ab, slice_mm + 2 * c0)));
-            // pass 2: as many slices per CTA as still leaves >= 4 CTAs per SM (fewer key atomics per pixel)
-            int dc2 = cn;
-            while (dc2 > 8 && (long long)tx * ty * cdiv(cn, dc2) < (long long)ctx->sm_count * 4) dc2 = (dc2 + 1) / 2;
-            LAUNCH(ctx, "gf_q", (k_gff_q<<<dim3(tx, ty, cdiv(cn, dc2)), GFF_THREADS, smem, ctx->stream>>>(
-                                    ab, gp.Gi, g, tp.c0, slice_mm + 2 * c0, min_d + c0, dc2, keys,
-                                    agg_dev ? agg_dev + (size_t)(c0 - d_lo) * n : nullptr)));
+            g.x0_base = v.x0_base + v.x0_step * c0;
+            float* agg_c = agg_dev ? agg_dev + (size_t)(c0 - d_lo) * n : nullptr;
+            if (win == 9) ASW_TRY(gff_launch<9>(ctx, fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0, cn, min_d + c0, keys, agg_c));
+            else if (win == 7) ASW_TRY(gff_launch<7>(ctx, fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0, cn, min_d + c0, keys, agg_c));
+            else ASW_TRY(gff_launch<5>(ctx, fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0, cn, min_d + c0, keys, agg_c));
         }
         return ASW_OK;
     }
