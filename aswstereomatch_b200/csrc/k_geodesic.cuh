@@ -133,6 +133,176 @@ k_geo_aggregate(const float* __restrict__ dref, const float* __restrict__ dtgt, 
     atomicMin(&keys[p], best);
 }
 
+// ------------------------------------------------------------------------------------------------
+// tiled aggregation: one CTA = one image row x GT_X pixels x 8*KC candidates.  Every thread owns 4 ADJACENT
+// pixels and KC candidates, so one LDS.128 feeds 4 taps.  Operands that are addressed at (x - d) are staged in
+// shared memory as 4 copies skewed by 0..3 elements: whatever (d, tap column) is, the 4 consecutive values a
+// thread needs start on a 16-byte boundary in one of the copies (the copy index is uniform across the warp).
+// Staged cells hold CLAMPED image columns, so max(0, x-d) / min(x+d, W-1) cost nothing; only the segment
+// whose window sample columns get clamped BEFORE the disparity shift (right image edge for LEFT, left edge
+// for RIGHT) takes the scalar BORDER path.  Per tap: VABSDIFF4.ACC, I2F, FMUL, FFMA, FADD + 2/4 LDS.128.
+// All terms are non-negative; accumulation is fp32 (relative error ~1e-6 over the 1225 taps, two orders of
+// magnitude inside the 1e-4 budget).  KC = 4 for full chunks of 32 candidates, smaller KC for the remainder
+// (D+1 candidates is never a multiple of 32) so that no candidate slot is wasted.
+// ------------------------------------------------------------------------------------------------
+#define GT_X 128
+#define GT_TC 12
+#define GT_THREADS 256
+
+template <bool BORDER, int KC>
+__global__ void __launch_bounds__(GT_THREADS, 2)
+k_geo_agg_tile(const float* __restrict__ dref, const float* __restrict__ dtgt, const uint32_t* __restrict__ pref,
+               const uint32_t* __restrict__ ptgt, GeoGeom g, int seg_first, int cand_first,
+               unsigned long long* __restrict__ keys, float* __restrict__ agg) {
+    extern __shared__ __align__(16) float sm_gt[];
+    constexpr int DC = 8 * KC;                                // candidates per CTA
+    constexpr int DRW = GT_X + DC + 4;                        // staged target-distance row (cells)
+    const int W = g.W, H = g.H, win = g.win, h = g.h, sign = g.sign;
+    const int CLW = (GT_X + 2 * h + 7) & ~3;                  // reference colour row
+    const int CRW = (GT_X + 2 * h + DC + 7) & ~3;             // target colour row
+    float* DLs = sm_gt;                                       // [GT_TC][GT_X]
+    float* DRs = DLs + GT_TC * GT_X;                          // [4][GT_TC][DRW]
+    uint32_t* CL = (uint32_t*)(DRs + 4 * GT_TC * DRW);        // [4][CLW]
+    uint32_t* CR = CL + 4 * CLW;                              // [4][CRW]
+    const int tid = threadIdx.x, pg = tid & 31, ds = tid >> 5;
+    const int y = blockIdx.y, xb = (seg_first + blockIdx.x) * GT_X;
+    const int c0 = cand_first + blockIdx.z * DC;
+    const int d_lo = g.d_first + c0, d_hi = d_lo + DC - 1;
+    const size_t n = (size_t)H * W;
+    const size_t rowoff = (size_t)y * W;
+    // candidate k of this thread: c0 + ds + 8k; sh = its shift inside the staged rows (0 .. DC-1)
+    int sh[KC];
+    const float* drp[KC];                                      // per-candidate base into the skewed DR copies
+    const uint32_t* crp[KC];                                   // unaligned start (copy 0) of the target colour quad
+#pragma unroll
+    for (int k = 0; k < KC; k++) {
+        int d = g.d_first + min(c0 + ds + 8 * k, g.n_cand - 1);
+        sh[k] = sign > 0 ? d_hi - d : d - d_lo;
+        drp[k] = DRs + (sh[k] & 3) * GT_TC * DRW + 4 * pg + (sh[k] & ~3);
+        crp[k] = CR + 4 * pg + sh[k];
+    }
+    const int oDR = sign > 0 ? xb - d_hi : xb + d_lo;         // image column of staged cell 0 (before clamping)
+    const int oCL = xb - h;
+    const int oCR = sign > 0 ? xb - h - d_hi : xb - h + d_lo;
+    float fn[KC * 4], fd[KC * 4];
+#pragma unroll
+    for (int a = 0; a < KC * 4; a++) { fn[a] = 0.0f; fd[a] = 0.0f; }
+    const int x0 = xb + 4 * pg;
+    const uint32_t* clp = CL + 4 * pg;
+
+    for (int j = 0; j < win; j++) {
+        const int ny = clampi(y - h + j, 0, H - 1);
+        __syncthreads();                                       // previous row's colour rows are dead
+        for (int e = tid; e < CLW; e += GT_THREADS) {
+            uint32_t v = pref[(size_t)ny * W + clampi(oCL + e, 0, W - 1)];
+#pragma unroll
+            for (int r = 0; r < 4; r++) if (e - r >= 0) CL[r * CLW + e - r] = v;
+        }
+        for (int e = tid; e < CRW; e += GT_THREADS) {
+            uint32_t v = ptgt[(size_t)ny * W + clampi(oCR + e, 0, W - 1)];
+#pragma unroll
+            for (int r = 0; r < 4; r++) if (e - r >= 0) CR[r * CRW + e - r] = v;
+        }
+        for (int i0 = 0; i0 < win; i0 += GT_TC) {
+            const int i1 = min(i0 + GT_TC, win);
+            __syncthreads();                                   // previous chunk consumed
+            for (int q = tid; q < (i1 - i0) * GT_X; q += GT_THREADS) {
+                int tt = q / GT_X, xx = q - tt * GT_X;
+                DLs[q] = dref[(size_t)(j * win + i0 + tt) * n + rowoff + min(xb + xx, W - 1)];
+            }
+            for (int q = tid; q < (i1 - i0) * DRW; q += GT_THREADS) {
+                int tt = q / DRW, e = q - tt * DRW;
+                float v = dtgt[(size_t)(j * win + i0 + tt) * n + rowoff + clampi(oDR + e, 0, W - 1)];
+#pragma unroll
+                for (int r = 0; r < 4; r++) if (e - r >= 0) DRs[(r * GT_TC + tt) * DRW + e - r] = v;
+            }
+            __syncthreads();
+            for (int i = i0; i < i1; i++) {
+                const int tt = i - i0;
+                const float4 dl = *(const float4*)(DLs + tt * GT_X + 4 * pg);
+                uint32_t cl[4];
+                if (!BORDER) {
+                    // copy r = i & 3 at aligned index i - r: address = clp + i + r * (CLW - 1)
+                    const uint4 c4 = *(const uint4*)(clp + i + (i & 3) * (CLW - 1));
+                    cl[0] = c4.x; cl[1] = c4.y; cl[2] = c4.z; cl[3] = c4.w;
+                } else {
+#pragma unroll
+                    for (int p = 0; p < 4; p++) cl[p] = CL[clampi(clampi(x0 + p - h + i, 0, W - 1) - oCL, 0, CLW - 1)];
+                }
+#pragma unroll
+                for (int k = 0; k < KC; k++) {
+                    const float4 dr = *(const float4*)(drp[k] + tt * DRW);
+                    uint32_t cr[4];
+                    if (!BORDER) {
+                        const uint4 c4 = *(const uint4*)(crp[k] + i + ((sh[k] + i) & 3) * (CRW - 1));
+                        cr[0] = c4.x; cr[1] = c4.y; cr[2] = c4.z; cr[3] = c4.w;
+                    } else {
+                        const int d = sign > 0 ? d_hi - sh[k] : d_lo + sh[k];
+#pragma unroll
+                        for (int p = 0; p < 4; p++) {
+                            int nx = clampi(x0 + p - h + i, 0, W - 1);
+                            int col = sign > 0 ? max(0, nx - d) : min(nx + d, W - 1);
+                            cr[p] = CR[clampi(col - oCR, 0, CRW - 1)];   // cells past either end hold the clamped column
+                        }
+                    }
+                    const float dlv[4] = {dl.x, dl.y, dl.z, dl.w};
+                    const float drv[4] = {dr.x, dr.y, dr.z, dr.w};
+#pragma unroll
+                    for (int p = 0; p < 4; p++) {
+                        float t = __fmul_rn(dlv[p], drv[p]);                              // A.cpp:1488-1489
+                        float cd = (float)__vsadu4(cl[p], cr[p]);                         // getColorDist
+                        fn[k * 4 + p] = fmaf(t, cd, fn[k * 4 + p]);
+                        fd[k * 4 + p] = __fadd_rn(fd[k * 4 + p], t);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const int x = x0 + p;
+        if (x >= W) continue;
+        unsigned long long best = WTA_KEY_EMPTY;
+#pragma unroll
+        for (int k = 0; k < KC; k++) {
+            int c = c0 + ds + 8 * k;
+            if (c < g.n_cand) {
+                double E = (double)fn[k * 4 + p] / (double)fd[k * 4 + p];
+                if (agg) agg[(size_t)c * n + rowoff + x] = (float)E;
+                best = min(best, wta_key_d(E, g.d_first + c));
+            }
+        }
+        atomicMin(&keys[rowoff + x], best);
+    }
+}
+
+template <bool BORDER, int KC>
+static asw_status geo_tile_launch(asw_ctx* ctx, const float* dref, const float* dtgt, const uint32_t* cref, const uint32_t* ctgt,
+                                  GeoGeom g, int seg_first, int seg_count, int cand_first, int n_chunks,
+                                  unsigned long long* keys, float* agg) {
+    if (seg_count <= 0 || n_chunks <= 0) return ASW_OK;
+    const int h = g.h, DC = 8 * KC;
+    const int CLW = (GT_X + 2 * h + 7) & ~3, CRW = (GT_X + 2 * h + DC + 7) & ~3, DRW = GT_X + DC + 4;
+    size_t smem = ((size_t)GT_TC * GT_X + (size_t)4 * GT_TC * DRW + (size_t)4 * (CLW + CRW)) * sizeof(float);
+    cudaFuncSetAttribute(k_geo_agg_tile<BORDER, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    LAUNCH(ctx, BORDER ? "geo_aggregate_border" : "geo_aggregate",
+           (k_geo_agg_tile<BORDER, KC><<<dim3(seg_count, g.H, n_chunks), GT_THREADS, smem, ctx->stream>>>(
+               dref, dtgt, cref, ctgt, g, seg_first, cand_first, keys, agg)));
+    return ASW_OK;
+}
+// all candidates of a segment range: full chunks of 32 (KC = 4), then one remainder chunk with the smallest KC
+template <bool BORDER>
+static asw_status geo_tile_segments(asw_ctx* ctx, const float* dref, const float* dtgt, const uint32_t* cref, const uint32_t* ctgt,
+                                    GeoGeom g, int seg_first, int seg_count, unsigned long long* keys, float* agg) {
+    int full = g.n_cand / 32, rem = g.n_cand - full * 32;
+    ASW_TRY((geo_tile_launch<BORDER, 4>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, 0, full, keys, agg)));
+    if (rem > 24) ASW_TRY((geo_tile_launch<BORDER, 4>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
+    else if (rem > 16) ASW_TRY((geo_tile_launch<BORDER, 3>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
+    else if (rem > 8) ASW_TRY((geo_tile_launch<BORDER, 2>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
+    else if (rem > 0) ASW_TRY((geo_tile_launch<BORDER, 1>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
+    return ASW_OK;
+}
+
 __global__ void k_pack_bgrx(const uint8_t* __restrict__ img, size_t n, uint32_t* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -190,8 +360,23 @@ static asw_status dev_geodesic(asw_ctx* ctx, const uint8_t* dL, const uint8_t* d
     g.sign = disp_type == ASW_DISPARITY_LEFT ? 1 : -1;
     g.d_first = min_d; g.n_cand = num_d + 1;                              // A.cpp:1447, 1467
     bool left = disp_type == ASW_DISPARITY_LEFT;
-    dim3 grid(cdiv(W, 128), H, cdiv(g.n_cand, GEO_Q));
-    LAUNCH(ctx, "geo_aggregate", (k_geo_aggregate<<<grid, 128, 0, ctx->stream>>>(left ? distL : distR, left ? distR : distL,
-                                                                                 left ? pl : pr, left ? pr : pl, g, keys, agg_dev)));
+    const float* dref = left ? distL : distR; const float* dtgt = left ? distR : distL;
+    const uint32_t* cref = left ? pl : pr; const uint32_t* ctgt = left ? pr : pl;
+    if (getenv("ASW_GEO_GENERIC")) {
+        dim3 grid(cdiv(W, 128), H, cdiv(g.n_cand, GEO_Q));
+        LAUNCH(ctx, "geo_aggregate", (k_geo_aggregate<<<grid, 128, 0, ctx->stream>>>(dref, dtgt, cref, ctgt, g, keys, agg_dev)));
+        return keys_to_disp(ctx, keys, n, disp_dev);
+    }
+    const int h = g.h, nseg = cdiv(W, GT_X);
+    // segments whose window sample columns are clamped BEFORE the disparity shift take the scalar BORDER path:
+    // the right image edge for LEFT (x + h > W-1), the left edge for RIGHT (x - h < 0)
+    int int_first, int_count;
+    if (left) { int_first = 0; int_count = (W - 1 - h - (GT_X - 1) >= 0) ? (W - 1 - h - (GT_X - 1)) / GT_X + 1 : 0; }
+    else { int_first = h > 0 ? 1 : 0; int_count = nseg - int_first; }
+    if (int_count < 0) int_count = 0;
+    if (int_count > nseg - int_first) int_count = nseg - int_first;
+    ASW_TRY(geo_tile_segments<false>(ctx, dref, dtgt, cref, ctgt, g, int_first, int_count, keys, agg_dev));
+    ASW_TRY(geo_tile_segments<true>(ctx, dref, dtgt, cref, ctgt, g, 0, int_first, keys, agg_dev));
+    ASW_TRY(geo_tile_segments<true>(ctx, dref, dtgt, cref, ctgt, g, int_first + int_count, nseg - int_first - int_count, keys, agg_dev));
     return keys_to_disp(ctx, keys, n, disp_dev);
 }
