@@ -1,0 +1,335 @@
+// k_guided_stream.cuh -- GuidedF_2 (A.cpp:2766-2854, 2976-3050) as ONE streaming kernel per view:
+//     TAD C+G cost -> box -> (a, b) -> box -> q'      (k_gfs_filter, everything on chip)
+//     q' -> per-slice NORM_MINMAX affine -> WTA keys   (k_gfs_wta, 4 B per disparity evaluation)
+// What it replaces: the two tiled passes of k_guided_fast.cuh, which moved a 16-byte (a,b) record per disparity
+// evaluation through HBM, recomputed the cost on a 2-D halo (32x64 inputs for 24x56 outputs) and held both window
+// passes' operands in shared memory.
+//
+// Mapping.  A CTA owns a strip of 64 image columns, NS = 4 consecutive disparity slices and a band of rows, and
+// walks down the band K rows per step.  Both box levels are separable with the VERTICAL pass first:
+//   A/V1  thread = (slice, column): evaluates the cost of its column for the K new rows and keeps the vertical
+//         window sum of (I0 c, I1 c, I2 c, c) in registers -- the last K rows live in a register ring, so a window
+//         value is never re-read from anywhere -- and writes the K vertical sums to shared memory
+//   H1    thread = (slice, row, run of 8 columns): sliding horizontal window over the vertical sums -> mean_p,
+//         corr_Ip -> (a, b) of A.cpp:2805-2847 -> shared memory
+//   V2    thread = (slice, column): vertical window sum of (a, b) through a second register ring
+//   H2    thread = (slice, row, run of 8 columns): horizontal window -> q' = abar . I + bbar -> HBM (4 B)
+// The vertical halo disappears (a band is entered once: K + a + 1 warm-up rows per band instead of K-1 halo rows
+// per 24 output rows), the horizontal one is 2(K-1) of 64 columns, and nothing but q' is written.
+//
+// Borders.  Level 1 filters p with BORDER_REFLECT_101: virtual rows / columns are mapped to source pixels when the
+// cost is evaluated.  Level 2 filters the (a,b) IMAGE with BORDER_REFLECT_101, i.e. out-of-image (a,b) are copies of
+// in-image (a,b), not values derived from reflected costs: columns are handled by letting the V2 thread of an
+// out-of-image column read the mirrored column of the strip; rows by two closed-form steps on the register ring
+// (first K rows of the image -> output rows 0..a; last K rows -> output rows H-a..H-1).  Bands are aligned so that
+// the top band's ring holds rows 0..K-1 after its first block and the bottom band's last block ends at row H-1.
+//
+// Numerics: fp32 throughout (packed FADD2/FFMA2 for the window sums, FMA in the (a,b) epilogue); every running sum
+// is restarted from the ring once per K rows, so rounding does not accumulate down a column.
+#pragma once
+#include "k_guided_fast.cuh"
+
+#define GFS_IW 64
+#define GFS_NS 4
+#define GFS_THREADS 256
+
+// float feature record: gradients as exact-integer floats (|g| <= 4080), colour bytes last so that (g0, g1) sits in
+// an aligned register pair.  The target plane stores NEGATED gradients: |ga - gb| = |ga + (-gb)| is one FADD2 + FADD.
+struct __align__(16) FeatF { float g0, g1, g2; uint32_t bgr; };
+
+__global__ void k_feat_to_float(const Feat* __restrict__ in, size_t n, float sign, FeatF* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Feat f = in[i];
+    FeatF o;
+    o.g0 = sign * (float)(int)(int16_t)(f.g01 & 0xFFFF);
+    o.g1 = sign * (float)(int)(int16_t)(f.g01 >> 16);
+    o.g2 = sign * (float)(int)(int16_t)(f.g2 & 0xFFFF);
+    o.bgr = f.bgr;
+    out[i] = o;
+}
+
+// guidance records for the (a,b) epilogue: Gnm = {-mean_I0, -mean_I1, -mean_I2, rd2}, Grd = {rd0, rd1} with
+// rd_c = (1/K^2) / (var_c + eps): the level-2 box normalisation is folded into a.
+__global__ void k_gfs_pack_guide(const float4* __restrict__ Gm, const float4* __restrict__ Gd, size_t n, float inv,
+                                 float4* __restrict__ Gnm, float2* __restrict__ Grd) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 m = Gm[i], d = Gd[i];
+    Gnm[i] = make_float4(-m.x, -m.y, -m.z, __fdiv_rn(inv, d.z));
+    Grd[i] = make_float2(__fdiv_rn(inv, d.x), __fdiv_rn(inv, d.y));
+}
+
+struct GfsGeom {
+    int H, W, Wp, Wq;          // image, padded target width, q' row pitch (floats) = strips * QW
+    int x0_base, x0_step;      // target crop column of slice index di = x0_base + x0_step * di
+    int D, nbands;
+};
+// integer form of the colour truncation (A.cpp:461-465) for integral thresholds + fp32 gradient / blend constants
+struct TadStream { int thr_c, add_c; float thr_g, reg_r, reg; };
+
+// c' = cost - c0 = regR * Cc + reg * max(G - T_G, 0)   (same value as tad_cost_prime, k_cost.cuh)
+__device__ __forceinline__ float gfs_cost(const FeatF& a, const FeatF& nb, const TadStream& p) {
+    uint32_t ad = __vabsdiffu4(a.bgr, nb.bgr);                                   // A.cpp:455
+    int s01 = __dp4a(ad, 0x00000101u, 0u);
+    int s = __dp4a(ad, 0x00010000u, (uint32_t)min(s01, 255));                    // (c0 + c1) saturates, then + c2
+    int color = ((s + 1) * 43691) >> 17;                                         // round(s / 3)
+    int cci = (color > p.thr_c) ? min(color + p.add_c, 255) : 0;                 // inverted truncation
+    float2 d01 = __fadd2_rn(make_float2(a.g0, a.g1), make_float2(nb.g0, nb.g1));
+    float d2 = a.g2 + nb.g2;
+    float S = (fabsf(d01.x) + fabsf(d01.y)) + fabsf(d2);                         // exact integer
+    float G = S * 0.33333334f;
+    return fmaf(p.reg_r, (float)cci, p.reg * fmaxf(G - p.thr_g, 0.0f));
+}
+
+// ring step: insert `nw` at slot j (a constant after unrolling) of a K-entry register ring and return the sum of the
+// ring.  Slot 0 restarts the sum from the ring (K-1 adds), the others slide (s - old + new).
+template <int K>
+__device__ __forceinline__ float4 gfs_ring_step(float4 (&r)[K], float4& s, float4 nw, int j) {
+    if (j == 0) {
+        r[0] = nw;
+        float4 t = p4add(r[0], r[1]);
+#pragma unroll
+        for (int i = 2; i < K; i++) t = p4add(t, r[i]);
+        s = t;
+    } else {
+        s = p4slide(s, r[j], nw);
+        r[j] = nw;
+    }
+    return s;
+}
+
+// REFLECT_101 window sum centred at ring index c over a ring that holds image rows base .. base+K-1, where rows
+// below `lo` (= ring index of image row 0, or -inf) and above `hi` (ring index of row H-1) are reflected.
+template <int K>
+__device__ __forceinline__ float4 gfs_reflect_sum(const float4 (&r)[K], int c, bool at_top) {
+    constexpr int A = K / 2;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int v = -A; v <= A; v++) {
+        int i = c + v;
+        if (at_top) { if (i < 0) i = -i; }                    // ring index 0 = image row 0
+        else { if (i > K - 1) i = 2 * (K - 1) - i; }          // ring index K-1 = image row H-1
+        t = (v == -A) ? r[i] : p4add(t, r[i]);
+    }
+    return t;
+}
+
+template <int K>
+__global__ void __launch_bounds__(GFS_THREADS, 2)
+k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const float4* __restrict__ Gi,
+             const float4* __restrict__ Gnm, const float2* __restrict__ Grd, GfsGeom g, TadStream tp, float c0,
+             float* __restrict__ qv, uint32_t* __restrict__ slice_mm) {
+    constexpr int A = K / 2;
+    constexpr int AW = GFS_IW - (K - 1);                       // (a,b) columns per strip
+    constexpr int QW = GFS_IW - 2 * (K - 1);                   // q' columns per strip
+    constexpr int P1 = GFS_IW + 1, P2 = AW | 1;                // odd float4 pitches
+    constexpr int NRUN1 = (AW + GFF_RUN - 1) / GFF_RUN, NRUN2 = (QW + GFF_RUN - 1) / GFF_RUN;
+    constexpr int ROWS = GFS_NS * K;
+    static_assert(ROWS * NRUN1 <= GFS_THREADS && GFS_NS * AW <= GFS_THREADS, "phase does not fit one pass");
+    extern __shared__ float4 sm_gfs[];
+    float4* VS1 = sm_gfs;                                      // [NS*K][P1] vertical sums of (I c, c)
+    float4* AB = VS1 + ROWS * P1;                              // [NS*K][P2] (a0,a1,a2,b)
+    float4* VS2 = AB + ROWS * P2;                              // [NS*K][P2] vertical sums of (a,b)
+
+    const int tid = threadIdx.x;
+    const int H = g.H, W = g.W;
+    const int x0 = blockIdx.x * QW;                            // first q' column of the strip
+    const int d0 = blockIdx.y * GFS_NS;
+    // ---- band geometry ----
+    const int nb = g.nbands, band = blockIdx.z;
+    const int yb0 = (int)(((long long)H * band) / nb), yb1 = (int)(((long long)H * (band + 1)) / nb);
+    const bool top = band == 0, bottom = band == nb - 1;
+    int a0, U;                                                 // first (a,b) row of block 1, number of (a,b) blocks
+    if (bottom) { U = (H - yb0 + A + K - 1) / K; a0 = H - K * U; }
+    else { a0 = top ? 0 : yb0 - A; U = (yb1 + A - a0 + K - 1) / K; }
+    const int n_iter = U + 1 + (bottom ? 1 : 0);
+
+    // ---- A/V1 role: (slice, column) ----
+    const int sl1 = tid >> 6, c1 = tid & 63;
+    const int di1 = min(d0 + sl1, g.D - 1);
+    const int sx1 = border_idx(x0 - 2 * A + c1, W, 1);
+    const int toff1 = sx1 + g.x0_base + g.x0_step * di1;
+    float4 r1[K], s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < K; j++) r1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float cmin = 3.0e38f, cmax = -3.0e38f;
+    const float inv = 1.0f / (float)(K * K);
+    // ---- V2 role: (slice, (a,b) column); out-of-image columns read their mirror column ----
+    const int sl2 = tid / AW, c2 = tid - sl2 * AW;
+    const bool v2_on = tid < GFS_NS * AW;
+    const int csrc = min(max(border_idx(x0 - A + c2, W, 1) - (x0 - A), 0), AW - 1);
+    float4 r2[K], s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < K; j++) r2[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- H roles: (run, slice*K + row) with consecutive lanes on consecutive rows ----
+    const int hrun = tid / ROWS, hrow = tid - hrun * ROWS;    // hrow = slice * K + j
+    const int hsl = hrow / K, hj = hrow - hsl * K;
+    const bool h_slice_ok = d0 + hsl < g.D;
+
+    for (int u = 0; u < n_iter; u++) {
+        const int pbase = a0 - A - 1 + K * u;                  // first p row of this block
+        const int abase = a0 + K * (u - 1);                    // first (a,b) row produced / consumed in this iteration
+        // ================= A / V1 =================
+        if (u <= U) {
+            const bool interior = pbase >= 0 && pbase + K <= H;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const int sy = interior ? pbase + j : border_idx(pbase + j, H, 1);
+                const FeatF fa = ref[sy * W + sx1];
+                const float4 I = __ldg(&Gi[sy * W + sx1]);
+                const FeatF fb = tgt[sy * g.Wp + toff1];
+                const float cp = gfs_cost(fa, fb, tp);
+                cmin = fminf(cmin, cp); cmax = fmaxf(cmax, cp);
+                const float cs = cp * inv;
+                const float2 p01 = __fmul2_rn(make_float2(I.x, I.y), make_float2(cs, cs));
+                const float4 nw = make_float4(p01.x, p01.y, I.z * cs, cs);
+                const float4 s = gfs_ring_step<K>(r1, s1, nw, j);
+                VS1[(sl1 * K + j) * P1 + c1] = s;
+            }
+        }
+        __syncthreads();
+        // ================= H1: horizontal window + (a,b) epilogue =================
+        if (u >= 1 && u <= U && hrun < NRUN1) {
+            const int ya = min(max(abase + hj, 0), H - 1);
+            const int xa0 = x0 - A + hrun * GFF_RUN;
+            float4* dst = AB + hrow * P2 + hrun * GFF_RUN;
+            gff_run<K>(VS1 + hrow * P1 + hrun * GFF_RUN, 1, min(GFF_RUN, AW - hrun * GFF_RUN), [&](int o, float4 s) {
+                const int pix = ya * W + min(max(xa0 + o, 0), W - 1);
+                const float4 nm = __ldg(&Gnm[pix]);
+                const float2 rd = __ldg(&Grd[pix]);
+                const float mP = s.w;
+                // cov = corr_Ip - mean_I * mean_p ; a = cov / (var + eps), pre-scaled by 1/K^2      (A.cpp:2805-2846)
+                const float2 cov01 = __ffma2_rn(make_float2(nm.x, nm.y), make_float2(mP, mP), make_float2(s.x, s.y));
+                const float2 a01 = __fmul2_rn(cov01, rd);
+                const float a2 = fmaf(nm.z, mP, s.z) * nm.w;
+                // b = mean_p - a . mean_I                                                            (A.cpp:2847)
+                const float b = fmaf(a01.x, nm.x, fmaf(a01.y, nm.y, fmaf(a2, nm.z, mP * inv)));
+                dst[o] = make_float4(a01.x, a01.y, a2, b);
+            });
+        }
+        __syncthreads();
+        // ================= V2: vertical window over (a,b) =================
+        if (u >= 1 && v2_on) {
+            const float4* src = AB + (sl2 * K) * P2 + csrc;
+            float4* dst = VS2 + (sl2 * K) * P2 + c2;
+            if (u == U + 1) {
+                // bottom of the image: ring = rows H-K .. H-1; output rows H-a .. H-1 (block rows 0 .. a-1)
+#pragma unroll
+                for (int i = 0; i < A; i++) dst[i * P2] = gfs_reflect_sum<K>(r2, K - A + i, false);
+            } else if (top && u == 1) {
+                // top of the image: ring <- rows 0 .. K-1; output rows 0 .. a (block rows a .. K-1)
+#pragma unroll
+                for (int j = 0; j < K; j++) r2[j] = src[j * P2];
+#pragma unroll
+                for (int i = 0; i <= A; i++) dst[(A + i) * P2] = gfs_reflect_sum<K>(r2, i, true);
+            } else {
+#pragma unroll
+                for (int j = 0; j < K; j++) {
+                    const float4 nw = src[j * P2];
+                    const float4 s = gfs_ring_step<K>(r2, s2, nw, j);
+                    dst[j * P2] = s;
+                }
+            }
+        }
+        __syncthreads();
+        // ================= H2: horizontal window + q' =================
+        if (u >= 1 && hrun < NRUN2 && h_slice_ok) {
+            const int rq = abase - A + hj;
+            if (rq >= yb0 && rq < yb1) {      // also drops the unused block rows of the two closed-form steps
+                const int xq0 = x0 + hrun * GFF_RUN;
+                const int len = min(GFF_RUN, QW - hrun * GFF_RUN);
+                float q[GFF_RUN];
+                gff_run<K>(VS2 + hrow * P2 + hrun * GFF_RUN, 1, len, [&](int o, float4 s) {
+                    const float4 I = __ldg(&Gi[rq * W + min(xq0 + o, W - 1)]);
+                    q[o] = fmaf(s.x, I.x, fmaf(s.y, I.y, fmaf(s.z, I.z, s.w)));          // abar . I + bbar (A.cpp:2852)
+                });
+                float4* out = (float4*)(qv + ((size_t)(d0 + hsl) * H + rq) * g.Wq + xq0);
+                out[0] = make_float4(q[0], q[1], q[2], q[3]);
+                if (len > 4) out[1] = make_float4(q[4], q[5], q[6], q[7]);
+            }
+        }
+        // no barrier: the next A/V1 writes VS1 (last read in H1, two barriers back); AB is rewritten after the next
+        // barrier, VS2 after two more
+    }
+    // ---- slice min / max of the raw cost: one atomic pair per warp (a warp = 32 columns of one slice) ----
+    for (int o = 16; o > 0; o >>= 1) {
+        cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+        cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    }
+    if ((tid & 31) == 0 && d0 + sl1 < g.D) {
+        atomicMin(&slice_mm[2 * di1], orderable_u32(__fadd_rn(c0, cmin)));
+        atomicMax(&slice_mm[2 * di1 + 1], orderable_u32(__fadd_rn(c0, cmax)));
+    }
+}
+
+// per-slice affine of cv::normalize (A.cpp:2775) applied after the (linear) filter: q = sf * q' + (c0 * sf + hf)
+__global__ void k_gfs_affine(const uint32_t* __restrict__ slice_mm, int D, float c0, float2* __restrict__ aff) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= D) return;
+    float sf, hf;
+    minmax_scale_shift((double)from_orderable(slice_mm[2 * d]), (double)from_orderable(slice_mm[2 * d + 1]), &sf, &hf);
+    aff[d] = make_float2(sf, (float)fma((double)c0, (double)sf, (double)hf));
+}
+
+// q' volume [D][H][Wq] -> normalised costs -> WTA keys (strict <, ascending d, NaN / inf never win; A.cpp:3032-3048).
+// One thread = 4 adjacent pixels; the D loads of a thread are independent (unrolled by 8).
+__global__ void __launch_bounds__(128)
+k_gfs_wta(const float* __restrict__ qv, const float2* __restrict__ aff, int D, int H, int W, int Wq, int d_label0,
+          unsigned long long* __restrict__ keys, float* __restrict__ agg) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= W) return;
+    const size_t slice = (size_t)H * Wq;
+    const float* p = qv + (size_t)y * Wq + x4;
+    float best[4] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
+    int bd[4] = {0, 0, 0, 0};
+    const size_t n = (size_t)H * W;
+#pragma unroll 8
+    for (int d = 0; d < D; d++) {
+        const float4 v = __ldcs((const float4*)(p + (size_t)d * slice));
+        const float2 sh = __ldg(&aff[d]);
+        const float q[4] = {fmaf(v.x, sh.x, sh.y), fmaf(v.y, sh.x, sh.y), fmaf(v.z, sh.x, sh.y), fmaf(v.w, sh.x, sh.y)};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (q[k] < best[k]) { best[k] = q[k]; bd[k] = d; }
+            if (agg && x4 + k < W) agg[(size_t)d * n + (size_t)y * W + x4 + k] = q[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (x4 + k < W && best[k] < __int_as_float(0x7f800000)) {
+            unsigned long long* kp = keys + (size_t)y * W + x4 + k;
+            *kp = min(*kp, wta_key(best[k], d_label0 + bd[k]));
+        }
+    }
+}
+
+// smallest image height the streaming kernel takes: >= 2 bands of >= 2K rows each
+static inline bool gfs_supported(int H, int W, int win) {
+    return (win == 5 || win == 7 || win == 9) && H >= 4 * win && W >= 2;
+}
+
+template <int K>
+static asw_status gfs_launch(asw_ctx* ctx, const FeatF* fref, const FeatF* ftgt, const float4* Gi, const float4* Gnm,
+                             const float2* Grd, GfsGeom g, const TadParams& tp, float* qv, uint32_t* slice_mm, float2* aff,
+                             int cn, int d_label0, unsigned long long* keys, float* agg) {
+    constexpr int AW = GFS_IW - (K - 1), QW = GFS_IW - 2 * (K - 1), ROWS = GFS_NS * K;
+    const size_t smem = ((size_t)ROWS * (GFS_IW + 1) + 2 * (size_t)ROWS * (AW | 1)) * sizeof(float4);
+    cudaFuncSetAttribute(k_gfs_filter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int strips = cdiv(g.W, QW), groups = cdiv(cn, GFS_NS);
+    // bands: enough CTAs for ~4 resident sets, every band at least 2K rows, at least 2 (one top, one bottom)
+    int nb = cdiv(8 * ctx->sm_count, strips * groups);
+    const char* e = getenv("ASW_GFS_BANDS");
+    if (e && atoi(e) > 0) nb = atoi(e);
+    nb = std::max(2, std::min(nb, g.H / (2 * K)));
+    g.D = cn; g.nbands = nb;
+    TadStream ts;
+    ts.thr_c = (int)floorf(tp.thr_c); ts.add_c = (int)rintf(tp.add_c); ts.thr_g = tp.thr_g;
+    ts.reg_r = (float)tp.reg_r; ts.reg = (float)tp.reg;
+    LAUNCH(ctx, "gfs_filter", (k_gfs_filter<K><<<dim3(strips, groups, nb), GFS_THREADS, smem, ctx->stream>>>(
+                                  fref, ftgt, Gi, Gnm, Grd, g, ts, tp.c0, qv, slice_mm)));
+    LAUNCH(ctx, "gfs_affine", (k_gfs_affine<<<cdiv(cn, 128), 128, 0, ctx->stream>>>(slice_mm, cn, tp.c0, aff)));
+    LAUNCH(ctx, "gfs_wta", (k_gfs_wta<<<dim3(cdiv(cdiv(g.W, 4), 128), g.H), 128, 0, ctx->stream>>>(
+                               qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg)));
+    return ASW_OK;
+}
