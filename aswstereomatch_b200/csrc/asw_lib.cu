@@ -238,7 +238,7 @@ __global__ void k_init_slice_mm(uint32_t* mm, int D) {
 __global__ void k_init_mm_u8(int* mm) { mm[0] = 255; mm[1] = 0; }
 
 // guidance moments for a C-channel u8 guide: planes I (C), mean_I (C), den (C) + packed records for C == 3
-struct GuidePrep { float* I; float* mI; float* den; float4 *Gi, *Gm, *Gd; };
+struct GuidePrep { float* I; float* mI; float* den; float4 *Gi, *Gm, *Gd; const int* mm; };
 static asw_status prep_guide(asw_ctx* ctx, const uint8_t* guide, int H, int W, int C, int r, double eps, GuidePrep* gp) {
     size_t n = (size_t)H * W;
     float *planes, *boxed;
@@ -257,7 +257,7 @@ static asw_status prep_guide(asw_ctx* ctx, const uint8_t* guide, int H, int W, i
     LAUNCH(ctx, "guide_normalize", (k_guide_normalize<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(guide, n, C, mm, planes, gp->Gi)));
     ASW_TRY(launch_box_f32(ctx, planes, boxed, H, W, r, 2 * C, n));
     LAUNCH(ctx, "guide_finish", (k_guide_finish<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(boxed, n, C, (float)eps, gp->Gm, gp->Gd)));
-    gp->I = planes; gp->mI = boxed; gp->den = boxed + n * C;
+    gp->I = planes; gp->mI = boxed; gp->den = boxed + n * C; gp->mm = mm;
     return ASW_OK;
 }
 
@@ -295,7 +295,7 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
     TadParams tp = make_tad_params(0.4, 10, 50);                                     // A.cpp:2990
     if (gfs_supported(H, W, win) && !getenv("ASW_GF_TILED") && !getenv("ASW_GF_GENERIC")) {
         // streaming kernel (k_guided_stream.cuh): cost, both box levels and q' on chip; 4 B per evaluation to HBM
-        FeatF *rff, *tff; float4* gnm; float2 *grd2, *aff;
+        FeatF *rff, *tff; float4 *gnm, *grd2; float2* aff;
         ASW_TRY(ws_get(ctx, WS_FEATF_REF, n, &rff));
         ASW_TRY(ws_get(ctx, WS_FEATF_TGT, (size_t)H * v.Wp, &tff));
         ASW_TRY(ws_get(ctx, WS_GUIDE_NM, n, &gnm));
@@ -319,9 +319,9 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
             int cn = (d_hi - c0 < chunk) ? d_hi - c0 : chunk;
             g.x0_base = v.x0_base + v.x0_step * c0;
             float* agg_c = agg_dev ? agg_dev + (size_t)(c0 - d_lo) * n : nullptr;
-            if (win == 9) ASW_TRY(gfs_launch<9>(ctx, rff, tff, gp.Gi, gnm, grd2, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
-            else if (win == 7) ASW_TRY(gfs_launch<7>(ctx, rff, tff, gp.Gi, gnm, grd2, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
-            else ASW_TRY(gfs_launch<5>(ctx, rff, tff, gp.Gi, gnm, grd2, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
+            if (win == 9) ASW_TRY(gfs_launch<9>(ctx, rff, tff, gp.Gi, gnm, grd2, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
+            else if (win == 7) ASW_TRY(gfs_launch<7>(ctx, rff, tff, gp.Gi, gnm, grd2, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
+            else ASW_TRY(gfs_launch<5>(ctx, rff, tff, gp.Gi, gnm, grd2, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
         }
         return ASW_OK;
     }

@@ -49,15 +49,15 @@ __global__ void k_feat_to_float(const Feat* __restrict__ in, size_t n, float sig
     out[i] = o;
 }
 
-// guidance records for the (a,b) epilogue: Gnm = {-mean_I0, -mean_I1, -mean_I2, rd2}, Grd = {rd0, rd1} with
+// guidance records for the (a,b) epilogue: Gnm = {-mean_I0, -mean_I1, -mean_I2, rd2}, Grd = {rd0, rd1, -, -} with
 // rd_c = (1/K^2) / (var_c + eps): the level-2 box normalisation is folded into a.
 __global__ void k_gfs_pack_guide(const float4* __restrict__ Gm, const float4* __restrict__ Gd, size_t n, float inv,
-                                 float4* __restrict__ Gnm, float2* __restrict__ Grd) {
+                                 float4* __restrict__ Gnm, float4* __restrict__ Grd) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 m = Gm[i], d = Gd[i];
     Gnm[i] = make_float4(-m.x, -m.y, -m.z, __fdiv_rn(inv, d.z));
-    Grd[i] = make_float2(__fdiv_rn(inv, d.x), __fdiv_rn(inv, d.y));
+    Grd[i] = make_float4(__fdiv_rn(inv, d.x), __fdiv_rn(inv, d.y), 0.0f, 0.0f);
 }
 
 struct GfsGeom {
@@ -115,24 +115,78 @@ __device__ __forceinline__ float4 gfs_reflect_sum(const float4 (&r)[K], int c, b
     return t;
 }
 
-template <int K>
-__global__ void __launch_bounds__(GFS_THREADS, 2)
-k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const float4* __restrict__ Gi,
-             const float4* __restrict__ Gnm, const float2* __restrict__ Grd, GfsGeom g, TadStream tp, float c0,
-             float* __restrict__ qv, uint32_t* __restrict__ slice_mm) {
-    constexpr int A = K / 2;
-    constexpr int AW = GFS_IW - (K - 1);                       // (a,b) columns per strip
-    constexpr int QW = GFS_IW - 2 * (K - 1);                   // q' columns per strip
-    constexpr int P1 = GFS_IW + 1, P2 = AW | 1;                // odd float4 pitches
-    constexpr int NRUN1 = (AW + GFF_RUN - 1) / GFF_RUN, NRUN2 = (QW + GFF_RUN - 1) / GFF_RUN;
-    constexpr int ROWS = GFS_NS * K;
-    static_assert(ROWS * NRUN1 <= GFS_THREADS && GFS_NS * AW <= GFS_THREADS, "phase does not fit one pass");
-    extern __shared__ float4 sm_gfs[];
-    float4* VS1 = sm_gfs;                                      // [NS*K][P1] vertical sums of (I c, c)
-    float4* AB = VS1 + ROWS * P1;                              // [NS*K][P2] (a0,a1,a2,b)
-    float4* VS2 = AB + ROWS * P2;                              // [NS*K][P2] vertical sums of (a,b)
+// named barriers (id 0 is __syncthreads)
+__device__ __forceinline__ void gfs_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void gfs_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+// single REFLECT_101 fold (|overshoot| < len)
+__device__ __forceinline__ int gfs_reflect1(int p, int len) { return p < 0 ? -p : (p >= len ? 2 * len - 2 - p : p); }
+// mbarrier + TMA 1-D bulk copy (global -> shared, completion counted in bytes on the mbarrier)
+__device__ __forceinline__ uint32_t gfs_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gfs_mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gfs_smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gfs_mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gfs_smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void gfs_mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t done, spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(gfs_smem_u32(b)), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();      // a lost copy becomes an error, not a hung GPU
+    } while (!done);
+}
+__device__ __forceinline__ void gfs_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gfs_smem_u32(dst)), "l"(src), "r"(bytes), "r"(gfs_smem_u32(b)) : "memory");
+}
 
-    const int tid = threadIdx.x;
+#define GFS_BAR_FULL 1       // +buf : VS1[buf] written by the cost warps
+#define GFS_BAR_EMPTY 3      // +buf : VS1[buf] (and the VS2 aliased onto it) consumed by the filter warps
+#define GFS_BAR_FILTER 5     // among the filter warps
+#define GFS_BAR_COST 6       // among the cost warps
+#define GFS_TP 68            // staged target row pitch (64 + NS - 1, padded)
+
+template <int K>
+struct GfsLayout {
+    static constexpr int A = K / 2;
+    static constexpr int AW = GFS_IW - (K - 1);                // (a,b) columns per strip
+    static constexpr int QW = GFS_IW - 2 * (K - 1);            // q' columns per strip
+    static constexpr int P1 = GFS_IW + 1, P2 = AW | 1, PQ = QW | 1;   // odd float4 pitches
+    static constexpr int ROWS = GFS_NS * K;
+    // float4 offsets
+    static constexpr int oVS1 = 0;                             // [2][ROWS][P1]  vertical sums of (I c, c); VS2 aliases the consumed buffer
+    static constexpr int oAB = oVS1 + 2 * ROWS * P1;           // [ROWS][P2]     (a0,a1,a2,b)
+    static constexpr int oRef = oAB + ROWS * P2;               // [2][K][64]     staged reference features
+    static constexpr int oTgt = oRef + 2 * K * GFS_IW;         // [2][K][GFS_TP] staged target features (NS slices share them)
+    static constexpr int oGA = oTgt + 2 * K * GFS_TP;          // [2][K][P2]     {-mI0,-mI1,-mI2, rd2}
+    static constexpr int oGB = oGA + 2 * K * P2;               // [2][K][P2]     {rd0, rd1, -, -}
+    static constexpr int oIQ = oGB + 2 * K * P2;               // [2][K][PQ]     guidance at the q' pixels
+    static constexpr int oBar = oIQ + 2 * K * PQ;              // 4 mbarriers
+    static constexpr size_t bytes = (size_t)(oBar + 2) * sizeof(float4);
+};
+
+// Warp-specialised, TMA-fed: warps 0..7 (cost warps) run A/V1 and own the level-1 rings, warps 8..15 (filter
+// warps) run H1, V2, H2 and own the level-2 rings.  No thread issues a global load: the rows of the next block
+// (reference / target features for the cost warps; guidance moments and guidance for the filter warps) arrive by 1-D
+// bulk copies (cp.async.bulk, completion on an mbarrier) issued one block ahead by one warp of each group, so the
+// copy latency is hidden behind a whole block of work.  VS1 is double-buffered between the groups: the cost
+// evaluation of block u+1 overlaps the filtering of block u.
+template <int K>
+__global__ void __launch_bounds__(2 * GFS_THREADS, 1)
+k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const float4* __restrict__ Gi,
+             const float4* __restrict__ Gnm, const float4* __restrict__ Grd, const int* __restrict__ guide_mm, GfsGeom g,
+             TadStream tp, float c0, float* __restrict__ qv, uint32_t* __restrict__ slice_mm) {
+    using L = GfsLayout<K>;
+    constexpr int A = L::A, AW = L::AW, QW = L::QW, P1 = L::P1, P2 = L::P2, PQ = L::PQ, ROWS = L::ROWS;
+    constexpr int NRUN1 = (AW + GFF_RUN - 1) / GFF_RUN, NRUN2 = (QW + GFF_RUN - 1) / GFF_RUN;
+    static_assert(ROWS * NRUN1 <= GFS_THREADS && GFS_NS * AW <= GFS_THREADS, "phase does not fit one pass");
+    static_assert(3 * K <= 32, "one lane per bulk copy");
+    extern __shared__ float4 sm_gfs[];
+    float4* VS1 = sm_gfs + L::oVS1;
+    float4* AB = sm_gfs + L::oAB;
+    uint64_t* mbar = (uint64_t*)(sm_gfs + L::oBar);            // [0..1] cost stages, [2..3] filter stages
+
     const int H = g.H, W = g.W;
     const int x0 = blockIdx.x * QW;                            // first q' column of the strip
     const int d0 = blockIdx.y * GFS_NS;
@@ -143,123 +197,201 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
     int a0, U;                                                 // first (a,b) row of block 1, number of (a,b) blocks
     if (bottom) { U = (H - yb0 + A + K - 1) / K; a0 = H - K * U; }
     else { a0 = top ? 0 : yb0 - A; U = (yb1 + A - a0 + K - 1) / K; }
-    const int n_iter = U + 1 + (bottom ? 1 : 0);
-
-    // ---- A/V1 role: (slice, column) ----
-    const int sl1 = tid >> 6, c1 = tid & 63;
-    const int di1 = min(d0 + sl1, g.D - 1);
-    const int sx1 = border_idx(x0 - 2 * A + c1, W, 1);
-    const int toff1 = sx1 + g.x0_base + g.x0_step * di1;
-    float4 r1[K], s1 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < K; j++) r1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float cmin = 3.0e38f, cmax = -3.0e38f;
     const float inv = 1.0f / (float)(K * K);
-    // ---- V2 role: (slice, (a,b) column); out-of-image columns read their mirror column ----
-    const int sl2 = tid / AW, c2 = tid - sl2 * AW;
-    const bool v2_on = tid < GFS_NS * AW;
-    const int csrc = min(max(border_idx(x0 - A + c2, W, 1) - (x0 - A), 0), AW - 1);
-    float4 r2[K], s2 = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int j = 0; j < K; j++) r2[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    // ---- H roles: (run, slice*K + row) with consecutive lanes on consecutive rows ----
-    const int hrun = tid / ROWS, hrow = tid - hrun * ROWS;    // hrow = slice * K + j
-    const int hsl = hrow / K, hj = hrow - hsl * K;
-    const bool h_slice_ok = d0 + hsl < g.D;
 
-    for (int u = 0; u < n_iter; u++) {
-        const int pbase = a0 - A - 1 + K * u;                  // first p row of this block
-        const int abase = a0 + K * (u - 1);                    // first (a,b) row produced / consumed in this iteration
-        // ================= A / V1 =================
-        if (u <= U) {
-            const bool interior = pbase >= 0 && pbase + K <= H;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) gfs_mbar_init(&mbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (threadIdx.x < GFS_THREADS) {
+        // =========================== cost warps: A / V1, thread = (slice, column) ===========================
+        const int tid = threadIdx.x;
+        const int sl1 = tid >> 6, c1 = tid & 63;
+        const int di1 = min(d0 + sl1, g.D - 1);
+        // source columns of the strip: REFLECT_101 only folds the range, so [sxmin, sxmax] is contiguous
+        const int sx1 = border_idx(x0 - 2 * A + c1, W, 1);
+        int sxmin, sxmax;
+        {   // the fold maps the interval x0-2A .. x0-2A+63 onto an interval; its ends are among these four points
+            const int lo = x0 - 2 * A, hi = lo + GFS_IW - 1;
+            const int cand[4] = {lo, hi, min(max(0, lo), hi), min(max(W - 1, lo), hi)};
+            sxmin = 0x7fffffff; sxmax = -1;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int f = border_idx(cand[q], W, 1);
+                sxmin = min(sxmin, f); sxmax = max(sxmax, f);
+            }
+        }
+        const int nref = sxmax - sxmin + 1;
+        const int xo_a = g.x0_base + g.x0_step * d0, xo_b = g.x0_base + g.x0_step * min(d0 + GFS_NS - 1, g.D - 1);
+        const int xomin = min(xo_a, xo_b), ntgt = nref + abs(xo_a - xo_b);
+        const uint32_t tx_cost = (uint32_t)(K * (nref + ntgt) * 16);
+        FeatF* sRef = (FeatF*)(sm_gfs + L::oRef);
+        FeatF* sTgt = (FeatF*)(sm_gfs + L::oTgt);
+        const int ia = sx1 - sxmin;
+        const int it = ia + (g.x0_base + g.x0_step * di1) - xomin;
+        // cv::normalize of the guidance (A.cpp:2774), same expression as k_guide_normalize
+        float gsf, ghf;
+        minmax_scale_shift((double)guide_mm[0], (double)guide_mm[1], &gsf, &ghf);
+        auto issue = [&](int u) {        // whole warp 0: rows of block u -> stage u & 1
+            const int st = u & 1, lane = tid & 31;
+            if (lane == 0) gfs_mbar_expect_tx(&mbar[st], tx_cost);
+            __syncwarp();
+            if (lane < 2 * K) {
+                const int j = lane % K, which = lane / K;
+                const int sy = gfs_reflect1(a0 - A - 1 + K * u + j, H);
+                if (which == 0) gfs_bulk_g2s(sRef + (st * K + j) * GFS_IW, ref + (size_t)sy * W + sxmin, nref * 16, &mbar[st]);
+                else gfs_bulk_g2s(sTgt + (st * K + j) * GFS_TP, tgt + (size_t)sy * g.Wp + sxmin + xomin, ntgt * 16, &mbar[st]);
+            }
+        };
+        if (tid < 32) issue(0);
+        float4 r1[K], s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < K; j++) r1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float cmin = 3.0e38f, cmax = -3.0e38f;
+        for (int u = 0; u <= U; u++) {
+            gfs_bar_sync(GFS_BAR_COST, GFS_THREADS);           // every cost thread is done with block u-1
+            if (tid < 32 && u + 1 <= U) issue(u + 1);
+            const FeatF* rs = sRef + ((u & 1) * K) * GFS_IW + ia;
+            const FeatF* ts = sTgt + ((u & 1) * K) * GFS_TP + it;
+            float4* vs = VS1 + (u & 1) * ROWS * P1 + (sl1 * K) * P1 + c1;
+            gfs_mbar_wait(&mbar[u & 1], (u >> 1) & 1);
+            if (u >= 3) gfs_bar_sync(GFS_BAR_EMPTY + (u & 1), 2 * GFS_THREADS);
 #pragma unroll
             for (int j = 0; j < K; j++) {
-                const int sy = interior ? pbase + j : border_idx(pbase + j, H, 1);
-                const FeatF fa = ref[sy * W + sx1];
-                const float4 I = __ldg(&Gi[sy * W + sx1]);
-                const FeatF fb = tgt[sy * g.Wp + toff1];
+                const FeatF fa = rs[j * GFS_IW];
+                const FeatF fb = ts[j * GFS_TP];
                 const float cp = gfs_cost(fa, fb, tp);
                 cmin = fminf(cmin, cp); cmax = fmaxf(cmax, cp);
                 const float cs = cp * inv;
-                const float2 p01 = __fmul2_rn(make_float2(I.x, I.y), make_float2(cs, cs));
-                const float4 nw = make_float4(p01.x, p01.y, I.z * cs, cs);
-                const float4 s = gfs_ring_step<K>(r1, s1, nw, j);
-                VS1[(sl1 * K + j) * P1 + c1] = s;
+                const float I0 = fmaf((float)(fa.bgr & 0xFF), gsf, ghf), I1 = fmaf((float)((fa.bgr >> 8) & 0xFF), gsf, ghf);
+                const float I2 = fmaf((float)((fa.bgr >> 16) & 0xFF), gsf, ghf);
+                const float2 p01 = __fmul2_rn(make_float2(I0, I1), make_float2(cs, cs));
+                const float4 nw = make_float4(p01.x, p01.y, I2 * cs, cs);
+                vs[j * P1] = gfs_ring_step<K>(r1, s1, nw, j);
             }
+            if (u >= 1) { __threadfence_block(); gfs_bar_arrive(GFS_BAR_FULL + (u & 1), 2 * GFS_THREADS); }
         }
-        __syncthreads();
-        // ================= H1: horizontal window + (a,b) epilogue =================
-        if (u >= 1 && u <= U && hrun < NRUN1) {
-            const int ya = min(max(abase + hj, 0), H - 1);
-            const int xa0 = x0 - A + hrun * GFF_RUN;
-            float4* dst = AB + hrow * P2 + hrun * GFF_RUN;
-            gff_run<K>(VS1 + hrow * P1 + hrun * GFF_RUN, 1, min(GFF_RUN, AW - hrun * GFF_RUN), [&](int o, float4 s) {
-                const int pix = ya * W + min(max(xa0 + o, 0), W - 1);
-                const float4 nm = __ldg(&Gnm[pix]);
-                const float2 rd = __ldg(&Grd[pix]);
-                const float mP = s.w;
-                // cov = corr_Ip - mean_I * mean_p ; a = cov / (var + eps), pre-scaled by 1/K^2      (A.cpp:2805-2846)
-                const float2 cov01 = __ffma2_rn(make_float2(nm.x, nm.y), make_float2(mP, mP), make_float2(s.x, s.y));
-                const float2 a01 = __fmul2_rn(cov01, rd);
-                const float a2 = fmaf(nm.z, mP, s.z) * nm.w;
-                // b = mean_p - a . mean_I                                                            (A.cpp:2847)
-                const float b = fmaf(a01.x, nm.x, fmaf(a01.y, nm.y, fmaf(a2, nm.z, mP * inv)));
-                dst[o] = make_float4(a01.x, a01.y, a2, b);
-            });
+        // slice min / max of the raw cost: one atomic pair per warp (a warp = 32 columns of one slice)
+        for (int o = 16; o > 0; o >>= 1) {
+            cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+            cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
         }
-        __syncthreads();
-        // ================= V2: vertical window over (a,b) =================
-        if (u >= 1 && v2_on) {
-            const float4* src = AB + (sl2 * K) * P2 + csrc;
-            float4* dst = VS2 + (sl2 * K) * P2 + c2;
-            if (u == U + 1) {
-                // bottom of the image: ring = rows H-K .. H-1; output rows H-a .. H-1 (block rows 0 .. a-1)
-#pragma unroll
-                for (int i = 0; i < A; i++) dst[i * P2] = gfs_reflect_sum<K>(r2, K - A + i, false);
-            } else if (top && u == 1) {
-                // top of the image: ring <- rows 0 .. K-1; output rows 0 .. a (block rows a .. K-1)
-#pragma unroll
-                for (int j = 0; j < K; j++) r2[j] = src[j * P2];
-#pragma unroll
-                for (int i = 0; i <= A; i++) dst[(A + i) * P2] = gfs_reflect_sum<K>(r2, i, true);
-            } else {
-#pragma unroll
-                for (int j = 0; j < K; j++) {
-                    const float4 nw = src[j * P2];
-                    const float4 s = gfs_ring_step<K>(r2, s2, nw, j);
-                    dst[j * P2] = s;
+        if ((tid & 31) == 0 && d0 + sl1 < g.D) {
+            atomicMin(&slice_mm[2 * di1], orderable_u32(__fadd_rn(c0, cmin)));
+            atomicMax(&slice_mm[2 * di1 + 1], orderable_u32(__fadd_rn(c0, cmax)));
+        }
+    } else {
+        // =========================== filter warps: H1, V2, H2 ===========================
+        const int tid = threadIdx.x - GFS_THREADS;
+        float4* sGA = sm_gfs + L::oGA;
+        float4* sGB = sm_gfs + L::oGB;
+        float4* sIQ = sm_gfs + L::oIQ;
+        // staged column ranges: (a,b) columns x0-A .. x0-A+AW-1 clamped into the image, q' columns x0 .. clamped
+        const int xamin = max(x0 - A, 0), xamax = min(x0 - A + AW - 1, W - 1);
+        const int nga = xamax - xamin + 1, niq = min(W, x0 + QW) - x0;
+        const uint32_t tx_filter = (uint32_t)(K * (2 * nga + niq) * 16);
+        const int n_iter = U + (bottom ? 1 : 0);
+        auto issue = [&](int u) {        // filter warp 7: rows of block u -> stage u & 1
+            const int st = u & 1, lane = tid & 31;
+            if (lane == 0) gfs_mbar_expect_tx(&mbar[2 + st], tx_filter);
+            __syncwarp();
+            if (lane < 3 * K) {
+                const int j = lane % K, which = lane / K;
+                const int abase = a0 + K * (u - 1);
+                if (which < 2) {
+                    const int ya = min(max(abase + j, 0), H - 1);
+                    gfs_bulk_g2s((which ? sGB : sGA) + (st * K + j) * P2, (which ? Grd : Gnm) + (size_t)ya * W + xamin, nga * 16, &mbar[2 + st]);
+                } else {
+                    const int rq = min(max(abase - A + j, 0), H - 1);
+                    gfs_bulk_g2s(sIQ + (st * K + j) * PQ, Gi + (size_t)rq * W + x0, niq * 16, &mbar[2 + st]);
                 }
             }
-        }
-        __syncthreads();
-        // ================= H2: horizontal window + q' =================
-        if (u >= 1 && hrun < NRUN2 && h_slice_ok) {
-            const int rq = abase - A + hj;
-            if (rq >= yb0 && rq < yb1) {      // also drops the unused block rows of the two closed-form steps
-                const int xq0 = x0 + hrun * GFF_RUN;
-                const int len = min(GFF_RUN, QW - hrun * GFF_RUN);
-                float q[GFF_RUN];
-                gff_run<K>(VS2 + hrow * P2 + hrun * GFF_RUN, 1, len, [&](int o, float4 s) {
-                    const float4 I = __ldg(&Gi[rq * W + min(xq0 + o, W - 1)]);
-                    q[o] = fmaf(s.x, I.x, fmaf(s.y, I.y, fmaf(s.z, I.z, s.w)));          // abar . I + bbar (A.cpp:2852)
+        };
+        const bool loader = tid >= GFS_THREADS - 32;
+        if (loader) issue(1);
+        // V2 role: (slice, (a,b) column); out-of-image columns read their mirror column
+        const int sl2 = tid / AW, c2 = tid - sl2 * AW;
+        const bool v2_on = tid < GFS_NS * AW;
+        const int csrc = min(max(border_idx(x0 - A + c2, W, 1) - (x0 - A), 0), AW - 1);
+        float4 r2[K], s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < K; j++) r2[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // H roles: (run, slice*K + row) with consecutive lanes on consecutive rows
+        const int hrun = tid / ROWS, hrow = tid - hrun * ROWS;    // hrow = slice * K + j
+        const int hsl = hrow / K, hj = hrow - hsl * K;
+        const bool h_slice_ok = d0 + hsl < g.D;
+        const int ga_shift = (x0 - A) - xamin + hrun * GFF_RUN;  // staged index of the run's first (a,b) column, before clamping
+        for (int u = 1; u <= n_iter; u++) {
+            const int abase = a0 + K * (u - 1);                // first (a,b) row of this block
+            float4* VS2 = VS1 + (u & 1) * ROWS * P1;           // aliases the VS1 buffer consumed by this block's H1
+            if (u <= U) gfs_bar_sync(GFS_BAR_FULL + (u & 1), 2 * GFS_THREADS);
+            else gfs_bar_sync(GFS_BAR_FILTER, GFS_THREADS);    // every filter thread is done with block u-1
+            if (loader && u + 1 <= n_iter) issue(u + 1);
+            gfs_mbar_wait(&mbar[2 + (u & 1)], ((u - 1) >> 1) & 1);   // blocks 1, 2 are the first use of stages 1, 0
+            // ---- H1: horizontal window + (a,b) epilogue ----
+            if (u <= U && hrun < NRUN1) {
+                float4* dst = AB + hrow * P2 + hrun * GFF_RUN;
+                const float4* src = VS2 + hrow * P1 + hrun * GFF_RUN;
+                const float4* ga = sGA + ((u & 1) * K + hj) * P2;
+                const float4* gb = sGB + ((u & 1) * K + hj) * P2;
+                gff_run<K>(src, 1, min(GFF_RUN, AW - hrun * GFF_RUN), [&](int o, float4 s) {
+                    const int ix = min(max(ga_shift + o, 0), nga - 1);
+                    const float4 nm = ga[ix];
+                    const float4 rd = gb[ix];
+                    const float mP = s.w;
+                    // cov = corr_Ip - mean_I * mean_p ; a = cov / (var + eps), pre-scaled by 1/K^2  (A.cpp:2805-2846)
+                    const float2 cov01 = __ffma2_rn(make_float2(nm.x, nm.y), make_float2(mP, mP), make_float2(s.x, s.y));
+                    const float2 a01 = __fmul2_rn(cov01, make_float2(rd.x, rd.y));
+                    const float a2 = fmaf(nm.z, mP, s.z) * nm.w;
+                    // b = mean_p - a . mean_I                                                        (A.cpp:2847)
+                    const float b = fmaf(a01.x, nm.x, fmaf(a01.y, nm.y, fmaf(a2, nm.z, mP * inv)));
+                    dst[o] = make_float4(a01.x, a01.y, a2, b);
                 });
-                float4* out = (float4*)(qv + ((size_t)(d0 + hsl) * H + rq) * g.Wq + xq0);
-                out[0] = make_float4(q[0], q[1], q[2], q[3]);
-                if (len > 4) out[1] = make_float4(q[4], q[5], q[6], q[7]);
             }
+            gfs_bar_sync(GFS_BAR_FILTER, GFS_THREADS);
+            // ---- V2: vertical window over (a,b) ----
+            if (v2_on) {
+                const float4* src = AB + (sl2 * K) * P2 + csrc;
+                float4* dst = VS2 + (sl2 * K) * P1 + c2;
+                if (u == U + 1) {
+                    // bottom of the image: ring = rows H-K .. H-1; output rows H-a .. H-1 (block rows 0 .. a-1)
+#pragma unroll
+                    for (int i = 0; i < A; i++) dst[i * P1] = gfs_reflect_sum<K>(r2, K - A + i, false);
+                } else if (top && u == 1) {
+                    // top of the image: ring <- rows 0 .. K-1; output rows 0 .. a (block rows a .. K-1)
+#pragma unroll
+                    for (int j = 0; j < K; j++) r2[j] = src[j * P2];
+#pragma unroll
+                    for (int i = 0; i <= A; i++) dst[(A + i) * P1] = gfs_reflect_sum<K>(r2, i, true);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < K; j++) dst[j * P1] = gfs_ring_step<K>(r2, s2, src[j * P2], j);
+                }
+            }
+            gfs_bar_sync(GFS_BAR_FILTER, GFS_THREADS);
+            // ---- H2: horizontal window + q' ----
+            if (hrun < NRUN2 && h_slice_ok) {
+                const int rq = abase - A + hj;
+                if (rq >= yb0 && rq < yb1) {      // also drops the unused block rows of the two closed-form steps
+                    const int xq0 = x0 + hrun * GFF_RUN;
+                    const int len = min(GFF_RUN, QW - hrun * GFF_RUN);
+                    const float4* iq = sIQ + ((u & 1) * K + hj) * PQ;
+                    float q[GFF_RUN];
+                    gff_run<K>(VS2 + hrow * P1 + hrun * GFF_RUN, 1, len, [&](int o, float4 s) {
+                        const float4 I = iq[min(hrun * GFF_RUN + o, niq - 1)];
+                        q[o] = fmaf(s.x, I.x, fmaf(s.y, I.y, fmaf(s.z, I.z, s.w)));      // abar . I + bbar (A.cpp:2852)
+                    });
+                    float4* out = (float4*)(qv + ((size_t)(d0 + hsl) * H + rq) * g.Wq + xq0);
+                    out[0] = make_float4(q[0], q[1], q[2], q[3]);
+                    if (len > 4) out[1] = make_float4(q[4], q[5], q[6], q[7]);
+                }
+            }
+            if (u + 2 <= U) { __threadfence_block(); gfs_bar_arrive(GFS_BAR_EMPTY + (u & 1), 2 * GFS_THREADS); }
+            // the next block's H1 rewrites AB (last read by V2, one filter barrier back)
         }
-        // no barrier: the next A/V1 writes VS1 (last read in H1, two barriers back); AB is rewritten after the next
-        // barrier, VS2 after two more
-    }
-    // ---- slice min / max of the raw cost: one atomic pair per warp (a warp = 32 columns of one slice) ----
-    for (int o = 16; o > 0; o >>= 1) {
-        cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
-        cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-    }
-    if ((tid & 31) == 0 && d0 + sl1 < g.D) {
-        atomicMin(&slice_mm[2 * di1], orderable_u32(__fadd_rn(c0, cmin)));
-        atomicMax(&slice_mm[2 * di1 + 1], orderable_u32(__fadd_rn(c0, cmax)));
     }
 }
 
@@ -311,14 +443,14 @@ static inline bool gfs_supported(int H, int W, int win) {
 
 template <int K>
 static asw_status gfs_launch(asw_ctx* ctx, const FeatF* fref, const FeatF* ftgt, const float4* Gi, const float4* Gnm,
-                             const float2* Grd, GfsGeom g, const TadParams& tp, float* qv, uint32_t* slice_mm, float2* aff,
+                             const float4* Grd, const int* guide_mm, GfsGeom g, const TadParams& tp, float* qv, uint32_t* slice_mm, float2* aff,
                              int cn, int d_label0, unsigned long long* keys, float* agg) {
-    constexpr int AW = GFS_IW - (K - 1), QW = GFS_IW - 2 * (K - 1), ROWS = GFS_NS * K;
-    const size_t smem = ((size_t)ROWS * (GFS_IW + 1) + 2 * (size_t)ROWS * (AW | 1)) * sizeof(float4);
+    constexpr int QW = GfsLayout<K>::QW;
+    const size_t smem = GfsLayout<K>::bytes;
     cudaFuncSetAttribute(k_gfs_filter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int strips = cdiv(g.W, QW), groups = cdiv(cn, GFS_NS);
     // bands: enough CTAs for ~4 resident sets, every band at least 2K rows, at least 2 (one top, one bottom)
-    int nb = cdiv(8 * ctx->sm_count, strips * groups);
+    int nb = cdiv(4 * ctx->sm_count, strips * groups);
     const char* e = getenv("ASW_GFS_BANDS");
     if (e && atoi(e) > 0) nb = atoi(e);
     nb = std::max(2, std::min(nb, g.H / (2 * K)));
@@ -326,8 +458,8 @@ static asw_status gfs_launch(asw_ctx* ctx, const FeatF* fref, const FeatF* ftgt,
     TadStream ts;
     ts.thr_c = (int)floorf(tp.thr_c); ts.add_c = (int)rintf(tp.add_c); ts.thr_g = tp.thr_g;
     ts.reg_r = (float)tp.reg_r; ts.reg = (float)tp.reg;
-    LAUNCH(ctx, "gfs_filter", (k_gfs_filter<K><<<dim3(strips, groups, nb), GFS_THREADS, smem, ctx->stream>>>(
-                                  fref, ftgt, Gi, Gnm, Grd, g, ts, tp.c0, qv, slice_mm)));
+    LAUNCH(ctx, "gfs_filter", (k_gfs_filter<K><<<dim3(strips, groups, nb), 2 * GFS_THREADS, smem, ctx->stream>>>(
+                                  fref, ftgt, Gi, Gnm, Grd, guide_mm, g, ts, tp.c0, qv, slice_mm)));
     LAUNCH(ctx, "gfs_affine", (k_gfs_affine<<<cdiv(cn, 128), 128, 0, ctx->stream>>>(slice_mm, cn, tp.c0, aff)));
     LAUNCH(ctx, "gfs_wta", (k_gfs_wta<<<dim3(cdiv(cdiv(g.W, 4), 128), g.H), 128, 0, ctx->stream>>>(
                                qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg)));
