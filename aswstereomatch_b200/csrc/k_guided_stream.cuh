@@ -147,6 +147,74 @@ __device__ __forceinline__ void gfs_bulk_g2s(void* dst, const void* src, uint32_
 #define GFS_BAR_COST 6       // among the cost warps
 #define GFS_TP 68            // staged target row pitch (64 + NS - 1, padded)
 
+// Horizontal sliding run of 8 window sums with the loads issued GFS_PF outputs ahead of their use (a filter warp
+// has one other warp per scheduler to hide behind, so the shared-memory latency must be covered inside the thread).
+#define GFS_PF 3
+template <int K>
+__device__ __forceinline__ float4 gfs_tree_sum(const float4* w) {
+    float4 t = p4add(w[0], w[1]);
+#pragma unroll
+    for (int i = 2; i < K; i++) t = p4add(t, w[i]);
+    return t;
+}
+// level 1: window sums of (I c, c) -> (a, b) of A.cpp:2805-2847, a pre-scaled by 1/K^2
+template <int K>
+__device__ __forceinline__ void gfs_h1(const float4* __restrict__ src, const float4* __restrict__ ga,
+                                       const float4* __restrict__ gb, int ga_shift, int nga, float4* __restrict__ dst,
+                                       int len, float inv) {
+    constexpr int N = GFF_RUN + K - 1;
+    float4 w[N], nm[GFF_RUN];
+    float2 rd[GFF_RUN];
+#pragma unroll
+    for (int i = 0; i < K - 1 + GFS_PF; i++) w[i] = src[i];
+#pragma unroll
+    for (int o = 0; o < GFS_PF; o++) {
+        const int ix = min(max(ga_shift + o, 0), nga - 1);
+        nm[o] = ga[ix]; rd[o] = *(const float2*)&gb[ix];
+    }
+    float4 s;
+#pragma unroll
+    for (int o = 0; o < GFF_RUN; o++) {
+        if (o + GFS_PF < GFF_RUN) {
+            w[K - 1 + o + GFS_PF] = src[K - 1 + o + GFS_PF];
+            const int ix = min(max(ga_shift + o + GFS_PF, 0), nga - 1);
+            nm[o + GFS_PF] = ga[ix]; rd[o + GFS_PF] = *(const float2*)&gb[ix];
+        }
+        s = (o == 0) ? gfs_tree_sum<K>(w) : p4slide(s, w[o - 1], w[o + K - 1]);
+        if (o < len) {
+            const float mP = s.w;
+            // cov = corr_Ip - mean_I * mean_p ; a = cov / (var + eps)                         (A.cpp:2805-2846)
+            const float2 cov01 = __ffma2_rn(make_float2(nm[o].x, nm[o].y), make_float2(mP, mP), make_float2(s.x, s.y));
+            const float2 a01 = __fmul2_rn(cov01, rd[o]);
+            const float a2 = fmaf(nm[o].z, mP, s.z) * nm[o].w;
+            // b = mean_p - a . mean_I                                                         (A.cpp:2847)
+            const float b = fmaf(a01.x, nm[o].x, fmaf(a01.y, nm[o].y, fmaf(a2, nm[o].z, mP * inv)));
+            dst[o] = make_float4(a01.x, a01.y, a2, b);
+        }
+    }
+}
+// level 2: window sums of (a, b) -> q' = abar . I + bbar (A.cpp:2852)
+template <int K>
+__device__ __forceinline__ void gfs_h2(const float4* __restrict__ src, const float4* __restrict__ iq, int iq0, int niq,
+                                       float (&q)[GFF_RUN]) {
+    constexpr int N = GFF_RUN + K - 1;
+    float4 w[N], I[GFF_RUN];
+#pragma unroll
+    for (int i = 0; i < K - 1 + GFS_PF; i++) w[i] = src[i];
+#pragma unroll
+    for (int o = 0; o < GFS_PF; o++) I[o] = iq[min(iq0 + o, niq - 1)];
+    float4 s;
+#pragma unroll
+    for (int o = 0; o < GFF_RUN; o++) {
+        if (o + GFS_PF < GFF_RUN) {
+            w[K - 1 + o + GFS_PF] = src[K - 1 + o + GFS_PF];
+            I[o + GFS_PF] = iq[min(iq0 + o + GFS_PF, niq - 1)];
+        }
+        s = (o == 0) ? gfs_tree_sum<K>(w) : p4slide(s, w[o - 1], w[o + K - 1]);
+        q[o] = fmaf(s.x, I[o].x, fmaf(s.y, I[o].y, fmaf(s.z, I[o].z, s.w)));
+    }
+}
+
 template <int K>
 struct GfsLayout {
     static constexpr int A = K / 2;
@@ -256,7 +324,7 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
             if (tid < 32 && u + 1 <= U) issue(u + 1);
             const FeatF* rs = sRef + ((u & 1) * K) * GFS_IW + ia;
             const FeatF* ts = sTgt + ((u & 1) * K) * GFS_TP + it;
-            float4* vs = VS1 + (u & 1) * ROWS * P1 + (sl1 * K) * P1 + c1;
+            float4* vs = VS1 + (u & 1) * ROWS * P1 + sl1 * P1 + c1;   // shared-memory row = j * NS + slice
             gfs_mbar_wait(&mbar[u & 1], (u >> 1) & 1);
             if (u >= 3) gfs_bar_sync(GFS_BAR_EMPTY + (u & 1), 2 * GFS_THREADS);
 #pragma unroll
@@ -270,7 +338,7 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
                 const float I2 = fmaf((float)((fa.bgr >> 16) & 0xFF), gsf, ghf);
                 const float2 p01 = __fmul2_rn(make_float2(I0, I1), make_float2(cs, cs));
                 const float4 nw = make_float4(p01.x, p01.y, I2 * cs, cs);
-                vs[j * P1] = gfs_ring_step<K>(r1, s1, nw, j);
+                vs[j * GFS_NS * P1] = gfs_ring_step<K>(r1, s1, nw, j);
             }
             if (u >= 1) { __threadfence_block(); gfs_bar_arrive(GFS_BAR_FULL + (u & 1), 2 * GFS_THREADS); }
         }
@@ -319,9 +387,11 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
         float4 r2[K], s2 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < K; j++) r2[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        // H roles: (run, slice*K + row) with consecutive lanes on consecutive rows
-        const int hrun = tid / ROWS, hrow = tid - hrun * ROWS;    // hrow = slice * K + j
-        const int hsl = hrow / K, hj = hrow - hsl * K;
+        // H roles: (run, shared-memory row) with consecutive lanes on consecutive rows.  Row = j * NS + slice: a
+        // quarter-warp then spans two image rows, so its loads of the per-pixel operands (identical for the NS
+        // slices) touch two addresses instead of eight
+        const int hrun = tid / ROWS, hrow = tid - hrun * ROWS;
+        const int hj = hrow / GFS_NS, hsl = hrow - hj * GFS_NS;
         const bool h_slice_ok = d0 + hsl < g.D;
         const int ga_shift = (x0 - A) - xamin + hrun * GFF_RUN;  // staged index of the run's first (a,b) column, before clamping
         for (int u = 1; u <= n_iter; u++) {
@@ -337,38 +407,26 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
                 const float4* src = VS2 + hrow * P1 + hrun * GFF_RUN;
                 const float4* ga = sGA + ((u & 1) * K + hj) * P2;
                 const float4* gb = sGB + ((u & 1) * K + hj) * P2;
-                gff_run<K>(src, 1, min(GFF_RUN, AW - hrun * GFF_RUN), [&](int o, float4 s) {
-                    const int ix = min(max(ga_shift + o, 0), nga - 1);
-                    const float4 nm = ga[ix];
-                    const float4 rd = gb[ix];
-                    const float mP = s.w;
-                    // cov = corr_Ip - mean_I * mean_p ; a = cov / (var + eps), pre-scaled by 1/K^2  (A.cpp:2805-2846)
-                    const float2 cov01 = __ffma2_rn(make_float2(nm.x, nm.y), make_float2(mP, mP), make_float2(s.x, s.y));
-                    const float2 a01 = __fmul2_rn(cov01, make_float2(rd.x, rd.y));
-                    const float a2 = fmaf(nm.z, mP, s.z) * nm.w;
-                    // b = mean_p - a . mean_I                                                        (A.cpp:2847)
-                    const float b = fmaf(a01.x, nm.x, fmaf(a01.y, nm.y, fmaf(a2, nm.z, mP * inv)));
-                    dst[o] = make_float4(a01.x, a01.y, a2, b);
-                });
+                gfs_h1<K>(src, ga, gb, ga_shift, nga, dst, min(GFF_RUN, AW - hrun * GFF_RUN), inv);
             }
             gfs_bar_sync(GFS_BAR_FILTER, GFS_THREADS);
             // ---- V2: vertical window over (a,b) ----
             if (v2_on) {
-                const float4* src = AB + (sl2 * K) * P2 + csrc;
-                float4* dst = VS2 + (sl2 * K) * P1 + c2;
+                const float4* src = AB + sl2 * P2 + csrc;
+                float4* dst = VS2 + sl2 * P1 + c2;
                 if (u == U + 1) {
                     // bottom of the image: ring = rows H-K .. H-1; output rows H-a .. H-1 (block rows 0 .. a-1)
 #pragma unroll
-                    for (int i = 0; i < A; i++) dst[i * P1] = gfs_reflect_sum<K>(r2, K - A + i, false);
+                    for (int i = 0; i < A; i++) dst[i * GFS_NS * P1] = gfs_reflect_sum<K>(r2, K - A + i, false);
                 } else if (top && u == 1) {
                     // top of the image: ring <- rows 0 .. K-1; output rows 0 .. a (block rows a .. K-1)
 #pragma unroll
-                    for (int j = 0; j < K; j++) r2[j] = src[j * P2];
+                    for (int j = 0; j < K; j++) r2[j] = src[j * GFS_NS * P2];
 #pragma unroll
-                    for (int i = 0; i <= A; i++) dst[(A + i) * P1] = gfs_reflect_sum<K>(r2, i, true);
+                    for (int i = 0; i <= A; i++) dst[(A + i) * GFS_NS * P1] = gfs_reflect_sum<K>(r2, i, true);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < K; j++) dst[j * P1] = gfs_ring_step<K>(r2, s2, src[j * P2], j);
+                    for (int j = 0; j < K; j++) dst[j * GFS_NS * P1] = gfs_ring_step<K>(r2, s2, src[j * GFS_NS * P2], j);
                 }
             }
             gfs_bar_sync(GFS_BAR_FILTER, GFS_THREADS);
@@ -380,10 +438,7 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
                     const int len = min(GFF_RUN, QW - hrun * GFF_RUN);
                     const float4* iq = sIQ + ((u & 1) * K + hj) * PQ;
                     float q[GFF_RUN];
-                    gff_run<K>(VS2 + hrow * P1 + hrun * GFF_RUN, 1, len, [&](int o, float4 s) {
-                        const float4 I = iq[min(hrun * GFF_RUN + o, niq - 1)];
-                        q[o] = fmaf(s.x, I.x, fmaf(s.y, I.y, fmaf(s.z, I.z, s.w)));      // abar . I + bbar (A.cpp:2852)
-                    });
+                    gfs_h2<K>(VS2 + hrow * P1 + hrun * GFF_RUN, iq, hrun * GFF_RUN, niq, q);
                     float4* out = (float4*)(qv + ((size_t)(d0 + hsl) * H + rq) * g.Wq + xq0);
                     out[0] = make_float4(q[0], q[1], q[2], q[3]);
                     if (len > 4) out[1] = make_float4(q[4], q[5], q[6], q[7]);
