@@ -295,17 +295,16 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
     TadParams tp = make_tad_params(0.4, 10, 50);                                     // A.cpp:2990
     if (gfs_supported(H, W, win) && !getenv("ASW_GF_TILED") && !getenv("ASW_GF_GENERIC")) {
         // streaming kernel (k_guided_stream.cuh): cost, both box levels and q' on chip; 4 B per evaluation to HBM
-        FeatF *rff, *tff; float4 *gnm, *grd2; float2* aff;
+        FeatF *rff, *tff; GfsMoments* gmom; float2* aff;
         ASW_TRY(ws_get(ctx, WS_FEATF_REF, n, &rff));
         ASW_TRY(ws_get(ctx, WS_FEATF_TGT, (size_t)H * v.Wp, &tff));
-        ASW_TRY(ws_get(ctx, WS_GUIDE_NM, n, &gnm));
-        ASW_TRY(ws_get(ctx, WS_GUIDE_RD2, n, &grd2));
+        ASW_TRY(ws_get(ctx, WS_GUIDE_NM, n, &gmom));
         ASW_TRY(ws_get(ctx, WS_AFF, (size_t)num_d, &aff));
         size_t nt = (size_t)H * v.Wp;
         LAUNCH(ctx, "feat_to_float", (k_feat_to_float<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(fref, n, 1.0f, rff)));
         LAUNCH(ctx, "feat_to_float", (k_feat_to_float<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ftgt, nt, -1.0f, tff)));
         LAUNCH(ctx, "gfs_pack_guide", (k_gfs_pack_guide<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-                                          gp.Gm, gp.Gd, n, 1.0f / (float)(win * win), gnm, grd2)));
+                                          gp.Gm, gp.Gd, n, 1.0f / (float)(win * win), gmom)));
         const int QW = GFS_IW - 2 * (win - 1);
         GfsGeom g;
         g.H = H; g.W = W; g.Wp = v.Wp; g.Wq = cdiv(W, QW) * QW; g.x0_step = v.x0_step; g.D = 0; g.nbands = 2;
@@ -319,9 +318,9 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
             int cn = (d_hi - c0 < chunk) ? d_hi - c0 : chunk;
             g.x0_base = v.x0_base + v.x0_step * c0;
             float* agg_c = agg_dev ? agg_dev + (size_t)(c0 - d_lo) * n : nullptr;
-            if (win == 9) ASW_TRY(gfs_launch<9>(ctx, rff, tff, gp.Gi, gnm, grd2, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
-            else if (win == 7) ASW_TRY(gfs_launch<7>(ctx, rff, tff, gp.Gi, gnm, grd2, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
-            else ASW_TRY(gfs_launch<5>(ctx, rff, tff, gp.Gi, gnm, grd2, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
+            if (win == 9) ASW_TRY(gfs_launch<9>(ctx, rff, tff, gp.Gi, gmom, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
+            else if (win == 7) ASW_TRY(gfs_launch<7>(ctx, rff, tff, gp.Gi, gmom, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
+            else ASW_TRY(gfs_launch<5>(ctx, rff, tff, gp.Gi, gmom, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
         }
         return ASW_OK;
     }

@@ -49,15 +49,18 @@ __global__ void k_feat_to_float(const Feat* __restrict__ in, size_t n, float sig
     out[i] = o;
 }
 
-// guidance records for the (a,b) epilogue: Gnm = {-mean_I0, -mean_I1, -mean_I2, rd2}, Grd = {rd0, rd1, -, -} with
+// guidance record for the (a,b) epilogue, 32 bytes per pixel: {-mean_I0, -mean_I1, -mean_I2, rd2, rd0, rd1, -, -} with
 // rd_c = (1/K^2) / (var_c + eps): the level-2 box normalisation is folded into a.
+struct __align__(16) GfsMoments { float4 nm; float4 rd; };
 __global__ void k_gfs_pack_guide(const float4* __restrict__ Gm, const float4* __restrict__ Gd, size_t n, float inv,
-                                 float4* __restrict__ Gnm, float4* __restrict__ Grd) {
+                                 GfsMoments* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 m = Gm[i], d = Gd[i];
-    Gnm[i] = make_float4(-m.x, -m.y, -m.z, __fdiv_rn(inv, d.z));
-    Grd[i] = make_float4(__fdiv_rn(inv, d.x), __fdiv_rn(inv, d.y), 0.0f, 0.0f);
+    GfsMoments r;
+    r.nm = make_float4(-m.x, -m.y, -m.z, __fdiv_rn(inv, d.z));
+    r.rd = make_float4(__fdiv_rn(inv, d.x), __fdiv_rn(inv, d.y), 0.0f, 0.0f);
+    out[i] = r;
 }
 
 struct GfsGeom {
@@ -144,7 +147,8 @@ __device__ __forceinline__ void gfs_bulk_g2s(void* dst, const void* src, uint32_
 #define GFS_BAR_FULL 1       // +buf : VS1[buf] written by the cost warps
 #define GFS_BAR_EMPTY 3      // +buf : VS1[buf] (and the VS2 aliased onto it) consumed by the filter warps
 #define GFS_BAR_FILTER 5     // among the filter warps
-#define GFS_BAR_COST 6       // among the cost warps
+#define GFS_BAR_COST 7        // among the cost warps
+#define GFS_BAR_FILTER2 6     // among the filter warps that have V2 / H2 items (all but the loader warp)
 #define GFS_TP 68            // staged target row pitch (64 + NS - 1, padded)
 
 // Horizontal sliding run of 8 window sums with the loads issued GFS_PF outputs ahead of their use (a filter warp
@@ -159,9 +163,8 @@ __device__ __forceinline__ float4 gfs_tree_sum(const float4* w) {
 }
 // level 1: window sums of (I c, c) -> (a, b) of A.cpp:2805-2847, a pre-scaled by 1/K^2
 template <int K>
-__device__ __forceinline__ void gfs_h1(const float4* __restrict__ src, const float4* __restrict__ ga,
-                                       const float4* __restrict__ gb, int ga_shift, int nga, float4* __restrict__ dst,
-                                       int len, float inv) {
+__device__ __forceinline__ void gfs_h1(const float4* __restrict__ src, const GfsMoments* __restrict__ gm, int ga_shift,
+                                       int nga, float4* __restrict__ dst, int len, float inv) {
     constexpr int N = GFF_RUN + K - 1;
     float4 w[N], nm[GFF_RUN];
     float2 rd[GFF_RUN];
@@ -170,7 +173,7 @@ __device__ __forceinline__ void gfs_h1(const float4* __restrict__ src, const flo
 #pragma unroll
     for (int o = 0; o < GFS_PF; o++) {
         const int ix = min(max(ga_shift + o, 0), nga - 1);
-        nm[o] = ga[ix]; rd[o] = *(const float2*)&gb[ix];
+        nm[o] = gm[ix].nm; rd[o] = *(const float2*)&gm[ix].rd;
     }
     float4 s;
 #pragma unroll
@@ -178,7 +181,7 @@ __device__ __forceinline__ void gfs_h1(const float4* __restrict__ src, const flo
         if (o + GFS_PF < GFF_RUN) {
             w[K - 1 + o + GFS_PF] = src[K - 1 + o + GFS_PF];
             const int ix = min(max(ga_shift + o + GFS_PF, 0), nga - 1);
-            nm[o + GFS_PF] = ga[ix]; rd[o + GFS_PF] = *(const float2*)&gb[ix];
+            nm[o + GFS_PF] = gm[ix].nm; rd[o + GFS_PF] = *(const float2*)&gm[ix].rd;
         }
         s = (o == 0) ? gfs_tree_sum<K>(w) : p4slide(s, w[o - 1], w[o + K - 1]);
         if (o < len) {
@@ -227,9 +230,8 @@ struct GfsLayout {
     static constexpr int oAB = oVS1 + 2 * ROWS * P1;           // [ROWS][P2]     (a0,a1,a2,b)
     static constexpr int oRef = oAB + ROWS * P2;               // [2][K][64]     staged reference features
     static constexpr int oTgt = oRef + 2 * K * GFS_IW;         // [2][K][GFS_TP] staged target features (NS slices share them)
-    static constexpr int oGA = oTgt + 2 * K * GFS_TP;          // [2][K][P2]     {-mI0,-mI1,-mI2, rd2}
-    static constexpr int oGB = oGA + 2 * K * P2;               // [2][K][P2]     {rd0, rd1, -, -}
-    static constexpr int oIQ = oGB + 2 * K * P2;               // [2][K][PQ]     guidance at the q' pixels
+    static constexpr int oGM = oTgt + 2 * K * GFS_TP;          // [2][K][P2]     32-byte moment records (2 float4 each)
+    static constexpr int oIQ = oGM + 2 * K * P2 * 2;           // [2][K][PQ]     guidance at the q' pixels
     static constexpr int oBar = oIQ + 2 * K * PQ;              // 4 mbarriers
     static constexpr size_t bytes = (size_t)(oBar + 2) * sizeof(float4);
 };
@@ -243,13 +245,14 @@ struct GfsLayout {
 template <int K>
 __global__ void __launch_bounds__(2 * GFS_THREADS, 1)
 k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const float4* __restrict__ Gi,
-             const float4* __restrict__ Gnm, const float4* __restrict__ Grd, const int* __restrict__ guide_mm, GfsGeom g,
+             const GfsMoments* __restrict__ Gmom, const int* __restrict__ guide_mm, GfsGeom g,
              TadStream tp, float c0, float* __restrict__ qv, uint32_t* __restrict__ slice_mm) {
     using L = GfsLayout<K>;
     constexpr int A = L::A, AW = L::AW, QW = L::QW, P1 = L::P1, P2 = L::P2, PQ = L::PQ, ROWS = L::ROWS;
     constexpr int NRUN1 = (AW + GFF_RUN - 1) / GFF_RUN, NRUN2 = (QW + GFF_RUN - 1) / GFF_RUN;
     static_assert(ROWS * NRUN1 <= GFS_THREADS && GFS_NS * AW <= GFS_THREADS, "phase does not fit one pass");
-    static_assert(3 * K <= 32, "one lane per bulk copy");
+    // K = 9: the last filter warp has no V2 / H2 items and stays out of the V2 -> H2 barrier
+    constexpr bool LOADER_FREE = GFS_NS * AW <= GFS_THREADS - 32 && ROWS * NRUN2 <= GFS_THREADS - 32;
     extern __shared__ float4 sm_gfs[];
     float4* VS1 = sm_gfs + L::oVS1;
     float4* AB = sm_gfs + L::oAB;
@@ -274,59 +277,60 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
     }
     __syncthreads();
 
+    // source columns of the strip: REFLECT_101 only folds the range, so [sxmin, sxmax] is contiguous
+    int sxmin, sxmax;
+    {   // the fold maps the interval x0-2A .. x0-2A+63 onto an interval; its ends are among these four points
+        const int lo = x0 - 2 * A, hi = lo + GFS_IW - 1;
+        const int cand[4] = {lo, hi, min(max(0, lo), hi), min(max(W - 1, lo), hi)};
+        sxmin = 0x7fffffff; sxmax = -1;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int f = border_idx(cand[q], W, 1);
+            sxmin = min(sxmin, f); sxmax = max(sxmax, f);
+        }
+    }
+    const int nref = sxmax - sxmin + 1;
+    const int xo_a = g.x0_base + g.x0_step * d0, xo_b = g.x0_base + g.x0_step * min(d0 + GFS_NS - 1, g.D - 1);
+    const int xomin = min(xo_a, xo_b), ntgt = nref + abs(xo_a - xo_b);
+    FeatF* sRef = (FeatF*)(sm_gfs + L::oRef);
+    FeatF* sTgt = (FeatF*)(sm_gfs + L::oTgt);
+
     if (threadIdx.x < GFS_THREADS) {
         // =========================== cost warps: A / V1, thread = (slice, column) ===========================
         const int tid = threadIdx.x;
         const int sl1 = tid >> 6, c1 = tid & 63;
         const int di1 = min(d0 + sl1, g.D - 1);
-        // source columns of the strip: REFLECT_101 only folds the range, so [sxmin, sxmax] is contiguous
         const int sx1 = border_idx(x0 - 2 * A + c1, W, 1);
-        int sxmin, sxmax;
-        {   // the fold maps the interval x0-2A .. x0-2A+63 onto an interval; its ends are among these four points
-            const int lo = x0 - 2 * A, hi = lo + GFS_IW - 1;
-            const int cand[4] = {lo, hi, min(max(0, lo), hi), min(max(W - 1, lo), hi)};
-            sxmin = 0x7fffffff; sxmax = -1;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int f = border_idx(cand[q], W, 1);
-                sxmin = min(sxmin, f); sxmax = max(sxmax, f);
-            }
-        }
-        const int nref = sxmax - sxmin + 1;
-        const int xo_a = g.x0_base + g.x0_step * d0, xo_b = g.x0_base + g.x0_step * min(d0 + GFS_NS - 1, g.D - 1);
-        const int xomin = min(xo_a, xo_b), ntgt = nref + abs(xo_a - xo_b);
-        const uint32_t tx_cost = (uint32_t)(K * (nref + ntgt) * 16);
-        FeatF* sRef = (FeatF*)(sm_gfs + L::oRef);
-        FeatF* sTgt = (FeatF*)(sm_gfs + L::oTgt);
         const int ia = sx1 - sxmin;
         const int it = ia + (g.x0_base + g.x0_step * di1) - xomin;
         // cv::normalize of the guidance (A.cpp:2774), same expression as k_guide_normalize
         float gsf, ghf;
         minmax_scale_shift((double)guide_mm[0], (double)guide_mm[1], &gsf, &ghf);
-        auto issue = [&](int u) {        // whole warp 0: rows of block u -> stage u & 1
-            const int st = u & 1, lane = tid & 31;
-            if (lane == 0) gfs_mbar_expect_tx(&mbar[st], tx_cost);
-            __syncwarp();
-            if (lane < 2 * K) {
-                const int j = lane % K, which = lane / K;
-                const int sy = gfs_reflect1(a0 - A - 1 + K * u + j, H);
-                if (which == 0) gfs_bulk_g2s(sRef + (st * K + j) * GFS_IW, ref + (size_t)sy * W + sxmin, nref * 16, &mbar[st]);
-                else gfs_bulk_g2s(sTgt + (st * K + j) * GFS_TP, tgt + (size_t)sy * g.Wp + sxmin + xomin, ntgt * 16, &mbar[st]);
+        const uint32_t tx_cost = (uint32_t)(K * (nref + ntgt) * 16);
+        auto issue_cost = [&](int u) {      // lane 0 of cost warp 0: feature rows of block u -> cost stage u & 1
+            const int st = u & 1;
+            gfs_mbar_expect_tx(&mbar[st], tx_cost);
+            const int p0 = a0 - A - 1 + K * u;
+#pragma unroll 1
+            for (int j = 0; j < K; j++) {
+                const int sy = gfs_reflect1(p0 + j, H);
+                gfs_bulk_g2s(sRef + (st * K + j) * GFS_IW, ref + (size_t)sy * W + sxmin, nref * 16, &mbar[st]);
+                gfs_bulk_g2s(sTgt + (st * K + j) * GFS_TP, tgt + (size_t)sy * g.Wp + sxmin + xomin, ntgt * 16, &mbar[st]);
             }
         };
-        if (tid < 32) issue(0);
+        if (tid == 0) issue_cost(0);
         float4 r1[K], s1 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < K; j++) r1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         float cmin = 3.0e38f, cmax = -3.0e38f;
         for (int u = 0; u <= U; u++) {
             gfs_bar_sync(GFS_BAR_COST, GFS_THREADS);           // every cost thread is done with block u-1
-            if (tid < 32 && u + 1 <= U) issue(u + 1);
+            if (tid == 0 && u + 1 <= U) issue_cost(u + 1);
             const FeatF* rs = sRef + ((u & 1) * K) * GFS_IW + ia;
             const FeatF* ts = sTgt + ((u & 1) * K) * GFS_TP + it;
             float4* vs = VS1 + (u & 1) * ROWS * P1 + sl1 * P1 + c1;   // shared-memory row = j * NS + slice
             gfs_mbar_wait(&mbar[u & 1], (u >> 1) & 1);
-            if (u >= 3) gfs_bar_sync(GFS_BAR_EMPTY + (u & 1), 2 * GFS_THREADS);
+            if (u >= 2) gfs_bar_sync(GFS_BAR_EMPTY + (u & 1), 2 * GFS_THREADS);   // the filter warps are done with block u-2
 #pragma unroll
             for (int j = 0; j < K; j++) {
                 const FeatF fa = rs[j * GFS_IW];
@@ -340,7 +344,8 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
                 const float4 nw = make_float4(p01.x, p01.y, I2 * cs, cs);
                 vs[j * GFS_NS * P1] = gfs_ring_step<K>(r1, s1, nw, j);
             }
-            if (u >= 1) { __threadfence_block(); gfs_bar_arrive(GFS_BAR_FULL + (u & 1), 2 * GFS_THREADS); }
+            __threadfence_block();
+            gfs_bar_arrive(GFS_BAR_FULL + (u & 1), 2 * GFS_THREADS);   // VS1[u & 1] written, staged rows of block u consumed
         }
         // slice min / max of the raw cost: one atomic pair per warp (a warp = 32 columns of one slice)
         for (int o = 16; o > 0; o >>= 1) {
@@ -354,32 +359,29 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
     } else {
         // =========================== filter warps: H1, V2, H2 ===========================
         const int tid = threadIdx.x - GFS_THREADS;
-        float4* sGA = sm_gfs + L::oGA;
-        float4* sGB = sm_gfs + L::oGB;
+        GfsMoments* sGM = (GfsMoments*)(sm_gfs + L::oGM);
         float4* sIQ = sm_gfs + L::oIQ;
         // staged column ranges: (a,b) columns x0-A .. x0-A+AW-1 clamped into the image, q' columns x0 .. clamped
         const int xamin = max(x0 - A, 0), xamax = min(x0 - A + AW - 1, W - 1);
         const int nga = xamax - xamin + 1, niq = min(W, x0 + QW) - x0;
         const uint32_t tx_filter = (uint32_t)(K * (2 * nga + niq) * 16);
         const int n_iter = U + (bottom ? 1 : 0);
-        auto issue = [&](int u) {        // filter warp 7: rows of block u -> stage u & 1
-            const int st = u & 1, lane = tid & 31;
-            if (lane == 0) gfs_mbar_expect_tx(&mbar[2 + st], tx_filter);
-            __syncwarp();
-            if (lane < 3 * K) {
-                const int j = lane % K, which = lane / K;
-                const int abase = a0 + K * (u - 1);
-                if (which < 2) {
-                    const int ya = min(max(abase + j, 0), H - 1);
-                    gfs_bulk_g2s((which ? sGB : sGA) + (st * K + j) * P2, (which ? Grd : Gnm) + (size_t)ya * W + xamin, nga * 16, &mbar[2 + st]);
-                } else {
-                    const int rq = min(max(abase - A + j, 0), H - 1);
-                    gfs_bulk_g2s(sIQ + (st * K + j) * PQ, Gi + (size_t)rq * W + x0, niq * 16, &mbar[2 + st]);
-                }
+        const int lane = tid & 31;
+        // every operand of a bulk copy is CTA-uniform: one lane walks the rows (a per-lane copy would be serialised
+        // through the uniform datapath anyway)
+        auto issue_filter = [&](int u) {    // moment / guidance rows of block u -> filter stage u & 1
+            if (lane != 0) return;
+            const int st = u & 1;
+            gfs_mbar_expect_tx(&mbar[2 + st], tx_filter);
+            const int abase = a0 + K * (u - 1);
+#pragma unroll 1
+            for (int j = 0; j < K; j++) {
+                const int ya = min(max(abase + j, 0), H - 1), rq = min(max(abase - A + j, 0), H - 1);
+                gfs_bulk_g2s(sGM + (st * K + j) * P2, Gmom + (size_t)ya * W + xamin, nga * 32, &mbar[2 + st]);
+                gfs_bulk_g2s(sIQ + (st * K + j) * PQ, Gi + (size_t)rq * W + x0, niq * 16, &mbar[2 + st]);
             }
         };
         const bool loader = tid >= GFS_THREADS - 32;
-        if (loader) issue(1);
         // V2 role: (slice, (a,b) column); out-of-image columns read their mirror column
         const int sl2 = tid / AW, c2 = tid - sl2 * AW;
         const bool v2_on = tid < GFS_NS * AW;
@@ -394,22 +396,27 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
         const int hj = hrow / GFS_NS, hsl = hrow - hj * GFS_NS;
         const bool h_slice_ok = d0 + hsl < g.D;
         const int ga_shift = (x0 - A) - xamin + hrun * GFF_RUN;  // staged index of the run's first (a,b) column, before clamping
-        for (int u = 1; u <= n_iter; u++) {
+        for (int u = 0; u <= n_iter; u++) {
             const int abase = a0 + K * (u - 1);                // first (a,b) row of this block
             float4* VS2 = VS1 + (u & 1) * ROWS * P1;           // aliases the VS1 buffer consumed by this block's H1
-            if (u <= U) gfs_bar_sync(GFS_BAR_FULL + (u & 1), 2 * GFS_THREADS);
+            if (u <= U) gfs_bar_sync(GFS_BAR_FULL + (u & 1), 2 * GFS_THREADS);   // also: the cost warps are done with block u
             else gfs_bar_sync(GFS_BAR_FILTER, GFS_THREADS);    // every filter thread is done with block u-1
-            if (loader && u + 1 <= n_iter) issue(u + 1);
-            gfs_mbar_wait(&mbar[2 + (u & 1)], ((u - 1) >> 1) & 1);   // blocks 1, 2 are the first use of stages 1, 0
+            if (u >= 1) gfs_mbar_wait(&mbar[2 + (u & 1)], ((u - 1) >> 1) & 1);   // blocks 1, 2 are the first use of stages 1, 0
             // ---- H1: horizontal window + (a,b) epilogue ----
-            if (u <= U && hrun < NRUN1) {
+            if (u >= 1 && u <= U && hrun < NRUN1) {
                 float4* dst = AB + hrow * P2 + hrun * GFF_RUN;
                 const float4* src = VS2 + hrow * P1 + hrun * GFF_RUN;
-                const float4* ga = sGA + ((u & 1) * K + hj) * P2;
-                const float4* gb = sGB + ((u & 1) * K + hj) * P2;
-                gfs_h1<K>(src, ga, gb, ga_shift, nga, dst, min(GFF_RUN, AW - hrun * GFF_RUN), inv);
+                const GfsMoments* gm = sGM + ((u & 1) * K + hj) * P2;
+                gfs_h1<K>(src, gm, ga_shift, nga, dst, min(GFF_RUN, AW - hrun * GFF_RUN), inv);
             }
-            gfs_bar_sync(GFS_BAR_FILTER, GFS_THREADS);
+            if (u >= 1) gfs_bar_sync(GFS_BAR_FILTER, GFS_THREADS);
+            if (loader) {
+                if (u + 1 <= n_iter) issue_filter(u + 1);      // filter stage (u+1) & 1: last read by H1 / H2 of block u-1
+            }
+            if (u == 0) {                                      // block 0 only warms the level-1 rings up
+                if (2 <= U) { __threadfence_block(); gfs_bar_arrive(GFS_BAR_EMPTY, 2 * GFS_THREADS); }
+                continue;
+            }
             // ---- V2: vertical window over (a,b) ----
             if (v2_on) {
                 const float4* src = AB + sl2 * P2 + csrc;
@@ -429,7 +436,7 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
                     for (int j = 0; j < K; j++) dst[j * GFS_NS * P1] = gfs_ring_step<K>(r2, s2, src[j * GFS_NS * P2], j);
                 }
             }
-            gfs_bar_sync(GFS_BAR_FILTER, GFS_THREADS);
+            if (!LOADER_FREE || !loader) gfs_bar_sync(GFS_BAR_FILTER2, LOADER_FREE ? GFS_THREADS - 32 : GFS_THREADS);
             // ---- H2: horizontal window + q' ----
             if (hrun < NRUN2 && h_slice_ok) {
                 const int rq = abase - A + hj;
@@ -497,8 +504,8 @@ static inline bool gfs_supported(int H, int W, int win) {
 }
 
 template <int K>
-static asw_status gfs_launch(asw_ctx* ctx, const FeatF* fref, const FeatF* ftgt, const float4* Gi, const float4* Gnm,
-                             const float4* Grd, const int* guide_mm, GfsGeom g, const TadParams& tp, float* qv, uint32_t* slice_mm, float2* aff,
+static asw_status gfs_launch(asw_ctx* ctx, const FeatF* fref, const FeatF* ftgt, const float4* Gi, const GfsMoments* Gmom,
+                             const int* guide_mm, GfsGeom g, const TadParams& tp, float* qv, uint32_t* slice_mm, float2* aff,
                              int cn, int d_label0, unsigned long long* keys, float* agg) {
     constexpr int QW = GfsLayout<K>::QW;
     const size_t smem = GfsLayout<K>::bytes;
@@ -514,7 +521,7 @@ static asw_status gfs_launch(asw_ctx* ctx, const FeatF* fref, const FeatF* ftgt,
     ts.thr_c = (int)floorf(tp.thr_c); ts.add_c = (int)rintf(tp.add_c); ts.thr_g = tp.thr_g;
     ts.reg_r = (float)tp.reg_r; ts.reg = (float)tp.reg;
     LAUNCH(ctx, "gfs_filter", (k_gfs_filter<K><<<dim3(strips, groups, nb), 2 * GFS_THREADS, smem, ctx->stream>>>(
-                                  fref, ftgt, Gi, Gnm, Grd, guide_mm, g, ts, tp.c0, qv, slice_mm)));
+                                  fref, ftgt, Gi, Gmom, guide_mm, g, ts, tp.c0, qv, slice_mm)));
     LAUNCH(ctx, "gfs_affine", (k_gfs_affine<<<cdiv(cn, 128), 128, 0, ctx->stream>>>(slice_mm, cn, tp.c0, aff)));
     LAUNCH(ctx, "gfs_wta", (k_gfs_wta<<<dim3(cdiv(cdiv(g.W, 4), 128), g.H), 128, 0, ctx->stream>>>(
                                qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg)));
