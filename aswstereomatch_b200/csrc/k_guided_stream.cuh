@@ -226,9 +226,10 @@ struct GfsLayout {
     static constexpr int P1 = GFS_IW + 1, P2 = AW | 1, PQ = QW | 1;   // odd float4 pitches
     static constexpr int ROWS = GFS_NS * K;
     // float4 offsets
-    static constexpr int oVS1 = 0;                             // [2][ROWS][P1]  vertical sums of (I c, c); VS2 aliases the consumed buffer
+    static constexpr int oVS1 = 0;                             // [2][ROWS][P1]  vertical sums of (I c, c)
     static constexpr int oAB = oVS1 + 2 * ROWS * P1;           // [ROWS][P2]     (a0,a1,a2,b)
-    static constexpr int oRef = oAB + ROWS * P2;               // [2][K][64]     staged reference features
+    static constexpr int oVS2 = oAB + ROWS * P2;               // [ROWS][P2]     vertical sums of (a,b)
+    static constexpr int oRef = oVS2 + ROWS * P2;              // [2][K][64]     staged reference features
     static constexpr int oTgt = oRef + 2 * K * GFS_IW;         // [2][K][GFS_TP] staged target features (NS slices share them)
     static constexpr int oGM = oTgt + 2 * K * GFS_TP;          // [2][K][P2]     32-byte moment records (2 float4 each)
     static constexpr int oIQ = oGM + 2 * K * P2 * 2;           // [2][K][PQ]     guidance at the q' pixels
@@ -256,6 +257,7 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
     extern __shared__ float4 sm_gfs[];
     float4* VS1 = sm_gfs + L::oVS1;
     float4* AB = sm_gfs + L::oAB;
+    float4* VS2 = sm_gfs + L::oVS2;
     uint64_t* mbar = (uint64_t*)(sm_gfs + L::oBar);            // [0..1] cost stages, [2..3] filter stages
 
     const int H = g.H, W = g.W;
@@ -398,42 +400,39 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
         const int ga_shift = (x0 - A) - xamin + hrun * GFF_RUN;  // staged index of the run's first (a,b) column, before clamping
         for (int u = 0; u <= n_iter; u++) {
             const int abase = a0 + K * (u - 1);                // first (a,b) row of this block
-            float4* VS2 = VS1 + (u & 1) * ROWS * P1;           // aliases the VS1 buffer consumed by this block's H1
             if (u <= U) gfs_bar_sync(GFS_BAR_FULL + (u & 1), 2 * GFS_THREADS);   // also: the cost warps are done with block u
             else gfs_bar_sync(GFS_BAR_FILTER, GFS_THREADS);    // every filter thread is done with block u-1
             if (u >= 1) gfs_mbar_wait(&mbar[2 + (u & 1)], ((u - 1) >> 1) & 1);   // blocks 1, 2 are the first use of stages 1, 0
             // ---- H1: horizontal window + (a,b) epilogue ----
             if (u >= 1 && u <= U && hrun < NRUN1) {
                 float4* dst = AB + hrow * P2 + hrun * GFF_RUN;
-                const float4* src = VS2 + hrow * P1 + hrun * GFF_RUN;
+                const float4* src = VS1 + (u & 1) * ROWS * P1 + hrow * P1 + hrun * GFF_RUN;
                 const GfsMoments* gm = sGM + ((u & 1) * K + hj) * P2;
                 gfs_h1<K>(src, gm, ga_shift, nga, dst, min(GFF_RUN, AW - hrun * GFF_RUN), inv);
             }
+            if (u + 2 <= U) { __threadfence_block(); gfs_bar_arrive(GFS_BAR_EMPTY + (u & 1), 2 * GFS_THREADS); }   // VS1[u & 1] consumed
             if (u >= 1) gfs_bar_sync(GFS_BAR_FILTER, GFS_THREADS);
             if (loader) {
                 if (u + 1 <= n_iter) issue_filter(u + 1);      // filter stage (u+1) & 1: last read by H1 / H2 of block u-1
             }
-            if (u == 0) {                                      // block 0 only warms the level-1 rings up
-                if (2 <= U) { __threadfence_block(); gfs_bar_arrive(GFS_BAR_EMPTY, 2 * GFS_THREADS); }
-                continue;
-            }
+            if (u == 0) continue;                              // block 0 only warms the level-1 rings up
             // ---- V2: vertical window over (a,b) ----
             if (v2_on) {
                 const float4* src = AB + sl2 * P2 + csrc;
-                float4* dst = VS2 + sl2 * P1 + c2;
+                float4* dst = VS2 + sl2 * P2 + c2;
                 if (u == U + 1) {
                     // bottom of the image: ring = rows H-K .. H-1; output rows H-a .. H-1 (block rows 0 .. a-1)
 #pragma unroll
-                    for (int i = 0; i < A; i++) dst[i * GFS_NS * P1] = gfs_reflect_sum<K>(r2, K - A + i, false);
+                    for (int i = 0; i < A; i++) dst[i * GFS_NS * P2] = gfs_reflect_sum<K>(r2, K - A + i, false);
                 } else if (top && u == 1) {
                     // top of the image: ring <- rows 0 .. K-1; output rows 0 .. a (block rows a .. K-1)
 #pragma unroll
                     for (int j = 0; j < K; j++) r2[j] = src[j * GFS_NS * P2];
 #pragma unroll
-                    for (int i = 0; i <= A; i++) dst[(A + i) * GFS_NS * P1] = gfs_reflect_sum<K>(r2, i, true);
+                    for (int i = 0; i <= A; i++) dst[(A + i) * GFS_NS * P2] = gfs_reflect_sum<K>(r2, i, true);
                 } else {
 #pragma unroll
-                    for (int j = 0; j < K; j++) dst[j * GFS_NS * P1] = gfs_ring_step<K>(r2, s2, src[j * GFS_NS * P2], j);
+                    for (int j = 0; j < K; j++) dst[j * GFS_NS * P2] = gfs_ring_step<K>(r2, s2, src[j * GFS_NS * P2], j);
                 }
             }
             if (!LOADER_FREE || !loader) gfs_bar_sync(GFS_BAR_FILTER2, LOADER_FREE ? GFS_THREADS - 32 : GFS_THREADS);
@@ -445,14 +444,14 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
                     const int len = min(GFF_RUN, QW - hrun * GFF_RUN);
                     const float4* iq = sIQ + ((u & 1) * K + hj) * PQ;
                     float q[GFF_RUN];
-                    gfs_h2<K>(VS2 + hrow * P1 + hrun * GFF_RUN, iq, hrun * GFF_RUN, niq, q);
-                    float4* out = (float4*)(qv + ((size_t)(d0 + hsl) * H + rq) * g.Wq + xq0);
+                    gfs_h2<K>(VS2 + hrow * P2 + hrun * GFF_RUN, iq, hrun * GFF_RUN, niq, q);
+                    float4* out = (float4*)(qv + ((size_t)rq * g.D + (d0 + hsl)) * g.Wq + xq0);
                     out[0] = make_float4(q[0], q[1], q[2], q[3]);
                     if (len > 4) out[1] = make_float4(q[4], q[5], q[6], q[7]);
                 }
             }
-            if (u + 2 <= U) { __threadfence_block(); gfs_bar_arrive(GFS_BAR_EMPTY + (u & 1), 2 * GFS_THREADS); }
-            // the next block's H1 rewrites AB (last read by V2, one filter barrier back)
+            // the next block's H1 rewrites AB (last read by V2, one filter barrier back); VS2 is rewritten after the next
+            // block's first filter barrier, which every filter thread reaches only after this H2
         }
     }
 }
@@ -466,15 +465,15 @@ __global__ void k_gfs_affine(const uint32_t* __restrict__ slice_mm, int D, float
     aff[d] = make_float2(sf, (float)fma((double)c0, (double)sf, (double)hf));
 }
 
-// q' volume [D][H][Wq] -> normalised costs -> WTA keys (strict <, ascending d, NaN / inf never win; A.cpp:3032-3048).
+// q' volume [H][D][Wq] -> normalised costs -> WTA keys (strict <, ascending d, NaN / inf never win; A.cpp:3032-3048).
 // One thread = 4 adjacent pixels; the D loads of a thread are independent (unrolled by 8).
 __global__ void __launch_bounds__(128)
 k_gfs_wta(const float* __restrict__ qv, const float2* __restrict__ aff, int D, int H, int W, int Wq, int d_label0,
           unsigned long long* __restrict__ keys, float* __restrict__ agg) {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     if (x4 >= W) return;
-    const size_t slice = (size_t)H * Wq;
-    const float* p = qv + (size_t)y * Wq + x4;
+    const size_t slice = (size_t)Wq;                         // q' is [H][D][Wq]: the D slices of a row are contiguous
+    const float* p = qv + (size_t)y * D * Wq + x4;
     float best[4] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
     int bd[4] = {0, 0, 0, 0};
     const size_t n = (size_t)H * W;
