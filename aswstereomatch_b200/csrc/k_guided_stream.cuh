@@ -281,14 +281,14 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
 
     // source columns of the strip: REFLECT_101 only folds the range, so [sxmin, sxmax] is contiguous
     int sxmin, sxmax;
-    {   // the fold maps the interval x0-2A .. x0-2A+63 onto an interval; its ends are among these four points
-        const int lo = x0 - 2 * A, hi = lo + GFS_IW - 1;
-        const int cand[4] = {lo, hi, min(max(0, lo), hi), min(max(W - 1, lo), hi)};
-        sxmin = 0x7fffffff; sxmax = -1;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int f = border_idx(cand[q], W, 1);
-            sxmin = min(sxmin, f); sxmax = max(sxmax, f);
+    {   // the fold maps the interval x0-2A .. x0-2A+63 onto an interval whose ends are images of the interval's
+        // ends or of the fold points k * (W-1) inside it (narrow images fold more than once)
+        const int lo = x0 - 2 * A, hi = lo + GFS_IW - 1, per = W - 1;
+        sxmin = min(border_idx(lo, W, 1), border_idx(hi, W, 1));
+        sxmax = max(border_idx(lo, W, 1), border_idx(hi, W, 1));
+        int k = lo >= 0 ? (lo + per - 1) / per : -((-lo) / per);           // ceil(lo / per)
+        for (; k * per <= hi; k++) {
+            if (k & 1) sxmax = W - 1; else sxmin = 0;
         }
     }
     const int nref = sxmax - sxmin + 1;

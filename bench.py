@@ -31,10 +31,12 @@ sys.path.insert(0, ROOT)
 H, W, D = 1080, 1920, 256
 WIN, EPS = 9, 1e-4
 VIEWS = 2
-# algorithmic bytes per disparity evaluation (SURVEY 8d, 3-pass model = 52 B/DE), split over our two kernels:
-#   gf_ab (model passes A+B: write p 4 + read L,R 6 + read p 4 + read I 3 + write a,b 16) = 33 B/DE
-#   gf_q  (model pass  C : read a,b 16 + read I 3)                                         = 19 B/DE
-ALG_BYTES = {"gf_ab": 33.0, "gf_q": 19.0}
+# algorithmic bytes per disparity evaluation (SURVEY 8d, 3-pass model = 52 B/DE: write p 4 + read L,R 6; read p 4 +
+# I 3, write a,b 16; read a,b 16 + I 3).  The streaming kernel gfs_filter runs all three model passes on chip, so
+# it is charged the whole 52 B/DE; the older tiled pair splits it 33 (gf_ab) + 19 (gf_q).
+ALG_BYTES = {"gfs_filter": 52.0, "gf_ab": 33.0, "gf_q": 19.0}
+# FP32-issue view of the same kernel (~80 lane-instructions per DE for the guided filter)
+ALG_LANE_INSTR = {"gfs_filter": 80.0}
 WORKLOAD = ("cfg5: batch of 1920x1080 synthetic pairs, 256 disparities, GuidedF_2 (r=9, eps=1e-4) left+right view "
             "+ LR check + weighted-median refine, pair-sharded")
 
@@ -255,8 +257,9 @@ def main():
             "ms_per_step": ms_res / args.steps, "ms_per_frame": ms_res / args.steps / P, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu": P, "image": [W, H], "disparities": D, "views": VIEWS,
-                       "l2": "inputs larger than L2: every step streams 0.8 GB of images and >10 GB of per-slice "
-                             "intermediates per GPU through the 126 MB L2", "result_check": ok},
+                       "l2": "inputs larger than L2: every step streams 0.8 GB of images and, per view, a 2.1 GB "
+                             "filtered-cost volume (written by the filter kernel, read by the WTA pass) through the "
+                             "126 MB L2", "result_check": ok},
             "clocks": clk,
             "e2e": {"value": e2e, "unit": "MDE/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(hL.nbytes + hR.nbytes), "d2h_bytes_per_step": int(hD.nbytes)},
@@ -265,8 +268,17 @@ def main():
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "avg_launch_ms": tot_ms / n_l, "share_of_step": tot_ms / total_prof,
                          "alg_bytes_per_de": alg, "de_per_launch": de_per_launch},
+            "fp32_issue": None,
             "kernels_ms_per_step": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]},
         }
+        if name in ALG_LANE_INSTR:
+            # secondary view: the kernel moves far fewer HBM bytes than the 3-pass model, its own bound is the FP32
+            # issue rate (148 SMs x 128 lanes x SM clock)
+            sm_clk = (clk or {}).get("sm_mhz") or 1965.0
+            peak_li = 148 * 128 * sm_clk * 1e6
+            ach_li = ALG_LANE_INSTR[name] * de_per_launch / (tot_ms / n_l * 1e-3)
+            line["fp32_issue"] = {"alg_lane_instr_per_de": ALG_LANE_INSTR[name], "achieved": ach_li, "peak": peak_li,
+                                  "unit": "lane-instr/s", "frac": ach_li / peak_li}
         if not args.no_cpu_baseline:
             try:
                 from oracle import orc
