@@ -303,6 +303,187 @@ static asw_status geo_tile_segments(asw_ctx* ctx, const float* dref, const float
     return ASW_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// diagonal-blocked aggregation (full chunks of 32 candidates on interior segments).  Same CTA tile as
+// k_geo_agg_tile (one image row x 128 pixels x 32 candidates) but a thread owns 4 adjacent pixels x 4 ADJACENT
+// candidates: the operands addressed at (x - d) then fall on a diagonal, 7 distinct values for the 16
+// (pixel, candidate) pairs, fetched as one aligned 8-wide window (2 LDS.128) instead of one quad per candidate
+// (4 LDS.128): 6 LDS.128 per tap instead of 10 for the same 16 evaluations.  Because a warp's 4 candidates start
+// at a multiple of 4, the window alignment of the target distances is CTA-uniform: one staged copy, no skewed
+// replicas.  Staging is asynchronous: the next 12-tap chunk of distance rows (and the next window row's colours)
+// are copied global -> shared with cp.async (4-byte, clamped columns) while the current chunk is evaluated.
+// ------------------------------------------------------------------------------------------------
+#define GD_DRW 160           // staged target-distance row: 4*31 + 28 + 8 cells
+__device__ __forceinline__ void gd_cp_async4(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void gd_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void gd_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// BORDER: the segment touches the image edge where the window's sample column is clamped BEFORE the disparity
+// shift (right edge for LEFT, left edge for RIGHT).  Those taps read the target colour at the shifted EDGE column,
+// which depends on the candidate only: 4 values per thread and window row, selected per evaluation.
+template <int SIGN, bool BORDER>
+__global__ void __launch_bounds__(GT_THREADS, 2)
+k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, const uint32_t* __restrict__ pref,
+               const uint32_t* __restrict__ ptgt, GeoGeom g, int seg_first, unsigned long long* __restrict__ keys,
+               float* __restrict__ agg) {
+    extern __shared__ __align__(16) float sm_gd[];
+    const int W = g.W, H = g.H, win = g.win, h = g.h;
+    const int CLW = (GT_X + 2 * h + 7) & ~3;                  // reference colour row (cells)
+    const int CRW = (GD_DRW + 2 * h + 7) & ~3;                // target colour row
+    float* DLs = sm_gd;                                       // [2][GT_TC][GT_X]
+    float* DRs = DLs + 2 * GT_TC * GT_X;                      // [2][GT_TC][GD_DRW]
+    uint32_t* CL = (uint32_t*)(DRs + 2 * GT_TC * GD_DRW);     // [2][4][CLW]   4 copies skewed by 0..3 cells
+    uint32_t* CR = CL + 2 * 4 * CLW;                          // [2][4][CRW]
+    const int tid = threadIdx.x, pg = tid & 31, ds = tid >> 5;
+    const int y = blockIdx.y, xb = (seg_first + blockIdx.x) * GT_X;
+    const int c0 = blockIdx.z * 32;
+    const int d_lo = g.d_first + c0;
+    const size_t n = (size_t)H * W;
+    const size_t rowoff = (size_t)y * W;
+    // staged cell 0 <-> image column (before clamping).  LEFT: a thread's 8-wide window starts at
+    // x - (d_lo + 4 ds) - 4 = oDR + (4 pg - 4 ds + 28); RIGHT: at x + d_lo + 4 ds = oDR + (4 pg + 4 ds)
+    const int oDR = SIGN > 0 ? xb - d_lo - 32 : xb + d_lo;
+    const int oCL = xb - h;
+    const int oCR = oDR - h;
+    const int e0 = SIGN > 0 ? 4 * pg - 4 * ds + 28 : 4 * pg + 4 * ds;   // window start (cells), multiple of 4
+    float fn[16], fd[16];
+#pragma unroll
+    for (int a = 0; a < 16; a++) { fn[a] = 0.0f; fd[a] = 0.0f; }
+
+    // chunk c of the window: row j = c / 3, taps i0 .. i1 of that row (3 chunks per row: 12 + 12 + rest)
+    const int cpr = (win + GT_TC - 1) / GT_TC, nchunk = win * cpr;
+    auto stage_dist = [&](int c, int buf) {
+        const int j = c / cpr, i0 = (c - j * cpr) * GT_TC, cnt = min(GT_TC, win - i0);
+        float* dl = DLs + buf * GT_TC * GT_X;
+        float* dr = DRs + buf * GT_TC * GD_DRW;
+        for (int q = tid; q < cnt * GT_X; q += GT_THREADS) {
+            const int tt = q >> 7, xx = q & (GT_X - 1);
+            gd_cp_async4(dl + q, dref + (size_t)(j * win + i0 + tt) * n + rowoff + min(xb + xx, W - 1));
+        }
+        for (int q = tid; q < cnt * GD_DRW; q += GT_THREADS) {
+            const int tt = q / GD_DRW, e = q - tt * GD_DRW;
+            gd_cp_async4(dr + q, dtgt + (size_t)(j * win + i0 + tt) * n + rowoff + clampi(oDR + e, 0, W - 1));
+        }
+    };
+    auto stage_colour = [&](int j, int buf) {
+        const int ny = clampi(y - h + j, 0, H - 1);
+        uint32_t* cl = CL + buf * 4 * CLW;
+        uint32_t* cr = CR + buf * 4 * CRW;
+        for (int e = tid; e < CLW; e += GT_THREADS) {
+            const uint32_t* src = pref + (size_t)ny * W + clampi(oCL + e, 0, W - 1);
+#pragma unroll
+            for (int r = 0; r < 4; r++) if (e - r >= 0) gd_cp_async4(cl + r * CLW + e - r, src);
+        }
+        for (int e = tid; e < CRW; e += GT_THREADS) {
+            const uint32_t* src = ptgt + (size_t)ny * W + clampi(oCR + e, 0, W - 1);
+#pragma unroll
+            for (int r = 0; r < 4; r++) if (e - r >= 0) gd_cp_async4(cr + r * CRW + e - r, src);
+        }
+    };
+    stage_colour(0, 0);
+    stage_dist(0, 0);
+    gd_cp_commit();
+    for (int c = 0; c < nchunk; c++) {
+        const int j = c / cpr, i0 = (c - j * cpr) * GT_TC, i1 = min(i0 + GT_TC, win);
+        gd_cp_wait_all();
+        __syncthreads();                                       // chunk c (and row j's colours) landed; chunk c-1 consumed
+        if (c + 1 < nchunk) {
+            const int jn = (c + 1) / cpr;
+            if (jn != j) stage_colour(jn, jn & 1);
+            stage_dist(c + 1, (c + 1) & 1);
+            gd_cp_commit();
+        }
+        const float* dl = DLs + (c & 1) * GT_TC * GT_X + 4 * pg;
+        const float* dr = DRs + (c & 1) * GT_TC * GD_DRW + e0;
+        const uint32_t* cl = CL + (j & 1) * 4 * CLW + 4 * pg;
+        const uint32_t* cr = CR + (j & 1) * 4 * CRW + e0;
+        uint32_t edge[4];
+        if (BORDER) {
+            const int ny = clampi(y - h + j, 0, H - 1);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int d = d_lo + 4 * ds + k;
+                edge[k] = __ldg(ptgt + (size_t)ny * W + (SIGN > 0 ? max(0, W - 1 - d) : min(d, W - 1)));
+            }
+        }
+        for (int i = i0; i < i1; i++) {
+            const int tt = i - i0, r = i & 3;
+            const float4 dl4 = *(const float4*)(dl + tt * GT_X);
+            const float4 dra = *(const float4*)(dr + tt * GD_DRW), drb = *(const float4*)(dr + tt * GD_DRW + 4);
+            // colour cell of pixel quad start: oCL + (4 pg + i) -> copy r = i & 3 at aligned index 4 pg + i - r
+            const uint4 cl4 = *(const uint4*)(cl + r * CLW + i - r);
+            const uint4 cra = *(const uint4*)(cr + r * CRW + i - r), crb = *(const uint4*)(cr + r * CRW + i - r + 4);
+            const float dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+            const float drv[8] = {dra.x, dra.y, dra.z, dra.w, drb.x, drb.y, drb.z, drb.w};
+            const uint32_t clv[4] = {cl4.x, cl4.y, cl4.z, cl4.w};
+            const uint32_t crv[8] = {cra.x, cra.y, cra.z, cra.w, crb.x, crb.y, crb.z, crb.w};
+#pragma unroll
+            for (int p = 0; p < 4; p++) {
+                const int nx = xb + 4 * pg + p - h + i;                       // sample column before clamping
+                const bool clamped = BORDER && (SIGN > 0 ? nx > W - 1 : nx < 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int w = SIGN > 0 ? p - k + 4 : p + k;               // position on the diagonal window
+                    const float t = __fmul_rn(dlv[p], drv[w]);                // A.cpp:1488-1489
+                    const uint32_t cright = BORDER ? (clamped ? edge[k] : crv[w]) : crv[w];
+                    const float cd = (float)__vsadu4(clv[p], cright);         // getColorDist
+                    fn[k * 4 + p] = fmaf(t, cd, fn[k * 4 + p]);
+                    fd[k * 4 + p] = __fadd_rn(fd[k * 4 + p], t);
+                }
+            }
+        }
+    }
+    const int x0 = xb + 4 * pg;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const int x = x0 + p;
+        if (x >= W) continue;
+        unsigned long long best = WTA_KEY_EMPTY;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int c = c0 + 4 * ds + k;
+            const double E = (double)fn[k * 4 + p] / (double)fd[k * 4 + p];
+            if (agg) agg[(size_t)c * n + rowoff + x] = (float)E;
+            best = min(best, wta_key_d(E, g.d_first + c));
+        }
+        atomicMin(&keys[rowoff + x], best);
+    }
+}
+
+template <int SIGN, bool BORDER>
+static asw_status geo_diag_launch(asw_ctx* ctx, const float* dref, const float* dtgt, const uint32_t* cref, const uint32_t* ctgt,
+                                  GeoGeom g, int seg_first, int seg_count, int n_chunks, unsigned long long* keys, float* agg) {
+    if (seg_count <= 0 || n_chunks <= 0) return ASW_OK;
+    const int h = g.h;
+    const int CLW = (GT_X + 2 * h + 7) & ~3, CRW = (GD_DRW + 2 * h + 7) & ~3;
+    size_t smem = (2 * (size_t)GT_TC * GT_X + 2 * (size_t)GT_TC * GD_DRW + 8 * (size_t)(CLW + CRW)) * sizeof(float);
+    cudaFuncSetAttribute(k_geo_agg_diag<SIGN, BORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    LAUNCH(ctx, BORDER ? "geo_aggregate_border" : "geo_aggregate",
+           (k_geo_agg_diag<SIGN, BORDER><<<dim3(seg_count, g.H, n_chunks), GT_THREADS, smem, ctx->stream>>>(
+                                     dref, dtgt, cref, ctgt, g, seg_first, keys, agg)));
+    return ASW_OK;
+}
+// a range of segments: full chunks of 32 candidates through the diagonal kernel, the remainder through the tile kernel
+template <bool BORDER>
+static asw_status geo_segments(asw_ctx* ctx, const float* dref, const float* dtgt, const uint32_t* cref,
+                               const uint32_t* ctgt, GeoGeom g, int seg_first, int seg_count,
+                               unsigned long long* keys, float* agg) {
+    if (getenv("ASW_GEO_TILE")) return geo_tile_segments<BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, keys, agg);
+    const int full = g.n_cand / 32, rem = g.n_cand - full * 32;
+    if (g.sign > 0) ASW_TRY((geo_diag_launch<1, BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full, keys, agg)));
+    else ASW_TRY((geo_diag_launch<-1, BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full, keys, agg)));
+    if (rem > 0) {
+        const int kc = (rem + 7) / 8;
+        if (kc == 4) ASW_TRY((geo_tile_launch<BORDER, 4>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
+        else if (kc == 3) ASW_TRY((geo_tile_launch<BORDER, 3>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
+        else if (kc == 2) ASW_TRY((geo_tile_launch<BORDER, 2>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
+        else ASW_TRY((geo_tile_launch<BORDER, 1>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
+    }
+    return ASW_OK;
+}
+
 __global__ void k_pack_bgrx(const uint8_t* __restrict__ img, size_t n, uint32_t* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -375,8 +556,8 @@ static asw_status dev_geodesic(asw_ctx* ctx, const uint8_t* dL, const uint8_t* d
     else { int_first = h > 0 ? 1 : 0; int_count = nseg - int_first; }
     if (int_count < 0) int_count = 0;
     if (int_count > nseg - int_first) int_count = nseg - int_first;
-    ASW_TRY(geo_tile_segments<false>(ctx, dref, dtgt, cref, ctgt, g, int_first, int_count, keys, agg_dev));
-    ASW_TRY(geo_tile_segments<true>(ctx, dref, dtgt, cref, ctgt, g, 0, int_first, keys, agg_dev));
-    ASW_TRY(geo_tile_segments<true>(ctx, dref, dtgt, cref, ctgt, g, int_first + int_count, nseg - int_first - int_count, keys, agg_dev));
+    ASW_TRY(geo_segments<false>(ctx, dref, dtgt, cref, ctgt, g, int_first, int_count, keys, agg_dev));
+    ASW_TRY(geo_segments<true>(ctx, dref, dtgt, cref, ctgt, g, 0, int_first, keys, agg_dev));
+    ASW_TRY(geo_segments<true>(ctx, dref, dtgt, cref, ctgt, g, int_first + int_count, nseg - int_first - int_count, keys, agg_dev));
     return keys_to_disp(ctx, keys, n, disp_dev);
 }

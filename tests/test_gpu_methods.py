@@ -62,6 +62,18 @@ def test_geodesic(ctx, H, W, D, win, disp_type, seed):
     assert (d == d_ref).mean() >= AGREE
 
 
+@pytest.mark.parametrize("H,W,D,win,disp_type,seed", [(20, 300, 33, 7, 0, 11), (18, 290, 40, 9, 1, 12), (14, 210, 32, 35, 0, 13),
+                                                       (16, 400, 70, 5, 1, 14)])
+def test_geodesic_wide_many_candidates(ctx, H, W, D, win, disp_type, seed):
+    """>= 32 candidates and rows longer than one 128-pixel segment: the diagonal-blocked kernel on interior and
+    edge segments (pre-shift clamp), plus the tile kernel on the candidate remainder"""
+    L, R, _ = make_pair(H, W, D, seed)
+    d, e = ctx.computeAdaptiveWeight_geodesic(L, R, disp_type, win, 0, D, agg=True, strict=True)
+    d_ref, e_ref = orc.asw_geodesic(L, R, disp_type, win, 0, D, agg=True)
+    assert rel_err(e, e_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+
+
 @pytest.mark.parametrize("H,W,D,sS,sR,seed", [(48, 64, 8, 10, 10, 1), (120, 160, 8, 10, 10, 2), (60, 90, 6, 7, 12, 3)])
 def test_bilateral_grid(ctx, H, W, D, sS, sR, seed):
     L, R, _ = make_pair(H, W, D, seed)
