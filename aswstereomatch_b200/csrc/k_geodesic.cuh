@@ -74,6 +74,79 @@ k_geo_dist(const uint32_t* __restrict__ ext, int H, int W, int win, float* __res
     }
 }
 
+// Window size as a template constant: the DP row (distances + the colours of the previous and the current window
+// row) lives in registers instead of local memory; the row update runs in place with one saved neighbour.
+template <int WIN>
+__global__ void __launch_bounds__(128)
+k_geo_dist_t(const uint32_t* __restrict__ ext, int H, int W, float* __restrict__ dist) {
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    constexpr int h = WIN / 2;
+    const int Wp = W + 2 * (h + 1);
+    const size_t n = (size_t)H * W, p = (size_t)y * W + x;
+    int d[WIN + 2];
+    uint32_t pprev[WIN + 2], pcur[WIN + 2];
+    // ---- backward sweep: rows WIN..1, cols WIN..1; neighbours (r,c+1), (r+1,c+1), (r+1,c), (r+1,c-1) ----
+#pragma unroll
+    for (int c = 0; c <= WIN + 1; c++) { d[c] = GEO_INF; pprev[c] = ext[(size_t)(y + WIN + 1) * Wp + x + c]; }
+#pragma unroll 1
+    for (int r = WIN; r >= 1; r--) {
+        const uint32_t* row = ext + (size_t)(y + r) * Wp + x;
+#pragma unroll
+        for (int c = 0; c <= WIN + 1; c++) pcur[c] = row[c];
+        int old_right = d[WIN + 1];                                 // previous row's value right of the current cell
+        d[WIN + 1] = GEO_INF;
+#pragma unroll
+        for (int c = WIN; c >= 1; c--) {
+            const int old_c = d[c];
+            const uint32_t me = pcur[c];
+            int v = (r == h + 1 && c == h + 1) ? 0 : GEO_INF;            // A.cpp:1416-1417
+            v = min(v, d[c + 1] + (int)__vsadu4(pcur[c + 1], me));        // right (already updated)
+            v = min(v, old_right + (int)__vsadu4(pprev[c + 1], me));      // bottom-right
+            v = min(v, old_c + (int)__vsadu4(pprev[c], me));              // bottom
+            v = min(v, d[c - 1] + (int)__vsadu4(pprev[c - 1], me));       // bottom-left (not yet updated)
+            d[c] = min(v, GEO_INF);
+            old_right = old_c;
+        }
+        d[0] = GEO_INF;
+#pragma unroll
+        for (int c = 1; c <= WIN; c++) dist[(size_t)((r - 1) * WIN + (c - 1)) * n + p] = (float)d[c];
+#pragma unroll
+        for (int c = 0; c <= WIN + 1; c++) pprev[c] = pcur[c];
+    }
+    // ---- forward sweep: rows 1..WIN, cols 1..WIN; neighbours (r,c-1), (r-1,c-1), (r-1,c), (r-1,c+1) ----
+#pragma unroll
+    for (int c = 0; c <= WIN + 1; c++) { d[c] = GEO_INF; pprev[c] = ext[(size_t)y * Wp + x + c]; }
+#pragma unroll 1
+    for (int r = 1; r <= WIN; r++) {
+        const uint32_t* row = ext + (size_t)(y + r) * Wp + x;
+        float back[WIN];
+#pragma unroll
+        for (int c = 0; c < WIN; c++) back[c] = dist[(size_t)((r - 1) * WIN + c) * n + p];   // left by the backward sweep
+#pragma unroll
+        for (int c = 0; c <= WIN + 1; c++) pcur[c] = row[c];
+        int old_left = d[0];
+        d[0] = GEO_INF;
+#pragma unroll
+        for (int c = 1; c <= WIN; c++) {
+            const int old_c = d[c];
+            const uint32_t me = pcur[c];
+            int v = (int)back[c - 1];
+            v = min(v, d[c - 1] + (int)__vsadu4(pcur[c - 1], me));        // left (already updated)
+            v = min(v, old_left + (int)__vsadu4(pprev[c - 1], me));       // up-left
+            v = min(v, old_c + (int)__vsadu4(pprev[c], me));              // up
+            v = min(v, d[c + 1] + (int)__vsadu4(pprev[c + 1], me));       // up-right (not yet updated)
+            d[c] = min(v, GEO_INF);
+            old_left = old_c;
+        }
+        d[WIN + 1] = GEO_INF;
+#pragma unroll
+        for (int c = 1; c <= WIN; c++) dist[(size_t)((r - 1) * WIN + (c - 1)) * n + p] = (float)d[c];
+#pragma unroll
+        for (int c = 0; c <= WIN + 1; c++) pprev[c] = pcur[c];
+    }
+}
+
 #define GEO_Q 4
 struct GeoGeom { int H, W, win, h, sign, d_first, n_cand; };
 
@@ -323,11 +396,13 @@ __device__ __forceinline__ void gd_cp_wait_all() { asm volatile("cp.async.wait_g
 // BORDER: the segment touches the image edge where the window's sample column is clamped BEFORE the disparity
 // shift (right edge for LEFT, left edge for RIGHT).  Those taps read the target colour at the shifted EDGE column,
 // which depends on the candidate only: 4 values per thread and window row, selected per evaluation.
-template <int SIGN, bool BORDER>
-__global__ void __launch_bounds__(GT_THREADS, 2)
+// NW warps per CTA = 4 NW candidates per CTA (8 for full chunks of 32; fewer for the candidate remainder).
+template <int SIGN, bool BORDER, int NW>
+__global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1)
 k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, const uint32_t* __restrict__ pref,
-               const uint32_t* __restrict__ ptgt, GeoGeom g, int seg_first, unsigned long long* __restrict__ keys,
-               float* __restrict__ agg) {
+               const uint32_t* __restrict__ ptgt, GeoGeom g, int seg_first, int cand_first,
+               unsigned long long* __restrict__ keys, float* __restrict__ agg) {
+    constexpr int NT = 32 * NW;
     extern __shared__ __align__(16) float sm_gd[];
     const int W = g.W, H = g.H, win = g.win, h = g.h;
     const int CLW = (GT_X + 2 * h + 7) & ~3;                  // reference colour row (cells)
@@ -338,7 +413,7 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
     uint32_t* CR = CL + 2 * 4 * CLW;                          // [2][4][CRW]
     const int tid = threadIdx.x, pg = tid & 31, ds = tid >> 5;
     const int y = blockIdx.y, xb = (seg_first + blockIdx.x) * GT_X;
-    const int c0 = blockIdx.z * 32;
+    const int c0 = cand_first + blockIdx.z * 32;
     const int d_lo = g.d_first + c0;
     const size_t n = (size_t)H * W;
     const size_t rowoff = (size_t)y * W;
@@ -358,11 +433,11 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
         const int j = c / cpr, i0 = (c - j * cpr) * GT_TC, cnt = min(GT_TC, win - i0);
         float* dl = DLs + buf * GT_TC * GT_X;
         float* dr = DRs + buf * GT_TC * GD_DRW;
-        for (int q = tid; q < cnt * GT_X; q += GT_THREADS) {
+        for (int q = tid; q < cnt * GT_X; q += NT) {
             const int tt = q >> 7, xx = q & (GT_X - 1);
             gd_cp_async4(dl + q, dref + (size_t)(j * win + i0 + tt) * n + rowoff + min(xb + xx, W - 1));
         }
-        for (int q = tid; q < cnt * GD_DRW; q += GT_THREADS) {
+        for (int q = tid; q < cnt * GD_DRW; q += NT) {
             const int tt = q / GD_DRW, e = q - tt * GD_DRW;
             gd_cp_async4(dr + q, dtgt + (size_t)(j * win + i0 + tt) * n + rowoff + clampi(oDR + e, 0, W - 1));
         }
@@ -371,12 +446,12 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
         const int ny = clampi(y - h + j, 0, H - 1);
         uint32_t* cl = CL + buf * 4 * CLW;
         uint32_t* cr = CR + buf * 4 * CRW;
-        for (int e = tid; e < CLW; e += GT_THREADS) {
+        for (int e = tid; e < CLW; e += NT) {
             const uint32_t* src = pref + (size_t)ny * W + clampi(oCL + e, 0, W - 1);
 #pragma unroll
             for (int r = 0; r < 4; r++) if (e - r >= 0) gd_cp_async4(cl + r * CLW + e - r, src);
         }
-        for (int e = tid; e < CRW; e += GT_THREADS) {
+        for (int e = tid; e < CRW; e += NT) {
             const uint32_t* src = ptgt + (size_t)ny * W + clampi(oCR + e, 0, W - 1);
 #pragma unroll
             for (int r = 0; r < 4; r++) if (e - r >= 0) gd_cp_async4(cr + r * CRW + e - r, src);
@@ -444,6 +519,7 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const int c = c0 + 4 * ds + k;
+            if (c >= g.n_cand) continue;
             const double E = (double)fn[k * 4 + p] / (double)fd[k * 4 + p];
             if (agg) agg[(size_t)c * n + rowoff + x] = (float)E;
             best = min(best, wta_key_d(E, g.d_first + c));
@@ -452,36 +528,48 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
     }
 }
 
-template <int SIGN, bool BORDER>
+template <int SIGN, bool BORDER, int NW>
 static asw_status geo_diag_launch(asw_ctx* ctx, const float* dref, const float* dtgt, const uint32_t* cref, const uint32_t* ctgt,
-                                  GeoGeom g, int seg_first, int seg_count, int n_chunks, unsigned long long* keys, float* agg) {
+                                  GeoGeom g, int seg_first, int seg_count, int cand_first, int n_chunks,
+                                  unsigned long long* keys, float* agg) {
     if (seg_count <= 0 || n_chunks <= 0) return ASW_OK;
     const int h = g.h;
     const int CLW = (GT_X + 2 * h + 7) & ~3, CRW = (GD_DRW + 2 * h + 7) & ~3;
     size_t smem = (2 * (size_t)GT_TC * GT_X + 2 * (size_t)GT_TC * GD_DRW + 8 * (size_t)(CLW + CRW)) * sizeof(float);
-    cudaFuncSetAttribute(k_geo_agg_diag<SIGN, BORDER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_geo_agg_diag<SIGN, BORDER, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     LAUNCH(ctx, BORDER ? "geo_aggregate_border" : "geo_aggregate",
-           (k_geo_agg_diag<SIGN, BORDER><<<dim3(seg_count, g.H, n_chunks), GT_THREADS, smem, ctx->stream>>>(
-                                     dref, dtgt, cref, ctgt, g, seg_first, keys, agg)));
+           (k_geo_agg_diag<SIGN, BORDER, NW><<<dim3(seg_count, g.H, n_chunks), 32 * NW, smem, ctx->stream>>>(
+                                     dref, dtgt, cref, ctgt, g, seg_first, cand_first, keys, agg)));
     return ASW_OK;
 }
-// a range of segments: full chunks of 32 candidates through the diagonal kernel, the remainder through the tile kernel
+// a range of segments: full chunks of 32 candidates with 8 warps per CTA, the candidate remainder with as many warps
+// as it needs (4 candidates per warp)
+template <int SIGN, bool BORDER>
+static asw_status geo_segments_signed(asw_ctx* ctx, const float* dref, const float* dtgt, const uint32_t* cref,
+                                      const uint32_t* ctgt, GeoGeom g, int seg_first, int seg_count,
+                                      unsigned long long* keys, float* agg) {
+    const int full = g.n_cand / 32, rem = g.n_cand - full * 32;
+    ASW_TRY((geo_diag_launch<SIGN, BORDER, 8>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, 0, full, keys, agg)));
+    const int nw = (rem + 3) / 4, c1 = full * 32;
+#define GEO_REM(NWV) ASW_TRY((geo_diag_launch<SIGN, BORDER, NWV>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, c1, 1, keys, agg)))
+    switch (nw) {
+        case 1: GEO_REM(1); break;
+        case 2: GEO_REM(2); break;
+        case 3: case 4: GEO_REM(4); break;
+        case 5: case 6: GEO_REM(6); break;
+        case 7: case 8: GEO_REM(8); break;
+        default: break;
+    }
+#undef GEO_REM
+    return ASW_OK;
+}
 template <bool BORDER>
 static asw_status geo_segments(asw_ctx* ctx, const float* dref, const float* dtgt, const uint32_t* cref,
                                const uint32_t* ctgt, GeoGeom g, int seg_first, int seg_count,
                                unsigned long long* keys, float* agg) {
     if (getenv("ASW_GEO_TILE")) return geo_tile_segments<BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, keys, agg);
-    const int full = g.n_cand / 32, rem = g.n_cand - full * 32;
-    if (g.sign > 0) ASW_TRY((geo_diag_launch<1, BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full, keys, agg)));
-    else ASW_TRY((geo_diag_launch<-1, BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full, keys, agg)));
-    if (rem > 0) {
-        const int kc = (rem + 7) / 8;
-        if (kc == 4) ASW_TRY((geo_tile_launch<BORDER, 4>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
-        else if (kc == 3) ASW_TRY((geo_tile_launch<BORDER, 3>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
-        else if (kc == 2) ASW_TRY((geo_tile_launch<BORDER, 2>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
-        else ASW_TRY((geo_tile_launch<BORDER, 1>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, full * 32, 1, keys, agg)));
-    }
-    return ASW_OK;
+    if (g.sign > 0) return geo_segments_signed<1, BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, keys, agg);
+    return geo_segments_signed<-1, BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, keys, agg);
 }
 
 __global__ void k_pack_bgrx(const uint8_t* __restrict__ img, size_t n, uint32_t* __restrict__ out) {
@@ -506,7 +594,13 @@ static asw_status dev_geodesic_dist(asw_ctx* ctx, const uint8_t* img, int H, int
     ASW_TRY(ws_get(ctx, WS_MISC2, (size_t)Hp * Wp, &ext));
     ASW_TRY(ws_get(ctx, ws_slot, n * win * win, &dist));
     LAUNCH(ctx, "pack_bgrx_pad", (k_pack_bgrx_pad<<<dim3(cdiv(Wp, 128), Hp), 128, 0, ctx->stream>>>(img, H, W, pad, ext)));   // A.cpp:1404
-    LAUNCH(ctx, "geo_dist", (k_geo_dist<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(ext, H, W, win, dist)));
+    dim3 dgrid(cdiv(W, 128), H);
+    if (getenv("ASW_GEO_DIST_GENERIC")) LAUNCH(ctx, "geo_dist", (k_geo_dist<<<dgrid, 128, 0, ctx->stream>>>(ext, H, W, win, dist)));
+    else if (win == 35) LAUNCH(ctx, "geo_dist", (k_geo_dist_t<35><<<dgrid, 128, 0, ctx->stream>>>(ext, H, W, dist)));
+    else if (win == 9) LAUNCH(ctx, "geo_dist", (k_geo_dist_t<9><<<dgrid, 128, 0, ctx->stream>>>(ext, H, W, dist)));
+    else if (win == 7) LAUNCH(ctx, "geo_dist", (k_geo_dist_t<7><<<dgrid, 128, 0, ctx->stream>>>(ext, H, W, dist)));
+    else if (win == 5) LAUNCH(ctx, "geo_dist", (k_geo_dist_t<5><<<dgrid, 128, 0, ctx->stream>>>(ext, H, W, dist)));
+    else LAUNCH(ctx, "geo_dist", (k_geo_dist<<<dgrid, 128, 0, ctx->stream>>>(ext, H, W, win, dist)));
     *dist_out = dist;
     return ASW_OK;
 }
