@@ -390,6 +390,12 @@ static asw_status geo_tile_segments(asw_ctx* ctx, const float* dref, const float
 __device__ __forceinline__ void gd_cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
+// sum of the 4 byte-wise absolute differences added onto an accumulator (one VABSDIFF4.ACC)
+__device__ __forceinline__ uint32_t gd_sad4_acc(uint32_t a, uint32_t b, uint32_t acc) {
+    uint32_t d;
+    asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
+    return d;
+}
 __device__ __forceinline__ void gd_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void gd_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -429,17 +435,22 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
 
     // chunk c of the window: row j = c / 3, taps i0 .. i1 of that row (3 chunks per row: 12 + 12 + rest)
     const int cpr = (win + GT_TC - 1) / GT_TC, nchunk = win * cpr;
+    // staging map without divisions: thread `tid` copies column `tid` (+ NT, ...) of every tap row; the clamped
+    // source column and the smem column are loop invariants, the tap advances by one plane (n floats)
     auto stage_dist = [&](int c, int buf) {
         const int j = c / cpr, i0 = (c - j * cpr) * GT_TC, cnt = min(GT_TC, win - i0);
-        float* dl = DLs + buf * GT_TC * GT_X;
-        float* dr = DRs + buf * GT_TC * GD_DRW;
-        for (int q = tid; q < cnt * GT_X; q += NT) {
-            const int tt = q >> 7, xx = q & (GT_X - 1);
-            gd_cp_async4(dl + q, dref + (size_t)(j * win + i0 + tt) * n + rowoff + min(xb + xx, W - 1));
+        const size_t tap0 = (size_t)(j * win + i0) * n + rowoff;
+        for (int xx = tid; xx < GT_X; xx += NT) {
+            const float* src = dref + tap0 + min(xb + xx, W - 1);
+            float* dst = DLs + buf * GT_TC * GT_X + xx;
+#pragma unroll 4
+            for (int tt = 0; tt < cnt; tt++) gd_cp_async4(dst + tt * GT_X, src + (size_t)tt * n);
         }
-        for (int q = tid; q < cnt * GD_DRW; q += NT) {
-            const int tt = q / GD_DRW, e = q - tt * GD_DRW;
-            gd_cp_async4(dr + q, dtgt + (size_t)(j * win + i0 + tt) * n + rowoff + clampi(oDR + e, 0, W - 1));
+        for (int e = tid; e < GD_DRW; e += NT) {
+            const float* src = dtgt + tap0 + clampi(oDR + e, 0, W - 1);
+            float* dst = DRs + buf * GT_TC * GD_DRW + e;
+#pragma unroll 4
+            for (int tt = 0; tt < cnt; tt++) gd_cp_async4(dst + tt * GD_DRW, src + (size_t)tt * n);
         }
     };
     auto stage_colour = [&](int j, int buf) {
@@ -483,29 +494,40 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
                 edge[k] = __ldg(ptgt + (size_t)ny * W + (SIGN > 0 ? max(0, W - 1 - d) : min(d, W - 1)));
             }
         }
-        for (int i = i0; i < i1; i++) {
-            const int tt = i - i0, r = i & 3;
-            const float4 dl4 = *(const float4*)(dl + tt * GT_X);
-            const float4 dra = *(const float4*)(dr + tt * GD_DRW), drb = *(const float4*)(dr + tt * GD_DRW + 4);
-            // colour cell of pixel quad start: oCL + (4 pg + i) -> copy r = i & 3 at aligned index 4 pg + i - r
-            const uint4 cl4 = *(const uint4*)(cl + r * CLW + i - r);
-            const uint4 cra = *(const uint4*)(cr + r * CRW + i - r), crb = *(const uint4*)(cr + r * CRW + i - r + 4);
-            const float dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
-            const float drv[8] = {dra.x, dra.y, dra.z, dra.w, drb.x, drb.y, drb.z, drb.w};
-            const uint32_t clv[4] = {cl4.x, cl4.y, cl4.z, cl4.w};
-            const uint32_t crv[8] = {cra.x, cra.y, cra.z, cra.w, crb.x, crb.y, crb.z, crb.w};
+        // i0 is a multiple of GT_TC = 12, so the skewed colour copy r = i & 3 = tt & 3 is static after unrolling; the
+        // four per-copy bases are chunk invariants, a tap then addresses everything with immediate offsets
+        const uint32_t* clb[4];
+        const uint32_t* crb4[4];
 #pragma unroll
-            for (int p = 0; p < 4; p++) {
-                const int nx = xb + 4 * pg + p - h + i;                       // sample column before clamping
-                const bool clamped = BORDER && (SIGN > 0 ? nx > W - 1 : nx < 0);
+        for (int r = 0; r < 4; r++) { clb[r] = cl + r * CLW + i0 - r; crb4[r] = cr + r * CRW + i0 - r; }
 #pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int w = SIGN > 0 ? p - k + 4 : p + k;               // position on the diagonal window
-                    const float t = __fmul_rn(dlv[p], drv[w]);                // A.cpp:1488-1489
-                    const uint32_t cright = BORDER ? (clamped ? edge[k] : crv[w]) : crv[w];
-                    const float cd = (float)__vsadu4(clv[p], cright);         // getColorDist
-                    fn[k * 4 + p] = fmaf(t, cd, fn[k * 4 + p]);
-                    fd[k * 4 + p] = __fadd_rn(fd[k * 4 + p], t);
+        for (int tt = 0; tt < GT_TC; tt++) {
+            if (tt < i1 - i0) {
+                const int i = i0 + tt, r = tt & 3;
+                const float4 dl4 = *(const float4*)(dl + tt * GT_X);
+                const float4 dra = *(const float4*)(dr + tt * GD_DRW), drb = *(const float4*)(dr + tt * GD_DRW + 4);
+                // colour cell of pixel quad start: oCL + (4 pg + i) -> copy r at aligned index 4 pg + i - r
+                const uint4 cl4 = *(const uint4*)(clb[r] + tt);
+                const uint4 cra = *(const uint4*)(crb4[r] + tt), crb = *(const uint4*)(crb4[r] + tt + 4);
+                const float dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
+                const float drv[8] = {dra.x, dra.y, dra.z, dra.w, drb.x, drb.y, drb.z, drb.w};
+                const uint32_t clv[4] = {cl4.x, cl4.y, cl4.z, cl4.w};
+                const uint32_t crv[8] = {cra.x, cra.y, cra.z, cra.w, crb.x, crb.y, crb.z, crb.w};
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const int nx = xb + 4 * pg + p - h + i;                   // sample column before clamping
+                    const bool clamped = BORDER && (SIGN > 0 ? nx > W - 1 : nx < 0);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int w = SIGN > 0 ? p - k + 4 : p + k;           // position on the diagonal window
+                        const float t = __fmul_rn(dlv[p], drv[w]);            // A.cpp:1488-1489
+                        const uint32_t cright = BORDER ? (clamped ? edge[k] : crv[w]) : crv[w];
+                        // getColorDist as a float without an integer->float conversion: the byte SAD accumulates onto
+                        // the bit pattern of 2^23, giving the float 2^23 + sad exactly; subtract 2^23 on the FMA pipe
+                        const float cd = __uint_as_float(gd_sad4_acc(clv[p], cright, 0x4B000000u)) - 8388608.0f;
+                        fn[k * 4 + p] = fmaf(t, cd, fn[k * 4 + p]);
+                        fd[k * 4 + p] = __fadd_rn(fd[k * 4 + p], t);
+                    }
                 }
             }
         }
