@@ -396,6 +396,15 @@ __device__ __forceinline__ uint32_t gd_sad4_acc(uint32_t a, uint32_t b, uint32_t
     asm("vabsdiff4.u32.u32.u32.add %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(acc));
     return d;
 }
+// two SADs straight into the halves of one 64-bit register pair (the operand of the packed FADD2 that follows)
+__device__ __forceinline__ float2 gd_sad4_acc_pair(uint32_t a0, uint32_t b0, uint32_t a1, uint32_t b1, uint32_t acc) {
+    unsigned long long r;
+    asm("{\n\t.reg .b32 lo, hi;\n\tvabsdiff4.u32.u32.u32.add lo, %1, %2, %5;\n\tvabsdiff4.u32.u32.u32.add hi, %3, %4, %5;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t}" : "=l"(r) : "r"(a0), "r"(b0), "r"(a1), "r"(b1), "r"(acc));
+    float2 f;
+    f.x = __uint_as_float((uint32_t)r); f.y = __uint_as_float((uint32_t)(r >> 32));
+    return f;
+}
 __device__ __forceinline__ void gd_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void gd_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -429,9 +438,17 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
     const int oCL = xb - h;
     const int oCR = oDR - h;
     const int e0 = SIGN > 0 ? 4 * pg - 4 * ds + 28 : 4 * pg + 4 * ds;   // window start (cells), multiple of 4
-    float fn[16], fd[16];
+    // accumulators: the 16 (pixel, candidate) pairs of a thread are evaluated as 6 packed pairs that share a target
+    // operand -- (p, k) and (p+1, k+SIGN), p even, sit on the same diagonal -- plus 4 singles, so that the FMA-pipe
+    // work of two evaluations issues as one FMUL2 / FADD2 / FFMA2
+    float2 fnp[2][3], fdp[2][3];
+    float fns[2][2], fds[2][2];
 #pragma unroll
-    for (int a = 0; a < 16; a++) { fn[a] = 0.0f; fd[a] = 0.0f; }
+    for (int a = 0; a < 2; a++) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) { fnp[a][q] = make_float2(0.f, 0.f); fdp[a][q] = make_float2(0.f, 0.f); }
+        fns[a][0] = fns[a][1] = fds[a][0] = fds[a][1] = 0.0f;
+    }
 
     // chunk c of the window: row j = c / 3, taps i0 .. i1 of that row (3 chunks per row: 12 + 12 + rest)
     const int cpr = (win + GT_TC - 1) / GT_TC, nchunk = win * cpr;
@@ -513,21 +530,42 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
                 const float drv[8] = {dra.x, dra.y, dra.z, dra.w, drb.x, drb.y, drb.z, drb.w};
                 const uint32_t clv[4] = {cl4.x, cl4.y, cl4.z, cl4.w};
                 const uint32_t crv[8] = {cra.x, cra.y, cra.z, cra.w, crb.x, crb.y, crb.z, crb.w};
+                bool clamped[4];
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
                     const int nx = xb + 4 * pg + p - h + i;                   // sample column before clamping
-                    const bool clamped = BORDER && (SIGN > 0 ? nx > W - 1 : nx < 0);
+                    clamped[p] = BORDER && (SIGN > 0 ? nx > W - 1 : nx < 0);
+                }
+                // getColorDist as a float without an integer->float conversion: the byte SAD accumulates onto the bit
+                // pattern of 2^23 (VABSDIFF4.ACC), giving the float 2^23 + sad exactly; 2^23 is subtracted on the FMA pipe
+                auto sadbits = [&](int p, int k, int w) {
+                    const uint32_t cright = BORDER ? (clamped[p] ? edge[k] : crv[w]) : crv[w];
+                    return __uint_as_float(gd_sad4_acc(clv[p], cright, 0x4B000000u));
+                };
+                const float2 m23 = make_float2(-8388608.0f, -8388608.0f);
 #pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        const int w = SIGN > 0 ? p - k + 4 : p + k;           // position on the diagonal window
-                        const float t = __fmul_rn(dlv[p], drv[w]);            // A.cpp:1488-1489
-                        const uint32_t cright = BORDER ? (clamped ? edge[k] : crv[w]) : crv[w];
-                        // getColorDist as a float without an integer->float conversion: the byte SAD accumulates onto
-                        // the bit pattern of 2^23, giving the float 2^23 + sad exactly; subtract 2^23 on the FMA pipe
-                        const float cd = __uint_as_float(gd_sad4_acc(clv[p], cright, 0x4B000000u)) - 8388608.0f;
-                        fn[k * 4 + p] = fmaf(t, cd, fn[k * 4 + p]);
-                        fd[k * 4 + p] = __fadd_rn(fd[k * 4 + p], t);
+                for (int a = 0; a < 2; a++) {
+                    const int pe = 2 * a;
+                    const float2 dl2 = make_float2(dlv[pe], dlv[pe + 1]);
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        const int k = SIGN > 0 ? q : q + 1;                   // (pe, k) and (pe+1, k+SIGN): same window cell
+                        const int w = SIGN > 0 ? pe - k + 4 : pe + k;
+                        const float2 t2 = __fmul2_rn(dl2, make_float2(drv[w], drv[w]));          // A.cpp:1488-1489
+                        const uint32_t cr0 = BORDER ? (clamped[pe] ? edge[k] : crv[w]) : crv[w];
+                        const uint32_t cr1 = BORDER ? (clamped[pe + 1] ? edge[k + SIGN] : crv[w]) : crv[w];
+                        const float2 cd2 = __fadd2_rn(gd_sad4_acc_pair(clv[pe], cr0, clv[pe + 1], cr1, 0x4B000000u), m23);
+                        fnp[a][q] = __ffma2_rn(t2, cd2, fnp[a][q]);
+                        fdp[a][q] = __fadd2_rn(fdp[a][q], t2);
                     }
+                    // singles: (pe, ks0) and (pe+1, ks1) have no partner on their diagonal
+                    const int ks0 = SIGN > 0 ? 3 : 0, ks1 = SIGN > 0 ? 0 : 3;
+                    const int w0 = SIGN > 0 ? pe - ks0 + 4 : pe + ks0, w1 = SIGN > 0 ? pe + 1 - ks1 + 4 : pe + 1 + ks1;
+                    const float t0 = __fmul_rn(dlv[pe], drv[w0]), t1 = __fmul_rn(dlv[pe + 1], drv[w1]);
+                    fns[a][0] = fmaf(t0, sadbits(pe, ks0, w0) - 8388608.0f, fns[a][0]);
+                    fds[a][0] = __fadd_rn(fds[a][0], t0);
+                    fns[a][1] = fmaf(t1, sadbits(pe + 1, ks1, w1) - 8388608.0f, fns[a][1]);
+                    fds[a][1] = __fadd_rn(fds[a][1], t1);
                 }
             }
         }
@@ -542,7 +580,15 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
         for (int k = 0; k < 4; k++) {
             const int c = c0 + 4 * ds + k;
             if (c >= g.n_cand) continue;
-            const double E = (double)fn[k * 4 + p] / (double)fd[k * 4 + p];
+            // (p, k) lives in: pair slot q of half a = p/2 (x for even p with k = q (LEFT) / q+1 (RIGHT), y for odd p
+            // with the partner's k), or one of the two singles of that half
+            const int a = p >> 1, odd = p & 1;
+            const int kq = SIGN > 0 ? (odd ? k - 1 : k) : (odd ? k : k - 1);          // pair slot if in 0..2
+            const bool single = odd ? (k == (SIGN > 0 ? 0 : 3)) : (k == (SIGN > 0 ? 3 : 0));
+            float vn, vd;
+            if (single) { vn = fns[a][odd]; vd = fds[a][odd]; }
+            else { vn = odd ? fnp[a][kq].y : fnp[a][kq].x; vd = odd ? fdp[a][kq].y : fdp[a][kq].x; }
+            const double E = (double)vn / (double)vd;
             if (agg) agg[(size_t)c * n + rowoff + x] = (float)E;
             best = min(best, wta_key_d(E, g.d_first + c));
         }
