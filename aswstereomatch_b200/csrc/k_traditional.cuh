@@ -13,6 +13,7 @@
 #pragma once
 #include "k_cost.cuh"
 
+#include <type_traits>
 #include <vector>
 
 struct TradGeom {
@@ -352,6 +353,252 @@ k_trad_fast(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// diagonal-blocked variant (ASW_TRAD_DIAG=1; not the default -- see dev_traditional): one CTA = one image row x 128 pixels x 4 NW candidates, thread = 4 adjacent
+// pixels x 4 ADJACENT candidates, as k_geo_agg_diag (k_geodesic.cuh):
+//   * the bilateral weights are evaluated ONCE per pixel and tap -- wL_n for the 128 reference pixels, wR_n for the
+//     128 + 4 NW + 4 target pixels the chunk can reach (one ex2 each) -- into shared memory, one 12-tap chunk ahead,
+//     and reused by every candidate: 280 SFU operations per tap instead of 128 x (candidates)
+//   * operands addressed at (x - d) sit on a diagonal of the thread's 4 x 4 block: the 7 distinct target weights
+//     are one aligned 8-wide window (2 LDS.128); the target cost samples 7 scalars
+//   * per evaluation: |dI| (FADD), w = wL wR (FMUL2), num += w |dI| (FFMA), den += w (FADD2)
+// Float tiles of the gray rows y-h .. y+h hold the cost samples (clamp addressing applied when they are staged).
+// BORDER segments (sample column clamped BEFORE the shift: right edge for LEFT, left edge for RIGHT) read the
+// shifted edge column, which depends on the candidate only.
+// Accumulation is fp32 over the window (all terms are non-negative; ~1e-6 relative against the reference's double).
+// ------------------------------------------------------------------------------------------------
+#define TD_X 128
+#define TD_TC 12
+
+template <int SIGN, bool BORDER, int NW>
+__device__ __forceinline__ void trad_diag_body(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt,
+                                               const float* __restrict__ c2h, float a2, const TradGeom& g, int xb, int c0,
+                                               unsigned long long* __restrict__ keys, float* __restrict__ agg) {
+    constexpr int NT = 32 * NW;
+    constexpr int WRW = TD_X + 4 * NW + 4;                     // staged target-weight row (cells)
+    extern __shared__ __align__(16) float sm_td[];
+    const int W = g.W, H = g.H, win = g.win, h = g.h;
+    const int RTW = (TD_X + 2 * h + 7) & ~3, TTW = (WRW + 2 * h + 7) & ~3;   // sample tiles (rows 16-byte aligned, 8 / 12-wide windows)
+    float* WLs = sm_td;                                        // [2][TD_TC][TD_X]
+    float* WRs = WLs + 2 * TD_TC * TD_X;                       // [2][TD_TC][WRW]
+    float* RT = WRs + 2 * TD_TC * WRW;                         // [win][RTW]  Lg(clamp(y-h+r), clamp(xb-h+c))
+    float* TT = RT + win * RTW;                                // [win][TTW]  Rg(clamp(y-h+r), clamp(oWR-h+c))
+    float* C2 = TT + win * TTW;                                // [nw]        spatial exponent of every tap
+    int* TAPW = (int*)(C2 + g.nw);                             // [nw]        weight tap: (dy + h) << 16 | (dx + h)
+    int* TAPS = TAPW + g.nw;                                   // [nw]        sample tap: ky << 16 | kx   (transposed)
+    const int tid = threadIdx.x, pg = tid & 31, ds = tid >> 5;
+    const int y = blockIdx.y;
+    const int d_lo = g.d_first + c0;
+    // staged target cell 0 <-> column (before clamping); a thread's 8-wide window starts at cell e0 (multiple of 4)
+    const int oWR = SIGN > 0 ? xb - d_lo - 4 * NW : xb + d_lo;
+    const int e0 = SIGN > 0 ? 4 * pg + 4 * (NW - 1 - ds) : 4 * pg + 4 * ds;
+    const size_t rowoff = (size_t)y * W;
+    // ---- sample tiles, tap tables ----
+    for (int i = tid; i < win * RTW; i += NT) {
+        const int r = i / RTW, c = i - r * RTW;
+        RT[i] = (float)ref[(size_t)clampi(y - h + r, 0, H - 1) * W + clampi(xb - h + c, 0, W - 1)];
+    }
+    for (int i = tid; i < win * TTW; i += NT) {
+        const int r = i / TTW, c = i - r * TTW;
+        TT[i] = (float)tgt[(size_t)clampi(y - h + r, 0, H - 1) * W + clampi(oWR - h + c, 0, W - 1)];
+    }
+    for (int n = tid; n < g.nw; n += NT) {
+        const int pw = n < g.cidx ? n : n + 1;                 // weight tap skips the centre (A.cpp:1044-1053)
+        const int pc = n <= g.cidx ? n : n + 1;                // sample tap skips centre + 1 (A.cpp:1088-1102)
+        C2[n] = __ldg(&c2h[n]);
+        TAPW[n] = ((pw / win) << 16) | (pw % win);
+        TAPS[n] = ((pc % win) << 16) | (pc / win);             // pc / win is the COLUMN offset, pc % win the ROW offset
+    }
+    __syncthreads();
+    // ---- weights of a 12-tap chunk: thread `tid` owns column `tid` (+ NT ...) of the reference and target rows.
+    // The weighted pixel and its neighbour come from the sample tiles (same clamp addressing); target cells that lie
+    // outside the image stand for the clamped edge pixel, whose neighbourhood the tile may not hold: global loads.
+    auto stage_weights = [&](int n0, int buf) {
+        const int cnt = min(TD_TC, g.nw - n0);
+        for (int col = tid; col < TD_X + WRW; col += NT) {
+            const bool is_ref = col < TD_X;
+            const int cell = is_ref ? col : col - TD_X;
+            const int xu = is_ref ? xb + cell : oWR + cell;                        // the weighted pixel, before clamping
+            float* dst = is_ref ? WLs + buf * TD_TC * TD_X + cell : WRs + buf * TD_TC * WRW + cell;
+            const int pitch = is_ref ? TD_X : WRW;
+            if (xu >= 0 && xu <= W - 1) {
+                const float* tile = (is_ref ? RT : TT) + cell;                     // tile column of (xu - h)
+                const int tw = is_ref ? RTW : TTW;
+                const float centre = tile[h * tw + h];
+                for (int t = 0; t < cnt; t++) {
+                    const int tp = TAPW[n0 + t];
+                    const float nb = tile[(tp >> 16) * tw + (tp & 0xFFFF)];
+                    // 3 exp(-(delta/gamma_c + dist/gamma_g)) = 2^(-(delta a2 + c2h[n]))   (A.cpp:1062-1066)
+                    dst[t * pitch] = fast_ex2(-fmaf(fabsf(nb - centre), a2, C2[n0 + t]));
+                }
+            } else {
+                const uint8_t* img = is_ref ? ref : tgt;
+                const int xc = clampi(xu, 0, W - 1);
+                const float centre = (float)img[rowoff + xc];
+                for (int t = 0; t < cnt; t++) {
+                    const int tp = TAPW[n0 + t];
+                    const int dy = (tp >> 16) - h, dx = (tp & 0xFFFF) - h;
+                    const float nb = (float)img[(size_t)clampi(y + dy, 0, H - 1) * W + clampi(xc + dx, 0, W - 1)];
+                    dst[t * pitch] = fast_ex2(-fmaf(fabsf(nb - centre), a2, C2[n0 + t]));
+                }
+            }
+        }
+    };
+    float2 fnp[2][3], fdp[2][3];
+    float fns[2][2], fds[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++) {
+#pragma unroll
+        for (int q = 0; q < 3; q++) { fnp[a][q] = make_float2(0.f, 0.f); fdp[a][q] = make_float2(0.f, 0.f); }
+        fns[a][0] = fns[a][1] = fds[a][0] = fds[a][1] = 0.0f;
+    }
+    stage_weights(0, 0);
+    __syncthreads();
+    const int nchunk = (g.nw + TD_TC - 1) / TD_TC;
+    for (int c = 0; c < nchunk; c++) {
+        const int n0 = c * TD_TC, cnt = min(TD_TC, g.nw - n0);
+        if (c + 1 < nchunk) stage_weights(n0 + TD_TC, (c + 1) & 1);      // next chunk's weights into the other buffer
+        const float* wl = WLs + (c & 1) * TD_TC * TD_X + 4 * pg;
+        const float* wr = WRs + (c & 1) * TD_TC * WRW + e0;
+        for (int t = 0; t < cnt; t++) {
+            const int tp = TAPS[n0 + t];
+            const int ky = tp >> 16, kx = tp & 0xFFFF;
+            const float4 wl4 = *(const float4*)(wl + t * TD_X);
+            const float4 wra = *(const float4*)(wr + t * WRW), wrb = *(const float4*)(wr + t * WRW + 4);
+            const float wlv[4] = {wl4.x, wl4.y, wl4.z, wl4.w};
+            const float wrv[8] = {wra.x, wra.y, wra.z, wra.w, wrb.x, wrb.y, wrb.z, wrb.w};
+            // cost samples: a thread's 4 reference and 7 target samples start at column (4 pg + kx): 16-byte aligned
+            // loads from the aligned-down column, the (warp-uniform) remainder kx & 3 picks the registers
+            const float4* rs4 = (const float4*)(RT + ky * RTW + 4 * pg + (kx & ~3));
+            const float4* ts4 = (const float4*)(TT + ky * TTW + e0 + (kx & ~3));
+            const float4 r0 = rs4[0], r1 = rs4[1], t0 = ts4[0], t1 = ts4[1], t2 = ts4[2];
+            const float rsw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+            const float tsw[12] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w};
+            float edge[4];
+            bool clamped[4];
+            if (BORDER) {
+                const int ny = clampi(y - h + ky, 0, H - 1);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int d = d_lo + 4 * ds + k;
+                    edge[k] = (float)__ldg(tgt + (size_t)ny * W + (SIGN > 0 ? max(0, W - 1 - d) : min(d, W - 1)));
+                }
+#pragma unroll
+                for (int p = 0; p < 4; p++) {
+                    const int nx = xb + 4 * pg + p - h + kx;              // sample column before clamping
+                    clamped[p] = SIGN > 0 ? nx > W - 1 : nx < 0;
+                }
+            }
+            auto tap = [&](auto sc) {
+                constexpr int S = decltype(sc)::value;
+                auto cost = [&](int p, int k, int w) {
+                    const float tv = BORDER ? (clamped[p] ? edge[k] : tsw[S + w]) : tsw[S + w];
+                    return fabsf(rsw[S + p] - tv);                        // |Lg - Rg| (A.cpp:1104)
+                };
+#pragma unroll
+                for (int a = 0; a < 2; a++) {
+                    const int pe = 2 * a;
+                    const float2 wl2 = make_float2(wlv[pe], wlv[pe + 1]);
+#pragma unroll
+                    for (int q = 0; q < 3; q++) {
+                        const int k = SIGN > 0 ? q : q + 1;               // (pe, k) and (pe+1, k+SIGN): same target pixel
+                        const int w = SIGN > 0 ? pe - k + 4 : pe + k;
+                        const float2 w2 = __fmul2_rn(wl2, make_float2(wrv[w], wrv[w]));       // wL * wR
+                        fnp[a][q].x = fmaf(w2.x, cost(pe, k, w), fnp[a][q].x);
+                        fnp[a][q].y = fmaf(w2.y, cost(pe + 1, k + SIGN, w), fnp[a][q].y);
+                        fdp[a][q] = __fadd2_rn(fdp[a][q], w2);
+                    }
+                    const int ks0 = SIGN > 0 ? 3 : 0, ks1 = SIGN > 0 ? 0 : 3;
+                    const int w0 = SIGN > 0 ? pe - ks0 + 4 : pe + ks0, w1 = SIGN > 0 ? pe + 1 - ks1 + 4 : pe + 1 + ks1;
+                    const float u0 = __fmul_rn(wlv[pe], wrv[w0]), u1 = __fmul_rn(wlv[pe + 1], wrv[w1]);
+                    fns[a][0] = fmaf(u0, cost(pe, ks0, w0), fns[a][0]);
+                    fds[a][0] = __fadd_rn(fds[a][0], u0);
+                    fns[a][1] = fmaf(u1, cost(pe + 1, ks1, w1), fns[a][1]);
+                    fds[a][1] = __fadd_rn(fds[a][1], u1);
+                }
+            };
+            switch (kx & 3) {
+                case 0: tap(std::integral_constant<int, 0>{}); break;
+                case 1: tap(std::integral_constant<int, 1>{}); break;
+                case 2: tap(std::integral_constant<int, 2>{}); break;
+                default: tap(std::integral_constant<int, 3>{}); break;
+            }
+        }
+        __syncthreads();          // chunk c consumed by everyone, chunk c+1's weights visible
+    }
+    const int x0 = xb + 4 * pg;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+        const int x = x0 + p;
+        if (x >= W) continue;
+        unsigned long long best = WTA_KEY_EMPTY;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ci = c0 + 4 * ds + k;
+            if (ci >= g.n_cand) continue;
+            const int a = p >> 1, odd = p & 1;
+            const int kq = SIGN > 0 ? (odd ? k - 1 : k) : (odd ? k : k - 1);
+            const bool single = odd ? (k == (SIGN > 0 ? 0 : 3)) : (k == (SIGN > 0 ? 3 : 0));
+            float vn, vd;
+            if (single) { vn = fns[a][odd]; vd = fds[a][odd]; }
+            else { vn = odd ? fnp[a][kq].y : fnp[a][kq].x; vd = odd ? fdp[a][kq].y : fdp[a][kq].x; }
+            const double E = (double)vn / (double)vd;
+            if (agg) agg[(size_t)ci * H * W + rowoff + x] = (float)E;
+            best = min(best, wta_key_d(E, g.d_first + ci));
+        }
+        atomicMin(&keys[rowoff + x], best);
+    }
+}
+
+// grid: (segments, H, candidate chunks).  Interior and edge segments run in ONE launch (the edge variant is a
+// CTA-uniform branch) so that small images still fill the GPU.
+template <int SIGN, int NW>
+__global__ void __launch_bounds__(32 * NW)
+k_trad_diag(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, const float* __restrict__ c2h, float a2,
+            TradGeom g, int cand_first, unsigned long long* __restrict__ keys, float* __restrict__ agg) {
+    const int xb = blockIdx.x * TD_X;
+    const int c0 = cand_first + blockIdx.z * (4 * NW);
+    const bool border = SIGN > 0 ? xb + TD_X - 1 + g.h > g.W - 1 : xb - g.h < 0;
+    if (border) trad_diag_body<SIGN, true, NW>(ref, tgt, c2h, a2, g, xb, c0, keys, agg);
+    else trad_diag_body<SIGN, false, NW>(ref, tgt, c2h, a2, g, xb, c0, keys, agg);
+}
+
+template <int SIGN, int NW>
+static asw_status trad_diag_launch(asw_ctx* ctx, const uint8_t* ref, const uint8_t* tgt, const float* c2h, float a2, TradGeom g,
+                                   int cand_first, int n_chunks, unsigned long long* keys, float* agg) {
+    if (n_chunks <= 0) return ASW_OK;
+    constexpr int WRW = TD_X + 4 * NW + 4;
+    const int h = g.h;
+    size_t smem = (2 * (size_t)TD_TC * (TD_X + WRW) + (size_t)g.win * ((TD_X + 2 * h + 7) & ~3) +
+                   (size_t)g.win * ((WRW + 2 * h + 7) & ~3) + 3 * (size_t)g.nw) * sizeof(float);
+    if (smem > 220 * 1024) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "window too large for the diagonal kernel%s%s");
+    cudaFuncSetAttribute(k_trad_diag<SIGN, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    LAUNCH(ctx, "trad_aggregate", (k_trad_diag<SIGN, NW><<<dim3(cdiv(g.W, TD_X), g.H, n_chunks), 32 * NW, smem, ctx->stream>>>(
+                                      ref, tgt, c2h, a2, g, cand_first, keys, agg)));
+    return ASW_OK;
+}
+// full chunks of 32 candidates (8 warps), then the remainder with the warps it needs
+template <int SIGN>
+static asw_status trad_diag_all(asw_ctx* ctx, const uint8_t* ref, const uint8_t* tgt, const float* c2h, float a2, TradGeom g,
+                                unsigned long long* keys, float* agg) {
+    const int full = g.n_cand / 32, rem = g.n_cand - full * 32, c1 = full * 32;
+    ASW_TRY((trad_diag_launch<SIGN, 8>(ctx, ref, tgt, c2h, a2, g, 0, full, keys, agg)));
+#define TRAD_REM(NWV) ASW_TRY((trad_diag_launch<SIGN, NWV>(ctx, ref, tgt, c2h, a2, g, c1, 1, keys, agg)))
+    switch ((rem + 3) / 4) {
+        case 1: TRAD_REM(1); break;
+        case 2: TRAD_REM(2); break;
+        case 3: TRAD_REM(3); break;
+        case 4: TRAD_REM(4); break;
+        case 5: TRAD_REM(5); break;
+        case 6: TRAD_REM(6); break;
+        case 7: TRAD_REM(7); break;
+        case 8: TRAD_REM(8); break;
+        default: break;
+    }
+#undef TRAD_REM
+    return ASW_OK;
+}
+
 // host: exact weight table [nw][256], (float)(k * exp(-(delta/gamma_c + sqrt(i*i+j*j)/gamma_g))), k = 3
 static void trad_build_table(int win, double gamma_c, double gamma_g, std::vector<float>& t) {
     int h = win / 2, nw = win * win - 1, cidx = win * win / 2;
@@ -388,6 +635,24 @@ static asw_status dev_traditional(asw_ctx* ctx, const uint8_t* dL, const uint8_t
     const int h = win / 2, IH = TR_TH + 2 * h, IWr = TR_TW + 2 * h, IWt = TR_TW + 2 * h + TR_Q - 1;
     const bool exact = getenv("ASW_TRAD_EXACT") != nullptr;
     size_t smem_fast = ((size_t)IH * IWr + (size_t)IH * IWt) * sizeof(float);
+    if (!exact && getenv("ASW_TRAD_DIAG") && win <= 41) {
+        // diagonal-blocked kernel (measured 15-25 % slower than the tiled single-SFU-op kernel below: kept selectable): per-side weights 2^(-(delta a2 + c2h[n])), c2h[n] = g_n log2(e)/gamma_g - log2(3)
+        std::vector<float> c2h(g.nw);
+        const double log2e = 1.4426950408889634;
+        for (int i = 0; i < g.nw; i++) {
+            int pw = i < g.cidx ? i : i + 1;
+            int dj = pw / win - h, di = pw % win - h;
+            c2h[i] = (float)(sqrt((double)(di * di + dj * dj)) * log2e / gamma_g - log2(3.0));
+        }
+        float* dc2;
+        ASW_TRY(ws_get(ctx, WS_TABLE1, c2h.size(), &dc2));
+        ASW_CUDA(ctx, cudaMemcpyAsync(dc2, c2h.data(), c2h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+        ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // c2h is a host temporary
+        const float a2 = (float)(log2e / gamma_c);
+        if (g.sign > 0) ASW_TRY((trad_diag_all<1>(ctx, ref, tgt, dc2, a2, g, keys, agg_dev)));
+        else ASW_TRY((trad_diag_all<-1>(ctx, ref, tgt, dc2, a2, g, keys, agg_dev)));
+        return keys_to_disp(ctx, keys, n, disp_dev);
+    }
     if (!exact && smem_fast <= 200 * 1024) {
         // c2[n] = 2 g_n log2(e)/gamma_g - log2(9), a2 = log2(e)/gamma_c  (k = 3 -> k*k = 9)
         std::vector<float> c2(g.nw);

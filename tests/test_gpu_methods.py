@@ -36,6 +36,40 @@ def test_traditional(ctx, H, W, D, win, disp_type, seed):
     assert np.array_equal(d, orc.wta(e, 0)) or (d == orc.wta(e, 0)).mean() >= 0.9999
 
 
+@pytest.mark.parametrize("H,W,D,win,disp_type,seed", [(14, 300, 33, 7, 0, 21), (12, 290, 40, 9, 1, 22), (10, 200, 16, 35, 0, 23),
+                                                       (10, 420, 70, 5, 1, 24), (9, 130, 3, 5, 0, 25)])
+@pytest.mark.parametrize("diag", [False, True])
+def test_traditional_wide_many_candidates(ctx, H, W, D, win, disp_type, seed, diag):
+    """rows longer than one tile / 128-pixel segment and >= 32 candidates, both views, for the default tiled kernel
+    and for the selectable diagonal-blocked kernel (interior and edge segments, full chunks plus remainder)"""
+    import os
+    L, R, _ = make_pair(H, W, D, seed)
+    if diag:
+        os.environ["ASW_TRAD_DIAG"] = "1"
+    try:
+        d, e = ctx.computeAdaptiveWeight(L, R, 30, 20, disp_type, win, 0, D, agg=True, strict=True)
+    finally:
+        os.environ.pop("ASW_TRAD_DIAG", None)
+    d_ref, e_ref = orc.asw_traditional(L, R, 30, 20, disp_type, win, 0, D, agg=True)
+    assert rel_err(e, e_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+
+
+@pytest.mark.parametrize("env", ["ASW_TRAD_DIAG", "ASW_TRAD_EXACT"])
+def test_traditional_other_kernels(ctx, env):
+    """the diagonal-blocked kernel and the exact-table kernel stay selectable and agree with the oracle"""
+    import os
+    L, R, _ = make_pair(40, 72, 8, 26)
+    os.environ[env] = "1"
+    try:
+        d, e = ctx.computeAdaptiveWeight(L, R, 30, 20, 0, 9, 0, 8, agg=True, strict=True)
+    finally:
+        del os.environ[env]
+    d_ref, e_ref = orc.asw_traditional(L, R, 30, 20, 0, 9, 0, 8, agg=True)
+    assert rel_err(e, e_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+
+
 def test_traditional_nonzero_min_disparity(ctx):
     L, R, _ = make_pair(40, 64, 12, 8)
     d = ctx.computeAdaptiveWeight(L, R, 30, 20, 0, 7, 3, 6, strict=True)
