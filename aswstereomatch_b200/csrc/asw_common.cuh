@@ -27,6 +27,8 @@ struct ProfEntry {
 struct asw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // batch transfers overlap the compute stream
+    cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;      // asw_timer_*
     cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;      // per-kernel profiling
     char err[512] = {0};

@@ -34,6 +34,9 @@ extern "C" asw_status asw_create(int device, asw_ctx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_t0) != cudaSuccess || cudaEventCreate(&ctx->ev_t1) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_p0) != cudaSuccess || cudaEventCreate(&ctx->ev_p1) != cudaSuccess) {
         delete ctx;
@@ -45,19 +48,24 @@ extern "C" asw_status asw_create(int device, asw_ctx** out) {
 extern "C" void asw_destroy(asw_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->h2d_stream);
     cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->d2h_stream);
     for (auto& b : ctx->bufs) if (b.p) cudaFree(b.p);
     if (ctx->flush.p) cudaFree(ctx->flush.p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
-    cudaEventDestroy(ctx->ev_p0); cudaEventDestroy(ctx->ev_p1);
+    cudaEventDestroy(ctx->ev_p0); cudaEventDestroy(ctx->ev_p1); cudaEventDestroy(ctx->ev_copy);
+    cudaStreamDestroy(ctx->h2d_stream); cudaStreamDestroy(ctx->d2h_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 extern "C" const char* asw_last_error(const asw_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
 extern "C" asw_status asw_sync(asw_ctx* ctx) {
     if (!ctx) return ASW_ERR_BAD_ARG;
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->h2d_stream));
     ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
     return ASW_OK;
 }
 extern "C" void* asw_stream(asw_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -75,6 +83,11 @@ extern "C" asw_status asw_timer_start(asw_ctx* ctx) {
 }
 extern "C" asw_status asw_timer_stop(asw_ctx* ctx, float* ms) {
     if (!ctx || !ms) return ASW_ERR_BAD_ARG;
+    // the timed region ends when the batch transfer streams have drained too
+    ASW_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->h2d_stream));
+    ASW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    ASW_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->d2h_stream));
+    ASW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
     ASW_CUDA(ctx, cudaEventRecord(ctx->ev_t1, ctx->stream));
     ASW_CUDA(ctx, cudaEventSynchronize(ctx->ev_t1));
     ASW_CUDA(ctx, cudaEventElapsedTime(ms, ctx->ev_t0, ctx->ev_t1));

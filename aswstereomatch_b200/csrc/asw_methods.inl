@@ -306,11 +306,26 @@ extern "C" asw_status asw_stereo_matching(asw_ctx* ctx, const asw_u8_image* L, c
 // -------------------------------------------------------------------------------------------------
 // device-resident batches
 // -------------------------------------------------------------------------------------------------
+// Transfers run on their own streams (H2D and D2H separately: PCIe is full duplex) and are ordered against the
+// compute stream per pair: uploaded[i] -> compute of pair i -> computed[i] -> download of pair i -> downloaded[i]
+// -> next compute of pair i; next upload of pair i waits for computed[i].  Uploading pair i+1 and downloading
+// pair i-1 therefore overlap the kernels of pair i.
 struct asw_batch {
     asw_ctx* ctx; int n, H, W;
     uint8_t* imgs;     // [n][2][H][W][3]
     float* disp;       // [n][H][W]
+    std::vector<cudaEvent_t> uploaded, computed, downloaded;
 };
+static asw_status batch_pair_begin(asw_batch* b, int i) {
+    asw_ctx* ctx = b->ctx;
+    ASW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, b->uploaded[i], 0));
+    ASW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, b->downloaded[i], 0));
+    return ASW_OK;
+}
+static asw_status batch_pair_end(asw_batch* b, int i) {
+    ASW_CUDA(b->ctx, cudaEventRecord(b->computed[i], b->ctx->stream));
+    return ASW_OK;
+}
 extern "C" asw_status asw_batch_create(asw_ctx* ctx, int n_pairs, int rows, int cols, asw_batch** out) {
     if (!ctx || !out || n_pairs <= 0 || rows <= 0 || cols <= 0) return ASW_ERR_BAD_ARG;
     ASW_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -322,13 +337,24 @@ extern "C" asw_status asw_batch_create(asw_ctx* ctx, int n_pairs, int rows, int 
         delete b;
         return asw_fail(ctx, ASW_ERR_NOMEM, "batch allocation failed%s%s");
     }
+    b->uploaded.resize(n_pairs); b->computed.resize(n_pairs); b->downloaded.resize(n_pairs);
+    for (int i = 0; i < n_pairs; i++) {
+        cudaEventCreateWithFlags(&b->uploaded[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&b->computed[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&b->downloaded[i], cudaEventDisableTiming);
+    }
     *out = b;
     return ASW_OK;
 }
 extern "C" void asw_batch_destroy(asw_batch* b) {
     if (!b) return;
     cudaSetDevice(b->ctx->device);
+    cudaStreamSynchronize(b->ctx->h2d_stream);
     cudaStreamSynchronize(b->ctx->stream);
+    cudaStreamSynchronize(b->ctx->d2h_stream);
+    for (size_t i = 0; i < b->uploaded.size(); i++) {
+        cudaEventDestroy(b->uploaded[i]); cudaEventDestroy(b->computed[i]); cudaEventDestroy(b->downloaded[i]);
+    }
     cudaFree(b->imgs); cudaFree(b->disp);
     delete b;
 }
@@ -339,8 +365,11 @@ extern "C" asw_status asw_batch_upload(asw_batch* b, int i, const asw_u8_image* 
     if (L->rows != b->H || L->cols != b->W) return asw_fail(ctx, ASW_ERR_SIZE_MISMATCH, "pair size differs from the batch%s%s");
     ASW_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t n3 = (size_t)b->H * b->W * 3;
-    ASW_TRY(upload_u8(ctx, L, b->imgs + (size_t)i * 2 * n3));
-    ASW_TRY(upload_u8(ctx, R, b->imgs + (size_t)i * 2 * n3 + n3));
+    ASW_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, b->computed[i], 0));     // the previous run still reads this pair
+    size_t rowb = (size_t)b->W * 3;
+    ASW_CUDA(ctx, cudaMemcpy2DAsync(b->imgs + (size_t)i * 2 * n3, rowb, L->data, L->step, rowb, b->H, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    ASW_CUDA(ctx, cudaMemcpy2DAsync(b->imgs + (size_t)i * 2 * n3 + n3, rowb, R->data, R->step, rowb, b->H, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    ASW_CUDA(ctx, cudaEventRecord(b->uploaded[i], ctx->h2d_stream));
     return ASW_OK;
 }
 extern "C" asw_status asw_batch_run_guidedf2_lr_refine(asw_batch* b, double eps, int win, int min_d, int num_d, float tol,
@@ -352,8 +381,10 @@ extern "C" asw_status asw_batch_run_guidedf2_lr_refine(asw_batch* b, double eps,
     size_t n = (size_t)b->H * b->W, n3 = n * 3;
     for (int i = 0; i < b->n; i++) {
         const uint8_t* dL = b->imgs + (size_t)i * 2 * n3;
+        ASW_TRY(batch_pair_begin(b, i));
         ASW_TRY(dev_guidedf2_lr_refine(ctx, dL, dL + n3, b->H, b->W, eps, win, min_d, num_d, tol, rate_s, rate_r,
                                        b->disp + (size_t)i * n, nullptr, nullptr, nullptr));
+        ASW_TRY(batch_pair_end(b, i));
     }
     return ASW_OK;
 }
@@ -368,7 +399,9 @@ extern "C" asw_status asw_batch_run_method(asw_batch* b, int algorithm, int disp
     size_t n = (size_t)b->H * b->W, n3 = n * 3;
     for (int i = 0; i < b->n; i++) {
         const uint8_t* dL = b->imgs + (size_t)i * 2 * n3;
+        ASW_TRY(batch_pair_begin(b, i));
         ASW_TRY(dev_run_method(ctx, m, dL, dL + n3, b->H, b->W, b->disp + (size_t)i * n, nullptr));
+        ASW_TRY(batch_pair_end(b, i));
     }
     return ASW_OK;
 }
@@ -378,7 +411,10 @@ extern "C" asw_status asw_batch_download(asw_batch* b, int i, asw_f32_image* dis
     ASW_TRY(check_f32(ctx, disp));
     if (disp->rows != b->H || disp->cols != b->W) return asw_fail(ctx, ASW_ERR_SIZE_MISMATCH, "map size differs from the batch%s%s");
     ASW_CUDA(ctx, cudaSetDevice(ctx->device));
-    ASW_TRY(download_f32(ctx, b->disp + (size_t)i * b->H * b->W, disp));
+    ASW_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, b->computed[i], 0));
+    size_t rowb = (size_t)b->W * 4;
+    ASW_CUDA(ctx, cudaMemcpy2DAsync(disp->data, disp->step, b->disp + (size_t)i * b->H * b->W, rowb, rowb, b->H, cudaMemcpyDeviceToHost, ctx->d2h_stream));
+    ASW_CUDA(ctx, cudaEventRecord(b->downloaded[i], ctx->d2h_stream));
     return ASW_OK;
 }
 
