@@ -96,6 +96,71 @@ __global__ void k_grid_pass(double* __restrict__ S, int* __restrict__ C, GridDim
     grid_pass_line(s + base, c + base, stride, n);
 }
 
+// splat + w + z fused: the CTA builds the (z, w) planes it owns directly in shared memory from the ~(2 sS)^2
+// pixels whose spatial key (cvRound(x/sS), cvRound(y/sS)) is the plane's (A.cpp:1897-1912; |L-R| is an integer, so
+// integer shared-memory atomics are exact and order independent), runs both recursive passes there and writes the
+// plane once: no zero-fill of the grid, no global atomics, no read-back before the first two passes, and no strided
+// per-thread global lines (the stand-alone w pass walked 28-cell lines with a 224-byte stride between threads).
+// One thread per line in shared memory, odd pitch against bank conflicts; PL planes per CTA, grid-stride.
+__global__ void __launch_bounds__(128)
+k_grid_build_wz(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, int H, int W, int d_first,
+                double* __restrict__ S, int* __restrict__ C, GridDims g, size_t n_planes, int PL) {
+    extern __shared__ double sm_grid[];
+    const int X = g.nx + 1, Y = g.ny + 1, Z = g.nz + 1, Wd = g.nw + 1, pitch = Wd | 1, cells = Z * Wd;
+    double* ss = sm_grid;                                   // [PL][Z][pitch]
+    int* cc = (int*)(ss + (size_t)PL * Z * pitch);          // [PL][Z][pitch]
+    int* si = cc + (size_t)PL * Z * pitch;                  // [PL][Z][pitch] integer sums while splatting
+    unsigned char* okf = (unsigned char*)(si + (size_t)PL * Z * pitch);   // [PL][2][side] key-match flags
+    const int tid = threadIdx.x;
+    const int rs = (int)ceil(g.rate_s);                     // pixels farther than this from sS*k cannot round to k
+    const int side = 2 * rs + 3;
+    for (size_t p0 = (size_t)blockIdx.x * PL; p0 < n_planes; p0 += (size_t)gridDim.x * PL) {
+        const int np = (int)min((size_t)PL, n_planes - p0);
+        for (int i = tid; i < np * Z * pitch; i += 128) { cc[i] = 0; si[i] = 0; }
+        // which columns / rows of the candidate window carry this plane's spatial key (2 * side tests per plane
+        // instead of side^2 double divisions)
+        for (int i = tid; i < np * 2 * side; i += 128) {
+            const int pl = i / (2 * side), r = i - pl * 2 * side, is_y = r >= side, o = is_y ? r - side : r;
+            const size_t p = p0 + pl;
+            const int xy = (int)(p % ((size_t)X * Y)), kx = xy / Y, ky = xy - kx * Y, k = is_y ? ky : kx;
+            const int v = (int)lrint(k * g.rate_s) - rs - 1 + o, lim = is_y ? H : W;
+            okf[i] = (v >= 0 && v < lim && cv_round((double)v / g.rate_s) == k) ? 1 : 0;
+        }
+        __syncthreads();
+        for (int i = tid; i < np * side * side; i += 128) {
+            const int pl = i / (side * side), r = i - pl * side * side, ox = r % side, oy = r / side;
+            if (!(okf[pl * 2 * side + ox] & okf[pl * 2 * side + side + oy])) continue;
+            const size_t p = p0 + pl;
+            const int gi = (int)(p / ((size_t)X * Y)), xy = (int)(p - (size_t)gi * X * Y), kx = xy / Y, ky = xy - kx * Y;
+            const int x = (int)lrint(kx * g.rate_s) - rs - 1 + ox, y = (int)lrint(ky * g.rate_s) - rs - 1 + oy;
+            const int d = d_first + gi;
+            const float lf = (float)lg[(size_t)y * W + x], rf = (float)rg[(size_t)y * W + max(0, x - d)];
+            const int kz = cv_round((double)lf / g.rate_r), kw = cv_round((double)rf / g.rate_r);
+            const int a = (pl * Z + kz) * pitch + kw;
+            atomicAdd(&si[a], (int)fabsf(lf - rf));         // A.cpp:1897-1912
+            atomicAdd(&cc[a], 1);
+        }
+        __syncthreads();
+        for (int i = tid; i < np * Z * pitch; i += 128) ss[i] = (double)si[i];
+        __syncthreads();
+        for (int l = tid; l < np * Z; l += 128)             // w pass: line = (plane, z), unit stride
+            grid_pass_line(ss + (size_t)l * pitch, cc + (size_t)l * pitch, 1, g.nw);
+        __syncthreads();
+        for (int l = tid; l < np * Wd; l += 128) {          // z pass: line = (plane, w), stride = pitch
+            const int pl = l / Wd, w = l - pl * Wd;
+            grid_pass_line(ss + (size_t)pl * Z * pitch + w, cc + (size_t)pl * Z * pitch + w, pitch, g.nz);
+        }
+        __syncthreads();
+        const size_t base = p0 * cells;
+        for (int i = tid; i < np * cells; i += 128) {
+            const int pl = i / cells, r = i - pl * cells, z = r / Wd, w = r - z * Wd;
+            S[base + i] = ss[(pl * Z + z) * pitch + w];
+            C[base + i] = cc[(pl * Z + z) * pitch + w];
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void k_grid_slice(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, int H, int W, int d_first,
                              int cand_first, GridDims g, const double* __restrict__ S, const int* __restrict__ C,
                              unsigned long long* __restrict__ keys, float* __restrict__ agg) {
@@ -168,12 +233,28 @@ static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint
     ASW_TRY(init_keys(ctx, keys, n));
     for (int c0 = 0; c0 < n_cand; c0 += batch) {
         int nb = n_cand - c0 < batch ? n_cand - c0 : batch;
-        ASW_CUDA(ctx, cudaMemsetAsync(S, 0, g.cells * nb * sizeof(double), ctx->stream));      // A.cpp:1874-1892
-        ASW_CUDA(ctx, cudaMemsetAsync(C, 0, g.cells * nb * sizeof(int), ctx->stream));
-        LAUNCH(ctx, "grid_splat", (k_grid_splat<<<dim3(cdiv(W, 128), H, nb), 128, 0, ctx->stream>>>(gl, gr, H, W, min_d + c0, g, S, C)));
-        for (int axis = 0; axis < 4; axis++) {
+        // splat + w + z fused through shared memory when a few (z, w) planes fit; otherwise zero-fill, global splat
+        // and one launch per axis
+        const int Zd = g.nz + 1, Wdd = g.nw + 1;
+        const size_t plane_bytes = (size_t)Zd * (Wdd | 1) * 16;       // double sum + int count + int splat sum
+        int first_axis = 0;
+        if (plane_bytes <= 96 * 1024 && !getenv("ASW_GRID_UNFUSED")) {
+            int PL = std::max(1, std::min(128 / std::max(Zd, Wdd), (int)((96 * 1024) / plane_bytes)));
+            size_t smem = plane_bytes * PL + (size_t)PL * 2 * (2 * (int)ceil(rate_s) + 3) + 16;
+            size_t n_planes = (size_t)(g.nx + 1) * (g.ny + 1) * nb;
+            cudaFuncSetAttribute(k_grid_build_wz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            unsigned blocks = (unsigned)std::min<size_t>((n_planes + PL - 1) / PL, (size_t)ctx->sm_count * 32);
+            LAUNCH(ctx, "grid_build_wz", (k_grid_build_wz<<<blocks, 128, smem, ctx->stream>>>(gl, gr, H, W, min_d + c0, S, C, g, n_planes, PL)));
+            first_axis = 2;
+        } else {
+            ASW_CUDA(ctx, cudaMemsetAsync(S, 0, g.cells * nb * sizeof(double), ctx->stream));      // A.cpp:1874-1892
+            ASW_CUDA(ctx, cudaMemsetAsync(C, 0, g.cells * nb * sizeof(int), ctx->stream));
+            LAUNCH(ctx, "grid_splat", (k_grid_splat<<<dim3(cdiv(W, 128), H, nb), 128, 0, ctx->stream>>>(gl, gr, H, W, min_d + c0, g, S, C)));
+        }
+        for (int axis = first_axis; axis < 4; axis++) {
             size_t lines = g.cells / (size_t)((axis == 0 ? g.nw : axis == 1 ? g.nz : axis == 2 ? g.ny : g.nx) + 1) * nb;
-            LAUNCH(ctx, "grid_pass", (k_grid_pass<<<(unsigned)((lines + 127) / 128), 128, 0, ctx->stream>>>(S, C, g, axis, nb)));
+            static const char* pass_name[4] = {"grid_pass_w", "grid_pass_z", "grid_pass_y", "grid_pass_x"};
+            LAUNCH(ctx, pass_name[axis], (k_grid_pass<<<(unsigned)((lines + 127) / 128), 128, 0, ctx->stream>>>(S, C, g, axis, nb)));
         }
         LAUNCH(ctx, "grid_slice", (k_grid_slice<<<dim3(cdiv(W, 128), H, nb), 128, 0, ctx->stream>>>(gl, gr, H, W, min_d + c0, c0, g, S, C, keys, agg_dev)));
     }
