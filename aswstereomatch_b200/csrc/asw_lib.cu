@@ -429,10 +429,17 @@ static asw_status dev_cost_sad_box(asw_ctx* ctx, const uint8_t* dL, const uint8_
     ASW_TRY(ws_get(ctx, WS_GRAY_R, (size_t)H * v.Wp, &gtgt));
     LAUNCH(ctx, "bgr2gray", (k_bgr2gray_pad<<<dim3(cdiv(W, 256), H), 256, 0, ctx->stream>>>(v.ref, H, W, 0, 0, gref)));
     LAUNCH(ctx, "bgr2gray", (k_bgr2gray_pad<<<dim3(cdiv(v.Wp, 256), H), 256, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, gtgt)));
-    float* ad;
-    ASW_TRY(ws_get(ctx, WS_VOL1, n * num_d, &ad));
-    LAUNCH(ctx, "gray_absdiff", (k_gray_absdiff<<<dim3(cdiv(W, 256), H, num_d), 256, 0, ctx->stream>>>(gref, gtgt, H, W, v.Wp, v.x0_base, v.x0_step, ad)));
-    ASW_TRY(launch_box_f32(ctx, ad, vol, H, W, win, num_d, n));
+    if (win - 1 < SADBOX_COLS / 2) {
+        int bands = std::max(1, std::min(cdiv(H, 4 * win), cdiv(4 * ctx->sm_count, cdiv(W, SADBOX_COLS - (win - 1)) * num_d)));
+        int band_rows = cdiv(cdiv(H, bands), 4) * 4;
+        dim3 grid(cdiv(W, SADBOX_COLS - (win - 1)), cdiv(H, band_rows), num_d);
+        LAUNCH(ctx, "sad_box", (k_sad_box_u8<4><<<grid, SADBOX_COLS, 0, ctx->stream>>>(gref, gtgt, H, W, v.Wp, v.x0_base, v.x0_step, win, band_rows, vol)));
+    } else {
+        float* ad;
+        ASW_TRY(ws_get(ctx, WS_VOL1, n * num_d, &ad));
+        LAUNCH(ctx, "gray_absdiff", (k_gray_absdiff<<<dim3(cdiv(W, 256), H, num_d), 256, 0, ctx->stream>>>(gref, gtgt, H, W, v.Wp, v.x0_base, v.x0_step, ad)));
+        ASW_TRY(launch_box_f32(ctx, ad, vol, H, W, win, num_d, n));
+    }
     if (gray_ref_out) *gray_ref_out = gref;
     if (gray_tgt_out) *gray_tgt_out = gtgt;
     return ASW_OK;

@@ -177,6 +177,184 @@ k_blo1_aggregate(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpa
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Register-resident BLO(1) aggregation (window side as template constant).
+//
+// One CTA = 256 threads owns a tile of WIN+1 rows x (128 - (WIN-1)) columns and walks a chunk of
+// disparities.  The 2*WIN halo rows of the tile split into two blocks of WIN rows; thread (g, cx) keeps
+// block g of halo column cx in registers as three floats per element,
+//     a = L*R_d, b = L+R_d, c = c_d,
+// so that for a level k the product |L-k|*|R_d-k|*c_d of A.cpp:2571-2583 is |a - k*b + k^2| * c: one FFMA
+// and one FADD (both exact: integers below 2^24) plus the FFMA that accumulates the block's running sum.
+// A window of WIN rows is always "suffix of block 0 + prefix of block 1", so the vertical window sums
+// of all WIN+1 output rows come out of the two running sums with no halo recomputation.  The horizontal
+// window sums go through shared memory as 32-column segment prefix sums; only the pixels that consume
+// the level (every pixel consumes <= 2 levels: A.cpp:2656-2667) read them, through a list of the
+// tile's pixels sorted by level that is built once per CTA.  Only levels some pixel of the tile
+// consumes are evaluated; nothing per-level reaches HBM.
+// ---------------------------------------------------------------------------------------------
+#define BLO2_COLS 128
+#define BLO2_PITCH 132
+#define BLO2_THREADS 256
+
+template <int WIN>
+__global__ void __launch_bounds__(BLO2_THREADS, 2)
+k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, const float* __restrict__ cost,
+            const float* __restrict__ Nk, BloGeom g, int dch, int d_label0, unsigned long long* __restrict__ keys,
+            float* __restrict__ agg) {
+    constexpr int TH = WIN + 1, SW = BLO2_COLS - (WIN - 1), NPIX = TH * SW, h = WIN / 2, PITCH = BLO2_PITCH;
+    extern __shared__ float sm_blo2[];
+    float* U = sm_blo2;                                           // [2][WIN][PITCH] running sums of the two blocks
+    float* Q = U + 2 * WIN * PITCH;                               // [TH][PITCH]     segment prefix sums of the row sums
+    float* part = Q + TH * PITCH;                                 // [NPIX]          (I - lo) * JB_lo
+    uint32_t* list = (uint32_t*)(part + NPIX);                    // [NPIX]          pixel | I << 16 | is_level << 24
+    unsigned long long* bestk = (unsigned long long*)(list + NPIX);   // [NPIX]
+    __shared__ int lstart[BLO_MAXLEV + 1];                        // lstart[k] = first list entry of level k; lstart[nl] = total
+    __shared__ int cursor[BLO_MAXLEV + 1];
+    __shared__ uint32_t need[(BLO_MAXLEV + 31) / 32];
+    const int tid = threadIdx.x, grp = tid >> 7, cx = tid & 127;
+    const int x0 = blockIdx.x * SW, y0 = blockIdx.y * TH;
+    const size_t n = (size_t)g.H * g.W;
+
+    // ---- pixel list sorted by (lower) level ----
+    for (int i = tid; i < BLO_MAXLEV + 1; i += BLO2_THREADS) lstart[i] = 0;
+    for (int i = tid; i < BLO_MAXLEV + 1; i += BLO2_THREADS) cursor[i] = 0;
+    if (tid < (BLO_MAXLEV + 31) / 32) need[tid] = 0;
+    __syncthreads();
+    for (int p = tid; p < NPIX; p += BLO2_THREADS) {
+        int o = p / SW, xo = p - o * SW, y = y0 + o, x = x0 + xo;
+        bestk[p] = WTA_KEY_EMPTY;
+        if (x < g.W && y < g.H) {
+            int I = lg[(size_t)y * g.W + x];
+            bool isl = (I % g.step == 0) || I == 255;               // discretInten membership (A.cpp:2656)
+            int key = (I == 255 && g.last255) ? g.nl - 1 : I / g.step;
+            atomicAdd(&lstart[key], 1);
+            atomicOr(&need[key >> 5], 1u << (key & 31));
+            if (!isl) atomicOr(&need[(key + 1) >> 5], 1u << ((key + 1) & 31));   // hi level = next level (A.cpp:2658-2663)
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int s = 0;                                                 // counts -> exclusive prefix
+        for (int i = 0; i <= g.nl; i++) { int c = lstart[i]; lstart[i] = s; s += c; }
+    }
+    __syncthreads();
+    for (int p = tid; p < NPIX; p += BLO2_THREADS) {
+        int o = p / SW, xo = p - o * SW, y = y0 + o, x = x0 + xo;
+        if (x < g.W && y < g.H) {
+            int I = lg[(size_t)y * g.W + x];
+            bool isl = (I % g.step == 0) || I == 255;
+            int key = (I == 255 && g.last255) ? g.nl - 1 : I / g.step;
+            int pos = lstart[key] + atomicAdd(&cursor[key], 1);
+            list[pos] = (uint32_t)p | ((uint32_t)I << 16) | ((uint32_t)isl << 24);
+        }
+    }
+    __syncthreads();
+    const int sx = border_idx(x0 - h + cx, g.W, 1);                // boxFilter BORDER_REFLECT_101
+    float* Ug = U + grp * (WIN * PITCH) + cx;
+    const float inv = 1.0f / (float)(WIN * WIN);
+
+    for (int dd = 0; dd < dch; dd++) {
+        const int di = blockIdx.z * dch + dd;
+        if (di >= g.D) break;
+        const int xoff = g.x0_base + g.x0_step * di;
+        const float* cd = cost + (size_t)di * n;
+        float a[WIN], b[WIN], c[WIN];
+#pragma unroll
+        for (int i = 0; i < WIN; i++) {
+            int r = grp ? WIN + i : WIN - 1 - i;                   // block 0 runs upwards: its running sum is a suffix sum
+            int sy = border_idx(y0 - h + r, g.H, 1);
+            int l = lg[(size_t)sy * g.W + sx], rr = rpad[(size_t)sy * g.Wp + xoff + sx];
+            a[i] = (float)(l * rr);
+            b[i] = (float)(l + rr);
+            c[i] = __ldg(&cd[(size_t)sy * g.W + sx]);
+        }
+        for (int li = 0; li < g.nl; li++) {
+            if (!((need[li >> 5] >> (li & 31)) & 1u)) continue;   // block-uniform
+            const int k = blo_level_value(g, li);
+            const float kf = (float)k, k2 = (float)(k * k);
+            float run = 0.0f;
+#pragma unroll
+            for (int i = 0; i < WIN; i++) {
+                float t = __fadd_rn(fmaf(b[i], -kf, a[i]), k2);    // (L-k)*(R-k), exact
+                run = fmaf(fabsf(t), c[i], run);                   // + |L-k|*|R-k|*c   (A.cpp:2571-2583)
+                Ug[i * PITCH] = run;
+            }
+            __syncthreads();
+            if (tid < 4 * TH) {
+                const int seg = tid / TH, o = tid - seg * TH;
+                // rows [o, o+WIN-1] of the halo = block-0 suffix from row o + block-1 prefix up to row o-1
+                const float4* u0 = (const float4*)(U + (WIN - 1 - o) * PITCH + seg * 32);
+                const float4* u1 = (const float4*)(U + (WIN + o - 1) * PITCH + seg * 32);
+                float4* q = (float4*)(Q + o * PITCH + seg * 32);
+                const bool h0 = o < WIN, h1 = o >= 1;
+                float s = 0.0f;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    float4 v = h0 ? u0[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 w = h1 ? u1[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 r4;
+                    s += v.x + w.x; r4.x = s;
+                    s += v.y + w.y; r4.y = s;
+                    s += v.z + w.z; r4.z = s;
+                    s += v.w + w.w; r4.w = s;
+                    q[j] = r4;
+                }
+            }
+            __syncthreads();
+            const int e1 = lstart[li], e0 = li > 0 ? lstart[li - 1] : e1, e2 = lstart[li + 1];   // level li-1 | level li
+            for (int t = e0 + tid; t < e2; t += BLO2_THREADS) {
+                const uint32_t e = list[t];
+                const bool role_hi = t < e1, isl = (e >> 24) & 1u;
+                if (role_hi && isl) continue;
+                const int pix = e & 0xFFFF, I = (e >> 16) & 0xFF;
+                const int o = pix / SW, xo = pix - o * SW;
+                const float* q = Q + o * PITCH;
+                const int cr = xo + WIN - 1, segr = cr >> 5;
+                float sum = q[cr];
+                int s = 0;
+                if (xo > 0) { sum -= q[xo - 1]; s = (xo - 1) >> 5; }
+                for (; s < segr; s++) sum += q[s * 32 + 31];
+                const size_t p = (size_t)(y0 + o) * g.W + (x0 + xo);
+                const float nk = __ldg(&Nk[(size_t)li * n + p]);
+                const float jb = __fdiv_rn(sum * inv, nk);                        // A.cpp:2594
+                float cst;
+                if (!role_hi) {
+                    if (!isl) { part[pix] = __fmul_rn((float)(I - k), jb); continue; }   // (I - lo) * JB_lo
+                    cst = jb;                                                     // I is a level: cost = JB_{I,d}
+                } else {
+                    cst = __fadd_rn(part[pix], __fmul_rn((float)(k - I), jb));    // + (hi - I) * JB_hi  (A.cpp:2666-2667)
+                }
+                if (agg) agg[(size_t)di * n + p] = cst;
+                const unsigned long long key = wta_key(cst, d_label0 + di);
+                if (key < bestk[pix]) bestk[pix] = key;
+            }
+            // the next level's running sums overwrite U only (the scan above is behind a barrier); Q, part and
+            // bestk are next touched after the next barrier
+        }
+        __syncthreads();
+    }
+    for (int p = tid; p < NPIX; p += BLO2_THREADS) {
+        int o = p / SW, xo = p - o * SW, y = y0 + o, x = x0 + xo;
+        if (x < g.W && y < g.H && bestk[p] != WTA_KEY_EMPTY) atomicMin(&keys[(size_t)y * g.W + x], bestk[p]);
+    }
+}
+
+template <int WIN>
+static asw_status launch_blo1_agg2(asw_ctx* ctx, const uint8_t* gref, const uint8_t* gtgt, const float* cost, const float* Nk,
+                                   const BloGeom& g, int min_d, unsigned long long* keys, float* agg_dev) {
+    constexpr int TH = WIN + 1, SW = BLO2_COLS - (WIN - 1), NPIX = TH * SW;
+    size_t smem = ((size_t)2 * WIN * BLO2_PITCH + (size_t)TH * BLO2_PITCH + NPIX) * sizeof(float) +
+                  (size_t)NPIX * sizeof(uint32_t) + (size_t)NPIX * sizeof(unsigned long long);
+    cudaFuncSetAttribute(k_blo1_agg2<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dch = 8;
+    const char* e = getenv("ASW_BLO_DCH");
+    if (e && atoi(e) > 0) dch = atoi(e);
+    dim3 grid(cdiv(g.W, SW), cdiv(g.H, TH), cdiv(g.D, dch));
+    LAUNCH(ctx, "blo1_aggregate", (k_blo1_agg2<WIN><<<grid, BLO2_THREADS, smem, ctx->stream>>>(gref, gtgt, cost, Nk, g, dch, min_d, keys, agg_dev)));
+    return ASW_OK;
+}
+
 static asw_status dev_blo1(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_r, int win,
                            int min_d, int num_d, float* disp_dev, float* agg_dev) {
     size_t n = (size_t)H * W;
@@ -208,7 +386,18 @@ static asw_status dev_blo1(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, i
     unsigned long long* keys;
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
     ASW_TRY(init_keys(ctx, keys, n));
-    LAUNCH(ctx, "blo1_aggregate", (k_blo1_aggregate<<<dim3(tiles.x, tiles.y, num_d), BLO_THREADS, smem_a, ctx->stream>>>(
-                                      gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)));
+    const char* tiled = getenv("ASW_BLO_TILED");
+    const bool generic = tiled && atoi(tiled) == 1;
+    switch (generic ? 0 : win) {
+        case 5: ASW_TRY(launch_blo1_agg2<5>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+        case 7: ASW_TRY(launch_blo1_agg2<7>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+        case 9: ASW_TRY(launch_blo1_agg2<9>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+        case 15: ASW_TRY(launch_blo1_agg2<15>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+        case 25: ASW_TRY(launch_blo1_agg2<25>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+        case 35: ASW_TRY(launch_blo1_agg2<35>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+        default:
+            LAUNCH(ctx, "blo1_aggregate_tiled", (k_blo1_aggregate<<<dim3(tiles.x, tiles.y, num_d), BLO_THREADS, smem_a, ctx->stream>>>(
+                                                    gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)));
+    }
     return keys_to_disp(ctx, keys, n, disp_dev);
 }

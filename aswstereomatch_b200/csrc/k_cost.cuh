@@ -95,6 +95,55 @@ __global__ void k_gray_absdiff(const uint8_t* __restrict__ ref, const uint8_t* _
     vol[((size_t)di * H + y) * W + x] = (float)abs(v);
 }
 
+// Fused getCostSAD_d (A.cpp:2477-2480) for every d: gray |L - R_d| -> normalised win x win boxFilter,
+// BORDER_REFLECT_101.  The absolute differences are integers, so the window sum is exact in int32 whatever the
+// order, and (float)(sum * (1/win^2)) in double is what cv::boxFilter returns.  One thread per halo column walks
+// down a band of rows keeping the vertical window sum in a register (one row in, one row out); the
+// horizontal sums run over shared memory, RB rows per barrier.  Nothing but the result reaches HBM.
+#define SADBOX_COLS 256
+template <int RB>
+__global__ void __launch_bounds__(SADBOX_COLS)
+k_sad_box_u8(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, int H, int W, int Wp, int x0_base,
+             int x0_step, int win, int band_rows, float* __restrict__ vol) {
+    __shared__ int vs[2][RB][SADBOX_COLS];
+    const int h = win / 2, SW = SADBOX_COLS - (win - 1);
+    const int cx = threadIdx.x, x0 = blockIdx.x * SW, di = blockIdx.z;
+    const int sx = border_idx(x0 - h + cx, W, 1);
+    const uint8_t* rc = ref + sx;
+    const uint8_t* tc = tgt + x0_base + x0_step * di + sx;
+    const int y_begin = blockIdx.y * band_rows, y_end = min(H, y_begin + band_rows);
+    auto ad = [&](int y) {
+        int sy = border_idx(y, H, 1);
+        return abs((int)rc[(size_t)sy * W] - (int)tc[(size_t)sy * Wp]);
+    };
+    int s = 0;
+    for (int j = -h; j < h; j++) s += ad(y_begin + j);
+    const double scale = 1.0 / ((double)win * win);
+    const bool writer = cx < SW && x0 + cx < W;
+    float* out = vol + (size_t)di * H * W + x0 + cx;
+    int buf = 0;
+    for (int y = y_begin; y < y_end; y += RB) {
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            s += ad(y + r + h);
+            vs[buf][r][cx] = s;
+            s -= ad(y + r - h);
+        }
+        __syncthreads();
+        if (writer) {
+#pragma unroll
+            for (int r = 0; r < RB; r++) {
+                if (y + r < y_end) {
+                    int acc = 0;
+                    for (int j = 0; j < win; j++) acc += vs[buf][r][cx + j];
+                    out[(size_t)(y + r) * W] = (float)((double)acc * scale);
+                }
+            }
+        }
+        buf ^= 1;
+    }
+}
+
 // WTA over a materialised volume -> 64-bit keys (strict <, ascending d, NaN/inf never win)
 __global__ void k_wta_keys(const float* __restrict__ vol, int D, size_t n, int d_first,
                            unsigned long long* __restrict__ keys) {

@@ -121,7 +121,8 @@ def test_bilateral_grid(ctx, H, W, D, sS, sR, seed):
     assert np.array_equal(d, d_ref)
 
 
-@pytest.mark.parametrize("H,W,D,win,seed", [(40, 56, 8, 7, 7), (64, 96, 12, 9, 2), (70, 100, 8, 35, 3)])
+@pytest.mark.parametrize("H,W,D,win,seed", [(40, 56, 8, 7, 7), (64, 96, 12, 9, 2), (70, 100, 8, 35, 3), (50, 300, 20, 15, 4),
+                                            (150, 200, 9, 25, 5), (48, 64, 8, 11, 6)])
 def test_blo1(ctx, H, W, D, win, seed):
     L, R, _ = make_pair(H, W, D, seed)
     d, q = ctx.computeAdaptiveWeight_BLO1(L, R, 0, 0.015, win, 0, D, agg=True, strict=True)
