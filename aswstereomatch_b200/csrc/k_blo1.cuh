@@ -28,6 +28,8 @@ __device__ __forceinline__ int blo_level_value(const BloGeom& g, int li) {
 }
 
 // N_k = box(|L-k| * |R_{D-1}-k|), exact: integer window sums, (float)(sum * (1/win^2)) as cv::boxFilter.
+// Only the two levels a pixel consumes are kept: Nk is [H][W][2] = {N at the lower level, N at the next level}
+// (7 MB at 1280x720, L2-resident) instead of the nl full-resolution planes.
 // grid: (tiles_x, tiles_y, nl)
 __global__ void __launch_bounds__(BLO_THREADS)
 k_blo1_norm(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, BloGeom g, float* __restrict__ Nk) {
@@ -63,11 +65,19 @@ k_blo1_norm(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, Bl
         int s = 0;
         for (int j = 0; j < win; j++) s += src[j * HP];
         const double scale = 1.0 / ((double)win * win);
+        const int li = blockIdx.z;
 #pragma unroll
         for (int o = 0; o < 8; o++) {
             if (o > 0) s += src[(o - 1 + win) * HP] - src[(o - 1) * HP];
             int y = y0t + rseg * 8 + o;
-            if (x < g.W && y < g.H) Nk[(size_t)blockIdx.z * g.H * g.W + (size_t)y * g.W + x] = (float)((double)s * scale);
+            if (x < g.W && y < g.H) {
+                // a pixel consumes N_k at its lower level (slot 0) and, unless its intensity is a level, at the next one (slot 1)
+                const int I = lg[(size_t)y * g.W + x];
+                const bool isl = (I % g.step == 0) || I == 255;
+                const int key = (I == 255 && g.last255) ? g.nl - 1 : I / g.step;
+                if (li == key) Nk[((size_t)y * g.W + x) * 2] = (float)((double)s * scale);
+                else if (li == key + 1 && !isl) Nk[((size_t)y * g.W + x) * 2 + 1] = (float)((double)s * scale);
+            }
         }
     }
 }
@@ -155,7 +165,7 @@ k_blo1_aggregate(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpa
                 if (o > 0) s += src[(o - 1 + win) * HP] - src[(o - 1) * HP];
                 if (lo_li[o] == li || hi_li[o] == li) {
                     int y = y0t + rseg * 8 + o;
-                    float nk = __ldg(&Nk[(size_t)li * n + (size_t)y * g.W + x]);
+                    float nk = __ldg(&Nk[((size_t)y * g.W + x) * 2 + (lo_li[o] == li ? 0 : 1)]);
                     float jb = __fdiv_rn(s * inv, nk);                          // A.cpp:2594
                     if (hi_li[o] < 0) part_lo[o] = jb;                          // I is a level: cost = JB_{I,d}
                     else if (lo_li[o] == li) part_lo[o] = __fmul_rn((float)(I8[o] - k), jb);    // (I - lo) * JB_lo
@@ -204,8 +214,10 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
             float* __restrict__ agg) {
     constexpr int TH = WIN + 1, SW = BLO2_COLS - (WIN - 1), NPIX = TH * SW, h = WIN / 2, PITCH = BLO2_PITCH;
     extern __shared__ float sm_blo2[];
-    float* U = sm_blo2;                                           // [2][WIN][PITCH] running sums of the two blocks
-    float* Q = U + 2 * WIN * PITCH;                               // [TH][PITCH]     segment prefix sums of the row sums
+    // running sums of the two blocks, each preceded by a row of zeros: [Z][U0: WIN rows][Z][U1: WIN rows]
+    float* U0 = sm_blo2 + PITCH;
+    float* U1 = U0 + (WIN + 1) * PITCH;
+    float* Q = U1 + WIN * PITCH;                                  // [TH][PITCH]     segment prefix sums of the row sums
     float* part = Q + TH * PITCH;                                 // [NPIX]          (I - lo) * JB_lo
     uint32_t* list = (uint32_t*)(part + NPIX);                    // [NPIX]          pixel | I << 16 | is_level << 24
     unsigned long long* bestk = (unsigned long long*)(list + NPIX);   // [NPIX]
@@ -251,7 +263,8 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
     }
     __syncthreads();
     const int sx = border_idx(x0 - h + cx, g.W, 1);                // boxFilter BORDER_REFLECT_101
-    float* Ug = U + grp * (WIN * PITCH) + cx;
+    float* Ug = (grp ? U1 : U0) + cx;
+    if (tid < PITCH) { U0[tid - PITCH] = 0.0f; U1[tid - PITCH] = 0.0f; }
     const float inv = 1.0f / (float)(WIN * WIN);
 
     for (int dd = 0; dd < dch; dd++) {
@@ -273,6 +286,15 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
             if (!((need[li >> 5] >> (li & 31)) & 1u)) continue;   // block-uniform
             const int k = blo_level_value(g, li);
             const float kf = (float)k, k2 = (float)(k * k);
+            // this thread's first consumer entry of the level: fetch its normaliser now, use it after the two barriers
+            const int e1 = lstart[li], e0 = li > 0 ? lstart[li - 1] : e1, e2 = lstart[li + 1];   // level li-1 | level li
+            float nk_pre = 0.0f;
+            const int rt = BLO2_THREADS - 1 - tid;                 // consumers are taken by the highest threads first:
+            if (e0 + rt < e2) {                                    // the scan keeps the lowest 4 * TH threads busy
+                const uint32_t e = list[e0 + rt];
+                const int pix = e & 0xFFFF, o = pix / SW, xo = pix - o * SW;
+                nk_pre = __ldg(&Nk[((size_t)(y0 + o) * g.W + (x0 + xo)) * 2 + (e0 + rt < e1 ? 1 : 0)]);
+            }
             float run = 0.0f;
 #pragma unroll
             for (int i = 0; i < WIN; i++) {
@@ -284,26 +306,26 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
             if (tid < 4 * TH) {
                 const int seg = tid / TH, o = tid - seg * TH;
                 // rows [o, o+WIN-1] of the halo = block-0 suffix from row o + block-1 prefix up to row o-1
-                const float4* u0 = (const float4*)(U + (WIN - 1 - o) * PITCH + seg * 32);
-                const float4* u1 = (const float4*)(U + (WIN + o - 1) * PITCH + seg * 32);
+                // (o = WIN: the suffix is empty -> the zero row before U0; o = 0: the prefix is empty -> the zero row before U1)
+                const float4* u0 = (const float4*)(U0 + (WIN - 1 - o) * PITCH + seg * 32);
+                const float4* u1 = (const float4*)(U1 + (o - 1) * PITCH + seg * 32);
                 float4* q = (float4*)(Q + o * PITCH + seg * 32);
-                const bool h0 = o < WIN, h1 = o >= 1;
                 float s = 0.0f;
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    float4 v = h0 ? u0[j] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 w = h1 ? u1[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 v = u0[j];
+                    const float4 w = u1[j];
                     float4 r4;
-                    s += v.x + w.x; r4.x = s;
-                    s += v.y + w.y; r4.y = s;
-                    s += v.z + w.z; r4.z = s;
-                    s += v.w + w.w; r4.w = s;
+                    v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;          // off the dependent chain
+                    s += v.x; r4.x = s;
+                    s += v.y; r4.y = s;
+                    s += v.z; r4.z = s;
+                    s += v.w; r4.w = s;
                     q[j] = r4;
                 }
             }
             __syncthreads();
-            const int e1 = lstart[li], e0 = li > 0 ? lstart[li - 1] : e1, e2 = lstart[li + 1];   // level li-1 | level li
-            for (int t = e0 + tid; t < e2; t += BLO2_THREADS) {
+            for (int t = e0 + rt; t < e2; t += BLO2_THREADS) {
                 const uint32_t e = list[t];
                 const bool role_hi = t < e1, isl = (e >> 24) & 1u;
                 if (role_hi && isl) continue;
@@ -316,7 +338,7 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
                 if (xo > 0) { sum -= q[xo - 1]; s = (xo - 1) >> 5; }
                 for (; s < segr; s++) sum += q[s * 32 + 31];
                 const size_t p = (size_t)(y0 + o) * g.W + (x0 + xo);
-                const float nk = __ldg(&Nk[(size_t)li * n + p]);
+                const float nk = t < e0 + BLO2_THREADS ? nk_pre : __ldg(&Nk[p * 2 + (role_hi ? 1 : 0)]);
                 const float jb = __fdiv_rn(sum * inv, nk);                        // A.cpp:2594
                 float cst;
                 if (!role_hi) {
@@ -326,7 +348,7 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
                     cst = __fadd_rn(part[pix], __fmul_rn((float)(k - I), jb));    // + (hi - I) * JB_hi  (A.cpp:2666-2667)
                 }
                 if (agg) agg[(size_t)di * n + p] = cst;
-                const unsigned long long key = wta_key(cst, d_label0 + di);
+                const unsigned long long key = ((unsigned long long)orderable_u32(cst) << 16) | (unsigned)(d_label0 + di);
                 if (key < bestk[pix]) bestk[pix] = key;
             }
             // the next level's running sums overwrite U only (the scan above is behind a barrier); Q, part and
@@ -336,7 +358,14 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
     }
     for (int p = tid; p < NPIX; p += BLO2_THREADS) {
         int o = p / SW, xo = p - o * SW, y = y0 + o, x = x0 + xo;
-        if (x < g.W && y < g.H && bestk[p] != WTA_KEY_EMPTY) atomicMin(&keys[(size_t)y * g.W + x], bestk[p]);
+        if (x < g.W && y < g.H && bestk[p] != WTA_KEY_EMPTY) {
+            // back to the library's key format (orderable double cost | d)
+            const uint32_t ob = (uint32_t)(bestk[p] >> 16);
+            if (ob != 0xFFFFFFFFu) {                                                  // NaN never wins
+                const float cst = __uint_as_float((ob & 0x80000000u) ? (ob & 0x7FFFFFFFu) : ~ob);
+                atomicMin(&keys[(size_t)y * g.W + x], wta_key(cst, (int)(bestk[p] & 0xFFFFu)));
+            }
+        }
     }
 }
 
@@ -344,7 +373,7 @@ template <int WIN>
 static asw_status launch_blo1_agg2(asw_ctx* ctx, const uint8_t* gref, const uint8_t* gtgt, const float* cost, const float* Nk,
                                    const BloGeom& g, int min_d, unsigned long long* keys, float* agg_dev) {
     constexpr int TH = WIN + 1, SW = BLO2_COLS - (WIN - 1), NPIX = TH * SW;
-    size_t smem = ((size_t)2 * WIN * BLO2_PITCH + (size_t)TH * BLO2_PITCH + NPIX) * sizeof(float) +
+    size_t smem = ((size_t)(2 * WIN + 2) * BLO2_PITCH + (size_t)TH * BLO2_PITCH + NPIX) * sizeof(float) +
                   (size_t)NPIX * sizeof(uint32_t) + (size_t)NPIX * sizeof(unsigned long long);
     cudaFuncSetAttribute(k_blo1_agg2<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int dch = 8;
@@ -374,7 +403,7 @@ static asw_status dev_blo1(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, i
     g.H = H; g.W = W; g.Wp = v.Wp; g.win = win; g.h = win / 2; g.D = num_d;
     g.x0_base = v.x0_base; g.x0_step = v.x0_step;
     float* Nk;
-    ASW_TRY(ws_get(ctx, WS_TMP0, n * g.nl, &Nk));
+    ASW_TRY(ws_get(ctx, WS_TMP0, n * 2, &Nk));
     int IW = BLO_TW + win - 1, IH = BLO_TH + win - 1, PP = IW | 1, HP = BLO_TW + 1;
     size_t smem_n = ((size_t)IH * PP + (size_t)IH * HP) * sizeof(int);
     size_t smem_a = ((size_t)IH * PP * 2 + (size_t)IH * HP) * sizeof(float) + (size_t)IH * PP * 2;
