@@ -354,6 +354,140 @@ k_trad_fast(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// linear-addressing variant of the single-SFU-op kernel (the default).  Two observations remove every clamp
+// from the inner loop of ALL tiles, image borders included:
+//   * the reference clamps coordinates (A.cpp:1050-1060, 1093-1102); a tile that is STAGED through the clamp
+//     (cell (r, c) <-> pixel (clamp(y0 - h + r), clamp(x0 - h + c))) can be read with unclamped offsets;
+//   * the cost sample column is clamped BEFORE the candidate shift (nx = clamp(x - h + kx), then nx -/+ d,
+//     A.cpp:1093-1102): that is one min/max per TAP, after which the TR_Q candidates of the tap sit at
+//     compile-time offsets -SIGN*q from one pointer; the clamp after the shift is again the staging clamp.
+// Only where the candidate shift itself clamps the weighted pixel (x - d < 0 / x + d > W-1: the first or last
+// tile column) the target-weight operand needs one base pointer per candidate (XS_CLAMP).
+// The tap geometry (centre skip of the weight list, centre+1 skip and transposition of the sample list,
+// A.cpp:1050-1053, 1091-1102) is tabulated once per CTA in shared memory: 2 broadcast loads per tap instead of
+// ~45 integer instructions.
+// ------------------------------------------------------------------------------------------------
+template <int SIGN, bool XS_CLAMP>
+__device__ __forceinline__ void trad_lin_body(const float* __restrict__ RF, const float* __restrict__ TF,
+                                              const int4* __restrict__ taps, const float* __restrict__ c2s, float a2,
+                                              const TradGeom& g, int IWr, int IWt, int x0t, int y0t, int oxt, int x, int y,
+                                              int d_lo, double* num, double* den) {
+    const int W = g.W, H = g.H, win = g.win, h = g.h;
+    const int yc = min(y, H - 1), xc = min(x, W - 1);             // threads past the image edge compute a clamped copy
+    const int rowc = yc - y0t + h, colc = xc - x0t + h;           // centre cell in the reference tile
+    const float* cw = RF + rowc * IWr + colc;                     // weight neighbours: cw[dy * IWr + dx]
+    const float* cs = RF + (rowc - h) * IWr + (colc - h);         // cost samples:      cs[ky * IWr + kx]
+    const float rc = cw[0];
+    const float* trow = TF + rowc * IWt - oxt;                    // target tile row of the pixel, indexed by image column
+    const float* tq[XS_CLAMP ? TR_Q : 1];                         // weighted target pixel of candidate q
+    float tc[TR_Q];
+#pragma unroll
+    for (int q = 0; q < TR_Q; q++) {
+        const int xs = XS_CLAMP ? trad_shift(xc, d_lo + q, SIGN, W) : xc - SIGN * (d_lo + q);
+        if (XS_CLAMP) tq[q] = trow + xs; else if (q == 0) tq[0] = trow + xs;
+        tc[q] = trow[xs];
+    }
+    const float* ts = TF + (rowc - h) * IWt - oxt - SIGN * d_lo;  // cost samples of the target: ts[ky * IWt + nx - SIGN * q]
+    const int xl = xc - h;
+    int n = 0;
+    while (n < g.nw) {
+        const int n1 = min(n + win, g.nw);
+        float fn[TR_Q], fd[TR_Q];
+#pragma unroll
+        for (int q = 0; q < TR_Q; q++) { fn[q] = 0.0f; fd[q] = 0.0f; }
+#pragma unroll 2
+        for (; n < n1; n++) {
+            const int4 tp = taps[n];                              // {dy*IWr+dx, dy*IWt+dx, ky*IWr+kx, ky*IWt | kx << 20}
+            // e0 = -(dL * a2 + c2[n]); per candidate: w = 2^(e0 - dR * a2)
+            const float e0 = -fmaf(fabsf(cw[tp.x] - rc), a2, c2s[n]);
+            const float rs = cs[tp.z];
+            const int kx = tp.w >> 20;
+            const int nx = SIGN > 0 ? min(xl + kx, W - 1) : max(xl + kx, 0);      // clamp BEFORE the shift
+            const float* pf = ts + (tp.w & 0xFFFFF) + nx;
+            if (!XS_CLAMP) {
+                const float* pu = tq[0] + tp.y;
+#pragma unroll
+                for (int q = 0; q < TR_Q; q++) {
+                    float w = fast_ex2(fmaf(-fabsf(pu[-SIGN * q] - tc[q]), a2, e0));
+                    fn[q] = fmaf(w, fabsf(rs - pf[-SIGN * q]), fn[q]);
+                    fd[q] = __fadd_rn(fd[q], w);
+                }
+            } else {
+                // first / last tile columns: the shift clamps, so the sample column is clamped per candidate as well
+                const int nxc = clampi(xl + kx, 0, W - 1);
+                const float* pr = TF + (rowc - h) * IWt - oxt + (tp.w & 0xFFFFF);
+#pragma unroll
+                for (int q = 0; q < TR_Q; q++) {
+                    float w = fast_ex2(fmaf(-fabsf(tq[XS_CLAMP ? q : 0][tp.y] - tc[q]), a2, e0));
+                    fn[q] = fmaf(w, fabsf(rs - pr[trad_shift(nxc, d_lo + q, SIGN, W)]), fn[q]);
+                    fd[q] = __fadd_rn(fd[q], w);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < TR_Q; q++) { num[q] += (double)fn[q]; den[q] += (double)fd[q]; }
+    }
+}
+
+template <int SIGN>
+__global__ void __launch_bounds__(TR_TW * TR_TH)
+k_trad_lin(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, const float* __restrict__ c2, float a2,
+           TradGeom g, unsigned long long* __restrict__ keys, float* __restrict__ agg) {
+    extern __shared__ __align__(16) float sm_tr[];
+    const int W = g.W, H = g.H, h = g.h, win = g.win;
+    const int IH = TR_TH + 2 * h, IWr = TR_TW + 2 * h, IWt = TR_TW + 2 * h + TR_Q - 1;
+    int4* taps = (int4*)sm_tr;                                    // [nw]
+    float* c2s = sm_tr + 4 * g.nw;                                // [nw]
+    float* RF = c2s + g.nw;                                       // [IH][IWr]  Lg(clamp(y0t-h+r), clamp(x0t-h+c))
+    float* TF = RF + IH * IWr;                                    // [IH][IWt]  Rg(clamp(y0t-h+r), clamp(oxt+c))
+    const int x0t = blockIdx.x * TR_TW, y0t = blockIdx.y * TR_TH;
+    const int c0 = blockIdx.z * TR_Q;
+    const int nq = min(TR_Q, g.n_cand - c0);
+    const int d_lo = g.d_first + c0, d_hi = d_lo + TR_Q - 1;      // the tile always spans TR_Q candidates
+    // image column of target cell 0: the leftmost weighted target pixel of the tile (after the shift clamp) minus h
+    const int oxt = SIGN > 0 ? max(0, x0t - d_hi) - h : min(x0t + d_lo, W - 1) - h;
+    const int tid = threadIdx.y * TR_TW + threadIdx.x;
+    for (int i = tid; i < IH * IWr; i += TR_TW * TR_TH) {
+        int r = i / IWr, c = i - r * IWr;
+        RF[i] = (float)ref[(size_t)clampi(y0t - h + r, 0, H - 1) * W + clampi(x0t - h + c, 0, W - 1)];
+    }
+    for (int i = tid; i < IH * IWt; i += TR_TW * TR_TH) {
+        int r = i / IWt, c = i - r * IWt;
+        TF[i] = (float)tgt[(size_t)clampi(y0t - h + r, 0, H - 1) * W + clampi(oxt + c, 0, W - 1)];
+    }
+    for (int n = tid; n < g.nw; n += TR_TW * TR_TH) {
+        const int pw = n < g.cidx ? n : n + 1;                    // weight tap skips the centre (A.cpp:1044-1053)
+        const int pc = n <= g.cidx ? n : n + 1;                   // sample tap skips centre + 1 (A.cpp:1088-1102)
+        const int dy = pw / win - h, dx = pw % win - h;
+        const int kx = pc / win, ky = pc % win;                   // pc / win is the COLUMN offset: transposed
+        taps[n] = make_int4(dy * IWr + dx, dy * IWt + dx, ky * IWr + kx, (ky * IWt) | (kx << 20));
+        c2s[n] = __ldg(&c2[n]);
+    }
+    __syncthreads();
+    const int x = x0t + threadIdx.x, y = y0t + threadIdx.y;
+    double num[TR_Q], den[TR_Q];
+#pragma unroll
+    for (int q = 0; q < TR_Q; q++) { num[q] = 0; den[q] = 0; }
+    // does the candidate shift clamp the weighted pixel anywhere in this tile?
+    const bool xs_clamp = SIGN > 0 ? (x0t - d_hi < 0) : (x0t + TR_TW - 1 + d_hi > W - 1);
+    if (xs_clamp) trad_lin_body<SIGN, true>(RF, TF, taps, c2s, a2, g, IWr, IWt, x0t, y0t, oxt, x, y, d_lo, num, den);
+    else trad_lin_body<SIGN, false>(RF, TF, taps, c2s, a2, g, IWr, IWt, x0t, y0t, oxt, x, y, d_lo, num, den);
+    if (x < W && y < H) {
+        unsigned long long best = WTA_KEY_EMPTY;
+        size_t p = (size_t)y * W + x;
+#pragma unroll
+        for (int q = 0; q < TR_Q; q++) {
+            if (q < nq) {
+                double E = num[q] / den[q];
+                if (agg) agg[(size_t)(c0 + q) * H * W + p] = (float)E;
+                best = min(best, wta_key_d(E, d_lo + q));
+            }
+        }
+        atomicMin(&keys[p], best);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // diagonal-blocked variant (ASW_TRAD_DIAG=1; not the default -- see dev_traditional): one CTA = one image row x 128 pixels x 4 NW candidates, thread = 4 adjacent
 // pixels x 4 ADJACENT candidates, as k_geo_agg_diag (k_geodesic.cuh):
 //   * the bilateral weights are evaluated ONCE per pixel and tap -- wL_n for the 128 reference pixels, wR_n for the
@@ -666,8 +800,21 @@ static asw_status dev_traditional(asw_ctx* ctx, const uint8_t* dL, const uint8_t
         ASW_TRY(ws_get(ctx, WS_TABLE1, c2.size(), &dc2));
         ASW_CUDA(ctx, cudaMemcpyAsync(dc2, c2.data(), c2.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
         ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // c2 is a host temporary
-        cudaFuncSetAttribute(k_trad_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
         dim3 grid(cdiv(W, TR_TW), cdiv(H, TR_TH), cdiv(g.n_cand, TR_Q));
+        const size_t smem_lin = smem_fast + (size_t)5 * g.nw * sizeof(float);
+        if (!getenv("ASW_TRAD_FAST") && smem_lin <= 200 * 1024 && (size_t)IH * IWt < (1u << 20)) {
+            if (g.sign > 0) {
+                cudaFuncSetAttribute(k_trad_lin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin);
+                LAUNCH(ctx, "trad_aggregate", (k_trad_lin<1><<<grid, dim3(TR_TW, TR_TH), smem_lin, ctx->stream>>>(
+                                                  ref, tgt, dc2, (float)(log2e / gamma_c), g, keys, agg_dev)));
+            } else {
+                cudaFuncSetAttribute(k_trad_lin<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin);
+                LAUNCH(ctx, "trad_aggregate", (k_trad_lin<-1><<<grid, dim3(TR_TW, TR_TH), smem_lin, ctx->stream>>>(
+                                                  ref, tgt, dc2, (float)(log2e / gamma_c), g, keys, agg_dev)));
+            }
+            return keys_to_disp(ctx, keys, n, disp_dev);
+        }
+        cudaFuncSetAttribute(k_trad_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
         LAUNCH(ctx, "trad_aggregate", (k_trad_fast<<<grid, dim3(TR_TW, TR_TH), smem_fast, ctx->stream>>>(
                                           ref, tgt, dc2, (float)(log2e / gamma_c), g, keys, agg_dev)));
         return keys_to_disp(ctx, keys, n, disp_dev);
