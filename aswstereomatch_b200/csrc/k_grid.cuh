@@ -102,43 +102,63 @@ __global__ void k_grid_pass(double* __restrict__ S, int* __restrict__ C, GridDim
 // plane once: no zero-fill of the grid, no global atomics, no read-back before the first two passes, and no strided
 // per-thread global lines (the stand-alone w pass walked 28-cell lines with a 224-byte stride between threads).
 // One thread per line in shared memory, odd pitch against bank conflicts; PL planes per CTA, grid-stride.
+// Tables (built on the host with the same double arithmetic, A.cpp:1897-1912 / 2290-2298):
+//   klut[v]  = cvRound(v / sR) for the 256 gray values          xq[x] = x / sS, yq[y] = y / sS, gq[v] = v / sR
+//   xr[kx]   = first pixel column whose cvRound(x / sS) is kx, xr[X + kx] = how many (keys are monotone, so the
+//              pixels of a spatial key are one contiguous run); yr likewise for rows
+// so neither kernel executes a double-precision division per pixel.
+struct GridTables {
+    const int* klut;             // [256]
+    const int* xr;               // [2 * X]
+    const int* yr;               // [2 * Y]
+    const double* xq;            // [W]
+    const double* yq;            // [H]
+    const double* gq;            // [256]
+    int max_run;                 // longest pixel run of a spatial key (both axes)
+};
+
 __global__ void __launch_bounds__(128)
 k_grid_build_wz(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, int H, int W, int d_first,
-                double* __restrict__ S, int* __restrict__ C, GridDims g, size_t n_planes, int PL) {
+                double* __restrict__ S, int* __restrict__ C, GridDims g, GridTables tb, int n_planes, int PL) {
     extern __shared__ double sm_grid[];
-    const int X = g.nx + 1, Y = g.ny + 1, Z = g.nz + 1, Wd = g.nw + 1, pitch = Wd | 1, cells = Z * Wd;
+    const int X = g.nx + 1, Y = g.ny + 1, Z = g.nz + 1, Wd = g.nw + 1, pitch = Wd | 1, cells = Z * Wd, XY = X * Y;
     double* ss = sm_grid;                                   // [PL][Z][pitch]
     int* cc = (int*)(ss + (size_t)PL * Z * pitch);          // [PL][Z][pitch]
     int* si = cc + (size_t)PL * Z * pitch;                  // [PL][Z][pitch] integer sums while splatting
-    unsigned char* okf = (unsigned char*)(si + (size_t)PL * Z * pitch);   // [PL][2][side] key-match flags
+    __shared__ int klut[256];
     const int tid = threadIdx.x;
-    const int rs = (int)ceil(g.rate_s);                     // pixels farther than this from sS*k cannot round to k
-    const int side = 2 * rs + 3;
-    for (size_t p0 = (size_t)blockIdx.x * PL; p0 < n_planes; p0 += (size_t)gridDim.x * PL) {
-        const int np = (int)min((size_t)PL, n_planes - p0);
+    for (int i = tid; i < 256; i += 128) klut[i] = tb.klut[i];
+    const int run = tb.max_run, per = run * run;
+    for (int p0 = blockIdx.x * PL; p0 < n_planes; p0 += gridDim.x * PL) {
+        const int np = min(PL, n_planes - p0);
         for (int i = tid; i < np * Z * pitch; i += 128) { cc[i] = 0; si[i] = 0; }
-        // which columns / rows of the candidate window carry this plane's spatial key (2 * side tests per plane
-        // instead of side^2 double divisions)
-        for (int i = tid; i < np * 2 * side; i += 128) {
-            const int pl = i / (2 * side), r = i - pl * 2 * side, is_y = r >= side, o = is_y ? r - side : r;
-            const size_t p = p0 + pl;
-            const int xy = (int)(p % ((size_t)X * Y)), kx = xy / Y, ky = xy - kx * Y, k = is_y ? ky : kx;
-            const int v = (int)lrint(k * g.rate_s) - rs - 1 + o, lim = is_y ? H : W;
-            okf[i] = (v >= 0 && v < lim && cv_round((double)v / g.rate_s) == k) ? 1 : 0;
-        }
         __syncthreads();
-        for (int i = tid; i < np * side * side; i += 128) {
-            const int pl = i / (side * side), r = i - pl * side * side, ox = r % side, oy = r / side;
-            if (!(okf[pl * 2 * side + ox] & okf[pl * 2 * side + side + oy])) continue;
-            const size_t p = p0 + pl;
-            const int gi = (int)(p / ((size_t)X * Y)), xy = (int)(p - (size_t)gi * X * Y), kx = xy / Y, ky = xy - kx * Y;
-            const int x = (int)lrint(kx * g.rate_s) - rs - 1 + ox, y = (int)lrint(ky * g.rate_s) - rs - 1 + oy;
-            const int d = d_first + gi;
-            const float lf = (float)lg[(size_t)y * W + x], rf = (float)rg[(size_t)y * W + max(0, x - d)];
-            const int kz = cv_round((double)lf / g.rate_r), kw = cv_round((double)rf / g.rate_r);
-            const int a = (pl * Z + kz) * pitch + kw;
-            atomicAdd(&si[a], (int)fabsf(lf - rf));         // A.cpp:1897-1912
-            atomicAdd(&cc[a], 1);
+        // splat: 4 pixels per thread and round, the global loads of a round issued together
+        for (int i0 = tid; i0 < np * per; i0 += 4 * 128) {
+            int cell[4], lv[4], rv[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u * 128;
+                cell[u] = -1;
+                if (i < np * per) {
+                    const int pl = i / per, r = i - pl * per, oy = r / run, ox = r - oy * run;
+                    const int p = p0 + pl, gi = p / XY, xy = p - gi * XY, kx = xy / Y, ky = xy - kx * Y;
+                    if (ox < tb.xr[X + kx] && oy < tb.yr[Y + ky]) {
+                        const int x = tb.xr[kx] + ox, y = tb.yr[ky] + oy;
+                        lv[u] = lg[(size_t)y * W + x];
+                        rv[u] = rg[(size_t)y * W + max(0, x - (d_first + gi))];
+                        cell[u] = pl * Z * pitch;
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (cell[u] >= 0) {
+                    const int a = cell[u] + klut[lv[u]] * pitch + klut[rv[u]];
+                    atomicAdd(&si[a], abs(lv[u] - rv[u]));   // A.cpp:1897-1912: |L-R| is an integer
+                    atomicAdd(&cc[a], 1);
+                }
+            }
         }
         __syncthreads();
         for (int i = tid; i < np * Z * pitch; i += 128) ss[i] = (double)si[i];
@@ -151,7 +171,7 @@ k_grid_build_wz(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, 
             grid_pass_line(ss + (size_t)pl * Z * pitch + w, cc + (size_t)pl * Z * pitch + w, pitch, g.nz);
         }
         __syncthreads();
-        const size_t base = p0 * cells;
+        const size_t base = (size_t)p0 * cells;
         for (int i = tid; i < np * cells; i += 128) {
             const int pl = i / cells, r = i - pl * cells, z = r / Wd, w = r - z * Wd;
             S[base + i] = ss[(pl * Z + z) * pitch + w];
@@ -162,16 +182,16 @@ k_grid_build_wz(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, 
 }
 
 __global__ void k_grid_slice(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, int H, int W, int d_first,
-                             int cand_first, GridDims g, const double* __restrict__ S, const int* __restrict__ C,
+                             int cand_first, GridDims g, GridTables tb, const double* __restrict__ S, const int* __restrict__ C,
                              unsigned long long* __restrict__ keys, float* __restrict__ agg) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     int d = d_first + blockIdx.z;
     const double* s = S + (size_t)blockIdx.z * g.cells;
     const int* c = C + (size_t)blockIdx.z * g.cells;
-    double x_ = (double)x / g.rate_s, y_ = (double)y / g.rate_s;                              // A.cpp:2290-2293
-    double cl = (double)lg[(size_t)y * W + x] / g.rate_r;
-    double cr = (double)rg[(size_t)y * W + max(0, x - d)] / g.rate_r;
+    double x_ = __ldg(&tb.xq[x]), y_ = __ldg(&tb.yq[y]);                                      // x / sS, y / sS (A.cpp:2290-2293)
+    double cl = __ldg(&tb.gq[lg[(size_t)y * W + x]]);                                         // L / sR
+    double cr = __ldg(&tb.gq[rg[(size_t)y * W + max(0, x - d)]]);                             // R(max(0, x-d)) / sR
     int X = cv_ceil(x_), Y = cv_ceil(y_), Z = cv_ceil(cl), Q = cv_ceil(cr);
     double fx = X - x_, fy = Y - y_, fz = Z - cl, fw = Q - cr;
     double val[2];
@@ -231,6 +251,37 @@ static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint
     unsigned long long* keys;
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
     ASW_TRY(init_keys(ctx, keys, n));
+    // host tables (same IEEE double operations as the kernels would execute; lrint = cvRound = half-to-even)
+    const int GX = g.nx + 1, GY = g.ny + 1;
+    std::vector<int> ti(256 + 2 * GX + 2 * GY, 0);
+    std::vector<double> td((size_t)W + H + 256);
+    int* h_klut = ti.data(); int* h_xr = h_klut + 256; int* h_yr = h_xr + 2 * GX;
+    double* h_xq = td.data(); double* h_yq = h_xq + W; double* h_gq = h_yq + H;
+    for (int v = 0; v < 256; v++) { h_gq[v] = (double)v / rate_r; h_klut[v] = (int)lrint(h_gq[v]); }
+    int max_run = 1;
+    for (int x = 0; x < W; x++) {
+        h_xq[x] = (double)x / rate_s;
+        int k = (int)lrint(h_xq[x]);
+        if (k > g.nx) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "bilateral grid: spatial key outside the grid%s%s");
+        if (h_xr[GX + k]++ == 0) h_xr[k] = x;
+        max_run = std::max(max_run, h_xr[GX + k]);
+    }
+    for (int y = 0; y < H; y++) {
+        h_yq[y] = (double)y / rate_s;
+        int k = (int)lrint(h_yq[y]);
+        if (k > g.ny) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "bilateral grid: spatial key outside the grid%s%s");
+        if (h_yr[GY + k]++ == 0) h_yr[k] = y;
+        max_run = std::max(max_run, h_yr[GY + k]);
+    }
+    int* d_ti; double* d_td;
+    ASW_TRY(ws_get(ctx, WS_TABLE0, ti.size(), &d_ti));
+    ASW_TRY(ws_get(ctx, WS_TABLE1, td.size(), &d_td));
+    ASW_CUDA(ctx, cudaMemcpyAsync(d_ti, ti.data(), ti.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    ASW_CUDA(ctx, cudaMemcpyAsync(d_td, td.data(), td.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the tables are host temporaries
+    GridTables tb;
+    tb.klut = d_ti; tb.xr = d_ti + 256; tb.yr = tb.xr + 2 * GX;
+    tb.xq = d_td; tb.yq = d_td + W; tb.gq = tb.yq + H; tb.max_run = max_run;
     for (int c0 = 0; c0 < n_cand; c0 += batch) {
         int nb = n_cand - c0 < batch ? n_cand - c0 : batch;
         // splat + w + z fused through shared memory when a few (z, w) planes fit; otherwise zero-fill, global splat
@@ -240,11 +291,11 @@ static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint
         int first_axis = 0;
         if (plane_bytes <= 96 * 1024 && !getenv("ASW_GRID_UNFUSED")) {
             int PL = std::max(1, std::min(128 / std::max(Zd, Wdd), (int)((96 * 1024) / plane_bytes)));
-            size_t smem = plane_bytes * PL + (size_t)PL * 2 * (2 * (int)ceil(rate_s) + 3) + 16;
-            size_t n_planes = (size_t)(g.nx + 1) * (g.ny + 1) * nb;
+            size_t smem = plane_bytes * PL + 16;
+            int n_planes = (g.nx + 1) * (g.ny + 1) * nb;
             cudaFuncSetAttribute(k_grid_build_wz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            unsigned blocks = (unsigned)std::min<size_t>((n_planes + PL - 1) / PL, (size_t)ctx->sm_count * 32);
-            LAUNCH(ctx, "grid_build_wz", (k_grid_build_wz<<<blocks, 128, smem, ctx->stream>>>(gl, gr, H, W, min_d + c0, S, C, g, n_planes, PL)));
+            unsigned blocks = (unsigned)std::min<size_t>((size_t)(n_planes + PL - 1) / PL, (size_t)ctx->sm_count * 32);
+            LAUNCH(ctx, "grid_build_wz", (k_grid_build_wz<<<blocks, 128, smem, ctx->stream>>>(gl, gr, H, W, min_d + c0, S, C, g, tb, n_planes, PL)));
             first_axis = 2;
         } else {
             ASW_CUDA(ctx, cudaMemsetAsync(S, 0, g.cells * nb * sizeof(double), ctx->stream));      // A.cpp:1874-1892
@@ -256,7 +307,7 @@ static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint
             static const char* pass_name[4] = {"grid_pass_w", "grid_pass_z", "grid_pass_y", "grid_pass_x"};
             LAUNCH(ctx, pass_name[axis], (k_grid_pass<<<(unsigned)((lines + 127) / 128), 128, 0, ctx->stream>>>(S, C, g, axis, nb)));
         }
-        LAUNCH(ctx, "grid_slice", (k_grid_slice<<<dim3(cdiv(W, 128), H, nb), 128, 0, ctx->stream>>>(gl, gr, H, W, min_d + c0, c0, g, S, C, keys, agg_dev)));
+        LAUNCH(ctx, "grid_slice", (k_grid_slice<<<dim3(cdiv(W, 128), H, nb), 128, 0, ctx->stream>>>(gl, gr, H, W, min_d + c0, c0, g, tb, S, C, keys, agg_dev)));
     }
     return keys_to_disp(ctx, keys, n, disp_dev);
 }
