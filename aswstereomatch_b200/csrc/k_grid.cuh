@@ -41,37 +41,48 @@ __global__ void k_grid_splat(const uint8_t* __restrict__ lg, const uint8_t* __re
     atomicAdd(&C[id], 1);
 }
 
-// one recursive in-place 5-tap pass along a strided line of n+1 cells (A.cpp:1936-2183)
-__device__ __forceinline__ void grid_pass_line(double* __restrict__ s, int* __restrict__ c, size_t stride, int n) {
-    // rolling registers: m2, m1 = already-updated v[i-2], v[i-1]; c0 = v[i]; p1, p2 = original v[i+1], v[i+2]
-    double sm2 = 0, sm1 = 0, s0 = s[0], sp1 = s[stride], sp2 = s[2 * stride];
-    double cm2 = 0, cm1 = 0, c0 = (double)c[0], cp1 = (double)c[stride], cp2 = (double)c[2 * stride];
-    for (int i = 0; i <= n; i++) {
-        double ns, nc;
-        if (i == 0) {
-            ns = 0.6 * s0 + 0.3 * sp1 + 0.1 * sp2;
-            nc = 0.6 * c0 + 0.3 * cp1 + 0.1 * cp2;
-        } else if (i == 1) {
-            ns = 0.2 * sm1 + 0.5 * s0 + 0.2 * sp1 + 0.1 * sp2;
-            nc = 0.2 * cm1 + 0.5 * c0 + 0.2 * cp1 + 0.1 * cp2;
-        } else if (i == n - 1) {
-            ns = 0.1 * sm2 + 0.2 * sm1 + 0.5 * s0 + 0.2 * sp1;
-            nc = 0.1 * cm2 + 0.2 * cm1 + 0.5 * c0 + 0.2 * cp1;
-        } else if (i == n) {
-            ns = 0.1 * sm2 + 0.3 * sm1 + 0.6 * s0;
-            nc = 0.1 * cm2 + 0.3 * cm1 + 0.6 * c0;
-        } else {
-            ns = 0.0625 * sm2 + 0.25 * sm1 + 0.375 * s0 + 0.25 * sp1 + 0.0625 * sp2;
-            nc = 0.0625 * cm2 + 0.25 * cm1 + 0.375 * c0 + 0.25 * cp1 + 0.0625 * cp2;
-        }
-        int nci = (int)nc;                              // pair<double,double> -> pair<double,int>: truncation
-        s[(size_t)i * stride] = ns;
-        c[(size_t)i * stride] = nci;
-        sm2 = sm1; sm1 = ns; s0 = sp1; sp1 = sp2;
-        cm2 = cm1; cm1 = (double)nci; c0 = cp1; cp1 = cp2;
-        if (i + 3 <= n) { sp2 = s[(size_t)(i + 3) * stride]; cp2 = (double)c[(size_t)(i + 3) * stride]; }
-        else { sp2 = 0; cp2 = 0; }
+// one recursive in-place 5-tap pass along a strided line of n+1 cells, n >= 3 (A.cpp:1936-2183).  The two edge
+// rules at either end are peeled, so the interior loop is branch-free; expressions keep the reference's order.
+template <typename ST>
+__device__ __forceinline__ void grid_pass_line(double* __restrict__ s, int* __restrict__ c, ST stride, int n) {
+    // rolling registers: m2, m1 = already-updated v[i-2], v[i-1]; s0 = v[i]; p1, p2 = original v[i+1], v[i+2]
+    double sm2, sm1, s0 = s[0], sp1 = s[stride], sp2 = s[2 * stride], sp3 = s[3 * stride];
+    double cm2, cm1, c0 = (double)c[0], cp1 = (double)c[stride], cp2 = (double)c[2 * stride], cp3 = (double)c[3 * stride];
+    double ns, nc;
+    int nci;
+#define GRID_STORE_SHIFT(i)                                                   \
+    nci = (int)nc; /* pair<double,double> -> pair<double,int>: truncation */ \
+    s[(ST)(i) * stride] = ns;                                                 \
+    c[(ST)(i) * stride] = nci;                                                \
+    sm2 = sm1; sm1 = ns; s0 = sp1; sp1 = sp2; sp2 = sp3;                      \
+    cm2 = cm1; cm1 = (double)nci; c0 = cp1; cp1 = cp2; cp2 = cp3;
+    // i = 0
+    ns = 0.6 * s0 + 0.3 * sp1 + 0.1 * sp2;
+    nc = 0.6 * c0 + 0.3 * cp1 + 0.1 * cp2;
+    sm1 = 0; cm1 = 0;
+    GRID_STORE_SHIFT(0)
+    if (4 <= n) { sp3 = s[(ST)4 * stride]; cp3 = (double)c[(ST)4 * stride]; }
+    // i = 1
+    ns = 0.2 * sm1 + 0.5 * s0 + 0.2 * sp1 + 0.1 * sp2;
+    nc = 0.2 * cm1 + 0.5 * c0 + 0.2 * cp1 + 0.1 * cp2;
+    GRID_STORE_SHIFT(1)
+    for (int i = 2; i <= n - 2; i++) {
+        if (i + 3 <= n) { sp3 = s[(ST)(i + 3) * stride]; cp3 = (double)c[(ST)(i + 3) * stride]; }
+        ns = 0.0625 * sm2 + 0.25 * sm1 + 0.375 * s0 + 0.25 * sp1 + 0.0625 * sp2;
+        nc = 0.0625 * cm2 + 0.25 * cm1 + 0.375 * c0 + 0.25 * cp1 + 0.0625 * cp2;
+        GRID_STORE_SHIFT(i)
     }
+    // i = n - 1
+    ns = 0.1 * sm2 + 0.2 * sm1 + 0.5 * s0 + 0.2 * sp1;
+    nc = 0.1 * cm2 + 0.2 * cm1 + 0.5 * c0 + 0.2 * cp1;
+    GRID_STORE_SHIFT(n - 1)
+    // i = n
+    ns = 0.1 * sm2 + 0.3 * sm1 + 0.6 * s0;
+    nc = 0.1 * cm2 + 0.3 * cm1 + 0.6 * c0;
+    nci = (int)nc;
+    s[(ST)n * stride] = ns;
+    c[(ST)n * stride] = nci;
+#undef GRID_STORE_SHIFT
 }
 
 // axis: 0 = w, 1 = z, 2 = y, 3 = x.  One thread per line; thread index ordered so that adjacent threads
@@ -93,7 +104,7 @@ __global__ void k_grid_pass(double* __restrict__ S, int* __restrict__ C, GridDim
     else if (axis == 1) { size_t xy = l / Wd; int w = (int)(l - xy * Wd); base = xy * Z * Wd + w; stride = Wd; n = g.nz; }
     else if (axis == 2) { size_t x = l / ((size_t)Z * Wd); size_t zw = l - x * Z * Wd; base = x * Y * Z * Wd + zw; stride = (size_t)Z * Wd; n = g.ny; }
     else { base = l; stride = (size_t)Y * Z * Wd; n = g.nx; }
-    grid_pass_line(s + base, c + base, stride, n);
+    grid_pass_line<size_t>(s + base, c + base, stride, n);
 }
 
 // splat + w + z fused: the CTA builds the (z, w) planes it owns directly in shared memory from the ~(2 sS)^2
@@ -164,19 +175,19 @@ k_grid_build_wz(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, 
         for (int i = tid; i < np * Z * pitch; i += 128) ss[i] = (double)si[i];
         __syncthreads();
         for (int l = tid; l < np * Z; l += 128)             // w pass: line = (plane, z), unit stride
-            grid_pass_line(ss + (size_t)l * pitch, cc + (size_t)l * pitch, 1, g.nw);
+            grid_pass_line<int>(ss + l * pitch, cc + l * pitch, 1, g.nw);
         __syncthreads();
         for (int l = tid; l < np * Wd; l += 128) {          // z pass: line = (plane, w), stride = pitch
             const int pl = l / Wd, w = l - pl * Wd;
-            grid_pass_line(ss + (size_t)pl * Z * pitch + w, cc + (size_t)pl * Z * pitch + w, pitch, g.nz);
+            grid_pass_line<int>(ss + pl * Z * pitch + w, cc + pl * Z * pitch + w, pitch, g.nz);
         }
         __syncthreads();
         const size_t base = (size_t)p0 * cells;
-        for (int i = tid; i < np * cells; i += 128) {
-            const int pl = i / cells, r = i - pl * cells, z = r / Wd, w = r - z * Wd;
-            S[base + i] = ss[(pl * Z + z) * pitch + w];
-            C[base + i] = cc[(pl * Z + z) * pitch + w];
-        }
+        for (int row = tid >> 5; row < np * Z; row += 4)     // one (plane, z) row per warp: no index divisions
+            for (int w = tid & 31; w < Wd; w += 32) {
+                S[base + row * Wd + w] = ss[row * pitch + w];
+                C[base + row * Wd + w] = cc[row * pitch + w];
+            }
         __syncthreads();
     }
 }
