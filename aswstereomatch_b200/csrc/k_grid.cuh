@@ -205,18 +205,24 @@ __global__ void k_grid_slice(const uint8_t* __restrict__ lg, const uint8_t* __re
     double cr = __ldg(&tb.gq[rg[(size_t)y * W + max(0, x - d)]]);                             // R(max(0, x-d)) / sR
     int X = cv_ceil(x_), Y = cv_ceil(y_), Z = cv_ceil(cl), Q = cv_ceil(cr);
     double fx = X - x_, fy = Y - y_, fz = Z - cl, fw = Q - cr;
+    // all 32 corner loads are issued before the first use (the gather is latency-bound otherwise)
+    double vs[16];
+    int vc[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+        int gx = X + ((k & 8) ? 1 : -1), gy = Y + ((k & 4) ? 1 : -1);
+        int gz = Z + ((k & 2) ? 1 : -1), gq = Q + ((k & 1) ? 1 : -1);
+        bool in = gx >= 0 && gx <= g.nx && gy >= 0 && gy <= g.ny && gz >= 0 && gz <= g.nz && gq >= 0 && gq <= g.nw;
+        size_t id = in ? gidx(g, gx, gy, gz, gq) : 0;
+        vs[k] = in ? __ldg(&s[id]) : 0.0;                               // map default-insert reads (0.0, 0)
+        vc[k] = in ? __ldg(&c[id]) : 0;
+    }
     double val[2];
 #pragma unroll
     for (int t = 0; t < 2; t++) {
         double v[16];
 #pragma unroll
-        for (int k = 0; k < 16; k++) {
-            int gx = X + ((k & 8) ? 1 : -1), gy = Y + ((k & 4) ? 1 : -1);
-            int gz = Z + ((k & 2) ? 1 : -1), gq = Q + ((k & 1) ? 1 : -1);
-            bool in = gx >= 0 && gx <= g.nx && gy >= 0 && gy <= g.ny && gz >= 0 && gz <= g.nz && gq >= 0 && gq <= g.nw;
-            size_t id = in ? gidx(g, gx, gy, gz, gq) : 0;
-            v[k] = in ? (t == 0 ? s[id] : (double)c[id]) : 0.0;         // map default-insert reads (0.0, 0)
-        }
+        for (int k = 0; k < 16; k++) v[k] = t == 0 ? vs[k] : (double)vc[k];
         double a[8], b[4], c2[2];
 #pragma unroll
         for (int k = 0; k < 8; k++) a[k] = v[2 * k] * (1 - fw) + v[2 * k + 1] * fw;          // A.cpp:2233-2250
