@@ -484,6 +484,24 @@ static asw_status dev_lr_refine(asw_ctx* ctx, const uint8_t* dL, const float* dl
     LAUNCH(ctx, "fill_invalid", (k_fill_invalid<<<grid, 128, 0, ctx->stream>>>(dl, valid, H, W, filled)));
     double alpha_r = (1.0 / rate_r) * (-1);
     float alpha_s = (float)((1.0 / rate_s) * (-1));
+    const size_t ne = (size_t)win * win, n = (size_t)H * W;
+    const int bt = (ne * (2 * 64 + 1)) * sizeof(float) <= 96 * 1024 ? 64 : (ne * (2 * 32 + 1)) * sizeof(float) <= 96 * 1024 ? 32 : 0;
+    if (bt && n < ((size_t)1 << 31) && !getenv("ASW_REFINE_DENSE")) {
+        int* list;
+        ASW_TRY(ws_get(ctx, WS_REFINE_LIST, n + 1, &list));               // list[0] = count
+        ASW_CUDA(ctx, cudaMemsetAsync(list, 0, sizeof(int), ctx->stream));
+        LAUNCH(ctx, "refine_compact", (k_refine_compact<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(filled, valid, (int)n, out, list + 1, list)));
+        const size_t smem = ne * (2 * bt + 1) * sizeof(float);
+        const unsigned blocks = (unsigned)std::min<size_t>((n + bt - 1) / bt, (size_t)ctx->sm_count * 16);
+        if (bt == 64) {
+            cudaFuncSetAttribute(k_wmedian_refine_list<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            LAUNCH(ctx, "wmedian_refine", (k_wmedian_refine_list<64><<<blocks, 64, smem, ctx->stream>>>(dL, filled, list + 1, list, H, W, win, alpha_r, alpha_s, out)));
+        } else {
+            cudaFuncSetAttribute(k_wmedian_refine_list<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            LAUNCH(ctx, "wmedian_refine", (k_wmedian_refine_list<32><<<blocks, 32, smem, ctx->stream>>>(dL, filled, list + 1, list, H, W, win, alpha_r, alpha_s, out)));
+        }
+        return ASW_OK;
+    }
     LAUNCH(ctx, "wmedian_refine", (k_wmedian_refine<<<dim3(cdiv(W, 32), H), 32, 0, ctx->stream>>>(dL, filled, valid, H, W, win, alpha_r, alpha_s, out)));
     return ASW_OK;
 }

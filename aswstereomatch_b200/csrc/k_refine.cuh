@@ -105,3 +105,75 @@ __global__ void k_wmedian_refine(const uint8_t* __restrict__ img, const float* _
     }
     out[p] = result;
 }
+
+// ---------------------------------------------------------------------------------------------
+// List-driven variant (the default when the window fits in shared memory).  Only the pixels the LR check rejected
+// are refined, and they are few and scattered: k_refine_compact copies the valid pixels through and appends the
+// invalid ones to a list, k_wmedian_refine_list walks the list with one thread per pixel (no idle lanes), evaluates
+// every window weight ONCE (one double-precision exp per element; the spatial factor comes from a per-CTA table)
+// into a thread-private shared-memory column together with the window's values, and runs the selection of
+// A.cpp:3276-3304 on those columns.  Same operations in the same order as k_wmedian_refine: identical results.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_refine_compact(const float* __restrict__ filled, const uint8_t* __restrict__ valid, int n,
+                                 float* __restrict__ out, int* __restrict__ list, int* __restrict__ count) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (valid[i]) { out[i] = filled[i]; return; }
+    list[atomicAdd(count, 1)] = i;
+}
+
+template <int BT>
+__global__ void __launch_bounds__(BT)
+k_wmedian_refine_list(const uint8_t* __restrict__ img, const float* __restrict__ filled, const int* __restrict__ list,
+                      const int* __restrict__ count, int H, int W, int win, double alpha_r, float alpha_s,
+                      float* __restrict__ out) {
+    extern __shared__ float sm_wm[];
+    const int ne = win * win, h = win / 2, tid = threadIdx.x;
+    float* wsp = sm_wm;                      // [ne]      exp(-dist^2 / rateS)  (A.cpp:3219-3225)
+    float* wts = wsp + ne;                   // [ne][BT]  colour * spatial weight of the thread's pixel
+    float* vals = wts + (size_t)ne * BT;     // [ne][BT]  window of the filled map
+    for (int e = tid; e < ne; e += BT) {
+        int wy = e / win, wx = e - wy * win;
+        float dist2 = __fadd_rn((float)((wx - h) * (wx - h)), (float)((wy - h) * (wy - h)));
+        wsp[e] = (float)exp((double)__fmul_rn(dist2, alpha_s));
+    }
+    __syncthreads();
+    const int n_inv = *count;
+    for (int idx = blockIdx.x * BT + tid; idx < n_inv; idx += gridDim.x * BT) {
+        const int p = list[idx], y = p / W, x = p - y * W;
+        const uint8_t* c = img + (size_t)p * 3;
+        double total = 0;
+        for (int wy = 0, e = 0; wy < win; wy++) {
+            const int sy = border_idx(y - h + wy, H, 0);
+            for (int wx = 0; wx < win; wx++, e++) {
+                const int sx = border_idx(x - h + wx, W, 0);
+                const size_t q = (size_t)sy * W + sx;
+                const float w = __fmul_rn(wm_color_weight(c, img + q * 3, alpha_r), wsp[e]);   // A.cpp:3273 order
+                wts[e * BT + tid] = w;
+                vals[e * BT + tid] = filled[q];
+                total += (double)w;
+            }
+        }
+        const double half = total / 2;
+        double partial = 0;
+        float cur = -INFINITY, prev_val = 0.0f, result = filled[p];
+        bool first = true, done = false;
+        while (!done) {
+            float nxt = INFINITY; bool found = false;                 // next distinct value above cur
+            for (int e = 0; e < ne; e++) {
+                const float v = vals[e * BT + tid];
+                if (v > cur && v <= nxt) { nxt = v; found = true; }
+            }
+            if (!found) break;
+            for (int e = 0; e < ne; e++) {                            // window row-major = the multimap's insertion order
+                if (vals[e * BT + tid] != nxt) continue;
+                partial += (double)wts[e * BT + tid];
+                if (partial > half) { result = first ? nxt : prev_val; done = true; break; }
+                first = false;
+                prev_val = nxt;
+            }
+            cur = nxt;
+        }
+        out[p] = result;
+    }
+}
