@@ -147,13 +147,14 @@ k_geo_dist_t(const uint32_t* __restrict__ ext, int H, int W, float* __restrict__
     }
 }
 
-#define GEO_Q 4
 struct GeoGeom { int H, W, win, h, sign, d_first, n_cand; };
 
 // thread = pixel, blockIdx.z = chunk of GEO_Q candidates.  dref/dtgt: [win*win][H][W]; pref/ptgt: packed BGRx [H][W]
+// c_base: index of the launch's first candidate in the aggregated-cost volume (g.d_first is its disparity).
+template <int GEO_Q>
 __global__ void __launch_bounds__(128)
-k_geo_aggregate(const float* __restrict__ dref, const float* __restrict__ dtgt, const uint32_t* __restrict__ pref,
-                const uint32_t* __restrict__ ptgt, GeoGeom g, unsigned long long* __restrict__ keys,
+k_geo_aggregate_q(const float* __restrict__ dref, const float* __restrict__ dtgt, const uint32_t* __restrict__ pref,
+                const uint32_t* __restrict__ ptgt, GeoGeom g, int c_base, unsigned long long* __restrict__ keys,
                 float* __restrict__ agg) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= g.W) return;
@@ -199,8 +200,12 @@ k_geo_aggregate(const float* __restrict__ dref, const float* __restrict__ dtgt, 
     for (int q = 0; q < GEO_Q; q++) {
         if (q < nq) {
             double E = num[q] / den[q];
-            if (agg) agg[(size_t)(c0 + q) * n + p] = (float)E;
-            best = min(best, wta_key_d(E, dq[q]));
+            if (agg) agg[(size_t)(c_base + c0 + q) * n + p] = (float)E;
+            // c_base > 0: the lower candidates come from another kernel (other summation order).  Where every operand of
+            // candidate d is clamped to the same pixels as for d - 1 (x + h <= d - 1 for LEFT, x - h >= W - d for RIGHT)
+            // the reference's two costs are the same number and strict < keeps the lower d: d cannot win there.
+            const bool same_as_lower = c_base > 0 && (g.sign > 0 ? x + h <= dq[q] - 1 : x - h >= W - dq[q]);
+            if (!same_as_lower) best = min(best, wta_key_d(E, dq[q]));
         }
     }
     atomicMin(&keys[p], best);
@@ -706,9 +711,26 @@ static asw_status dev_geodesic(asw_ctx* ctx, const uint8_t* dL, const uint8_t* d
     const float* dref = left ? distL : distR; const float* dtgt = left ? distR : distL;
     const uint32_t* cref = left ? pl : pr; const uint32_t* ctgt = left ? pr : pl;
     if (getenv("ASW_GEO_GENERIC")) {
-        dim3 grid(cdiv(W, 128), H, cdiv(g.n_cand, GEO_Q));
-        LAUNCH(ctx, "geo_aggregate", (k_geo_aggregate<<<grid, 128, 0, ctx->stream>>>(dref, dtgt, cref, ctgt, g, keys, agg_dev)));
+        dim3 grid(cdiv(W, 128), H, cdiv(g.n_cand, 4));
+        LAUNCH(ctx, "geo_aggregate", (k_geo_aggregate_q<4><<<grid, 128, 0, ctx->stream>>>(dref, dtgt, cref, ctgt, g, 0, keys, agg_dev)));
         return keys_to_disp(ctx, keys, n, disp_dev);
+    }
+    // D+1 candidates is one more than a multiple of 32 for the usual disparity ranges: a remainder of <= 4 candidates
+    // would run the diagonal kernel with one warp per CTA (all the staging, 1/8 of the work).  The thread-per-pixel
+    // kernel evaluates exactly those candidates over the whole image instead.
+    const int rem = g.n_cand % 32;
+    if (rem >= 1 && rem <= 4 && g.n_cand > 32 && !getenv("ASW_GEO_DIAG_REM")) {
+        GeoGeom gr = g;
+        const int c1 = g.n_cand - rem;
+        gr.d_first = g.d_first + c1; gr.n_cand = rem;
+        dim3 grid(cdiv(W, 128), H, 1);
+        switch (rem) {
+            case 1: LAUNCH(ctx, "geo_aggregate_rem", (k_geo_aggregate_q<1><<<grid, 128, 0, ctx->stream>>>(dref, dtgt, cref, ctgt, gr, c1, keys, agg_dev))); break;
+            case 2: LAUNCH(ctx, "geo_aggregate_rem", (k_geo_aggregate_q<2><<<grid, 128, 0, ctx->stream>>>(dref, dtgt, cref, ctgt, gr, c1, keys, agg_dev))); break;
+            case 3: LAUNCH(ctx, "geo_aggregate_rem", (k_geo_aggregate_q<3><<<grid, 128, 0, ctx->stream>>>(dref, dtgt, cref, ctgt, gr, c1, keys, agg_dev))); break;
+            default: LAUNCH(ctx, "geo_aggregate_rem", (k_geo_aggregate_q<4><<<grid, 128, 0, ctx->stream>>>(dref, dtgt, cref, ctgt, gr, c1, keys, agg_dev))); break;
+        }
+        g.n_cand = c1;
     }
     const int h = g.h, nseg = cdiv(W, GT_X);
     // segments whose window sample columns are clamped BEFORE the disparity shift take the scalar BORDER path:
