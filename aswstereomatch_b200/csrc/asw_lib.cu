@@ -298,26 +298,41 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
     Feat *fref, *ftgt;
     ASW_TRY(ws_get(ctx, WS_FEAT_REF, n, &fref));
     ASW_TRY(ws_get(ctx, WS_FEAT_TGT, (size_t)H * v.Wp, &ftgt));
-    LAUNCH(ctx, "features", (k_features<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(v.ref, H, W, 0, 0, fref)));
-    LAUNCH(ctx, "features", (k_features<<<dim3(cdiv(v.Wp, 128), H), 128, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, ftgt)));
+    const bool streaming = gfs_supported(H, W, win) && !getenv("ASW_GF_TILED") && !getenv("ASW_GF_GENERIC");
     GuidePrep gp;
-    ASW_TRY(prep_guide(ctx, v.ref, H, W, 3, win, eps, &gp));                        // A.cpp:3004 / 3019
+    if (!streaming) {
+        LAUNCH(ctx, "features", (k_features<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(v.ref, H, W, 0, 0, fref)));
+        LAUNCH(ctx, "features", (k_features<<<dim3(cdiv(v.Wp, 128), H), 128, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, ftgt)));
+        ASW_TRY(prep_guide(ctx, v.ref, H, W, 3, win, eps, &gp));                    // A.cpp:3004 / 3019
+    }
     uint32_t* slice_mm;
     ASW_TRY(ws_get(ctx, WS_SLICE_MM, (size_t)2 * num_d, &slice_mm));
     LAUNCH(ctx, "init_slice_mm", (k_init_slice_mm<<<cdiv(num_d, 128), 128, 0, ctx->stream>>>(slice_mm, num_d)));
     TadParams tp = make_tad_params(0.4, 10, 50);                                     // A.cpp:2990
-    if (gfs_supported(H, W, win) && !getenv("ASW_GF_TILED") && !getenv("ASW_GF_GENERIC")) {
+    if (streaming) {
         // streaming kernel (k_guided_stream.cuh): cost, both box levels and q' on chip; 4 B per evaluation to HBM
         FeatF *rff, *tff; GfsMoments* gmom; float2* aff;
+        int* gmm;
+        ASW_TRY(ws_get(ctx, WS_MISC0, (size_t)64, &gmm));
+        ASW_TRY(ws_get(ctx, WS_GUIDE_I, n, &gp.Gi));
+        gp.mm = gmm;
         ASW_TRY(ws_get(ctx, WS_FEATF_REF, n, &rff));
         ASW_TRY(ws_get(ctx, WS_FEATF_TGT, (size_t)H * v.Wp, &tff));
         ASW_TRY(ws_get(ctx, WS_GUIDE_NM, n, &gmom));
         ASW_TRY(ws_get(ctx, WS_AFF, (size_t)num_d, &aff));
-        size_t nt = (size_t)H * v.Wp;
-        LAUNCH(ctx, "feat_to_float", (k_feat_to_float<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(fref, n, 1.0f, rff)));
-        LAUNCH(ctx, "feat_to_float", (k_feat_to_float<<<(unsigned)((nt + 255) / 256), 256, 0, ctx->stream>>>(ftgt, nt, -1.0f, tff)));
-        LAUNCH(ctx, "gfs_pack_guide", (k_gfs_pack_guide<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
-                                          gp.Gm, gp.Gd, n, 1.0f / (float)(win * win), gmom)));
+        // float feature records straight from the images (the target's gradients negated)
+        LAUNCH(ctx, "features", (k_features_f<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(v.ref, H, W, 0, 0, 1.0f, rff)));
+        LAUNCH(ctx, "features", (k_features_f<<<dim3(cdiv(v.Wp, 128), H), 128, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, -1.0f, tff)));
+        {
+            // guidance: global min / max (cv::normalize is over all channels), then the fused moments kernel
+            LAUNCH(ctx, "init_mm", (k_init_mm_u8<<<1, 1, 0, ctx->stream>>>(gmm)));
+            LAUNCH(ctx, "minmax_u8", (k_minmax_u8<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(v.ref, n * 3, gmm)));
+            const int strips_g = cdiv(W, GFS_GM_COLS - (win - 1));
+            const int bands_g = std::max(1, std::min(cdiv(H, 2 * win), cdiv(4 * ctx->sm_count, strips_g)));
+            const int band_rows = cdiv(H, bands_g);
+            LAUNCH(ctx, "guide_moments", (k_gfs_guide_moments<<<dim3(strips_g, cdiv(H, band_rows)), GFS_GM_COLS, 0, ctx->stream>>>(
+                                             v.ref, gmm, H, W, win, (float)eps, band_rows, gp.Gi, gmom)));
+        }
         const int QW = GFS_IW - 2 * (win - 1);
         GfsGeom g;
         g.H = H; g.W = W; g.Wp = v.Wp; g.Wq = cdiv(W, QW) * QW; g.x0_step = v.x0_step; g.D = 0; g.nbands = 2;

@@ -35,7 +35,6 @@
 
 // float feature record: gradients as exact-integer floats (|g| <= 4080), colour bytes last so that (g0, g1) sits in
 // an aligned register pair.  The target plane stores NEGATED gradients: |ga - gb| = |ga + (-gb)| is one FADD2 + FADD.
-struct __align__(16) FeatF { float g0, g1, g2; uint32_t bgr; };
 
 __global__ void k_feat_to_float(const Feat* __restrict__ in, size_t n, float sign, FeatF* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,6 +60,70 @@ __global__ void k_gfs_pack_guide(const float4* __restrict__ Gm, const float4* __
     r.nm = make_float4(-m.x, -m.y, -m.z, __fdiv_rn(inv, d.z));
     r.rd = make_float4(__fdiv_rn(inv, d.x), __fdiv_rn(inv, d.y), 0.0f, 0.0f);
     out[i] = r;
+}
+
+// Fused guidance preparation of the streaming path (replaces guide_normalize + box_f32 over 6 planes + guide_finish +
+// gfs_pack_guide): I = normalize(guide) (A.cpp:2774), mean_I = box(I), corr_II = box(I*I) (A.cpp:2778, 2796),
+// var = corr_II - mean_I^2, den = eps + var (A.cpp:2799, 2846) -> Gi = {I} and the 32-byte moment record.
+// One thread per halo column walks down a band of rows with the 6 vertical window sums in double registers
+// (one row in, one row out -- box sums of these float values are exact in double, so any summation order rounds to
+// the same float as cv::boxFilter's), the horizontal sums run over shared memory.  Only the guide's bytes are read.
+#define GFS_GM_COLS 128
+__global__ void __launch_bounds__(GFS_GM_COLS)
+k_gfs_guide_moments(const uint8_t* __restrict__ guide, const int* __restrict__ mm, int H, int W, int k, float eps,
+                    int band_rows, float4* __restrict__ Gi, GfsMoments* __restrict__ out) {
+    __shared__ double vs[2][6][GFS_GM_COLS];
+    const int a = k / 2, SW = GFS_GM_COLS - (k - 1);
+    const int cx = threadIdx.x, x0 = blockIdx.x * SW;
+    const int sx = border_idx(x0 - a + cx, W, 1);                 // boxFilter default border: REFLECT_101
+    float sf, hf;
+    minmax_scale_shift((double)mm[0], (double)mm[1], &sf, &hf);
+    const int y_begin = blockIdx.y * band_rows, y_end = min(H, y_begin + band_rows);
+    double V[6];
+#pragma unroll
+    for (int c = 0; c < 6; c++) V[c] = 0.0;
+    auto add_row = [&](int y, double sign) {
+        const uint8_t* p = guide + ((size_t)border_idx(y, H, 1) * W + sx) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float v = fmaf((float)p[c], sf, hf);            // cv::normalize
+            V[c] += sign * (double)v;
+            V[3 + c] += sign * (double)__fmul_rn(v, v);           // guidedImg.mul(guidedImg)
+        }
+    };
+    for (int j = -a; j < a; j++) add_row(y_begin + j, 1.0);
+    const double scale = 1.0 / ((double)k * k);
+    const float inv = 1.0f / (float)(k * k);
+    const int xo = x0 + cx;                                       // output column of this thread
+    const bool writer = cx < SW && xo < W;
+    int buf = 0;
+    for (int y = y_begin; y < y_end; y++) {
+        add_row(y + a, 1.0);
+#pragma unroll
+        for (int c = 0; c < 6; c++) vs[buf][c][cx] = V[c];
+        add_row(y - a, -1.0);
+        __syncthreads();
+        if (writer) {
+            float m[3], dn[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                double s1 = 0.0, s2 = 0.0;
+                for (int j = 0; j < k; j++) { s1 += vs[buf][c][cx + j]; s2 += vs[buf][3 + c][cx + j]; }
+                m[c] = (float)(s1 * scale);
+                const float corr = (float)(s2 * scale);
+                const float var = __fsub_rn(corr, __fmul_rn(m[c], m[c]));          // A.cpp:2799
+                dn[c] = __fadd_rn(__fmul_rn(1.0f, eps), var);                      // A.cpp:2846
+            }
+            const size_t i = (size_t)y * W + xo;
+            const uint8_t* p = guide + i * 3;
+            Gi[i] = make_float4(fmaf((float)p[0], sf, hf), fmaf((float)p[1], sf, hf), fmaf((float)p[2], sf, hf), 0.0f);
+            GfsMoments r;
+            r.nm = make_float4(-m[0], -m[1], -m[2], __fdiv_rn(inv, dn[2]));
+            r.rd = make_float4(__fdiv_rn(inv, dn[0]), __fdiv_rn(inv, dn[1]), 0.0f, 0.0f);
+            out[i] = r;
+        }
+        buf ^= 1;
+    }
 }
 
 struct GfsGeom {
@@ -467,6 +530,9 @@ __global__ void k_gfs_affine(const uint32_t* __restrict__ slice_mm, int D, float
 
 // q' volume [H][D][Wq] -> normalised costs -> WTA keys (strict <, ascending d, NaN / inf never win; A.cpp:3032-3048).
 // One thread = 4 adjacent pixels; the D loads of a thread are independent (unrolled by 8).
+// AGG = false (the production path) has no store in the loop, and the loads of 8 slices are issued before the
+// first use: 128 bytes in flight per thread.
+template <bool AGG>
 __global__ void __launch_bounds__(128)
 k_gfs_wta(const float* __restrict__ qv, const float2* __restrict__ aff, int D, int H, int W, int Wq, int d_label0,
           unsigned long long* __restrict__ keys, float* __restrict__ agg) {
@@ -477,15 +543,23 @@ k_gfs_wta(const float* __restrict__ qv, const float2* __restrict__ aff, int D, i
     float best[4] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000), __int_as_float(0x7f800000)};
     int bd[4] = {0, 0, 0, 0};
     const size_t n = (size_t)H * W;
-#pragma unroll 8
-    for (int d = 0; d < D; d++) {
-        const float4 v = __ldcs((const float4*)(p + (size_t)d * slice));
-        const float2 sh = __ldg(&aff[d]);
-        const float q[4] = {fmaf(v.x, sh.x, sh.y), fmaf(v.y, sh.x, sh.y), fmaf(v.z, sh.x, sh.y), fmaf(v.w, sh.x, sh.y)};
+    for (int d0 = 0; d0 < D; d0 += 8) {
+        float4 v[8];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            if (q[k] < best[k]) { best[k] = q[k]; bd[k] = d; }
-            if (agg && x4 + k < W) agg[(size_t)d * n + (size_t)y * W + x4 + k] = q[k];
+        for (int u = 0; u < 8; u++)
+            if (d0 + u < D) v[u] = __ldcs((const float4*)(p + (size_t)(d0 + u) * slice));
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int d = d0 + u;
+            if (d < D) {
+                const float2 sh = __ldg(&aff[d]);
+                const float q[4] = {fmaf(v[u].x, sh.x, sh.y), fmaf(v[u].y, sh.x, sh.y), fmaf(v[u].z, sh.x, sh.y), fmaf(v[u].w, sh.x, sh.y)};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (q[k] < best[k]) { best[k] = q[k]; bd[k] = d; }
+                    if (AGG && x4 + k < W) agg[(size_t)d * n + (size_t)y * W + x4 + k] = q[k];
+                }
+            }
         }
     }
 #pragma unroll
@@ -522,7 +596,12 @@ static asw_status gfs_launch(asw_ctx* ctx, const FeatF* fref, const FeatF* ftgt,
     LAUNCH(ctx, "gfs_filter", (k_gfs_filter<K><<<dim3(strips, groups, nb), 2 * GFS_THREADS, smem, ctx->stream>>>(
                                   fref, ftgt, Gi, Gmom, guide_mm, g, ts, tp.c0, qv, slice_mm)));
     LAUNCH(ctx, "gfs_affine", (k_gfs_affine<<<cdiv(cn, 128), 128, 0, ctx->stream>>>(slice_mm, cn, tp.c0, aff)));
-    LAUNCH(ctx, "gfs_wta", (k_gfs_wta<<<dim3(cdiv(cdiv(g.W, 4), 128), g.H), 128, 0, ctx->stream>>>(
-                               qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg)));
+    if (agg) {
+        LAUNCH(ctx, "gfs_wta", (k_gfs_wta<true><<<dim3(cdiv(cdiv(g.W, 4), 128), g.H), 128, 0, ctx->stream>>>(
+                                   qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg)));
+    } else {
+        LAUNCH(ctx, "gfs_wta", (k_gfs_wta<false><<<dim3(cdiv(cdiv(g.W, 4), 128), g.H), 128, 0, ctx->stream>>>(
+                                   qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg)));
+    }
     return ASW_OK;
 }

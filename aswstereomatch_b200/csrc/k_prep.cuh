@@ -18,8 +18,14 @@ struct __align__(16) Feat {
 // Build records for an image padded on the column axis with BORDER_REFLECT (pad_l / pad_r columns);
 // the gradient is filter2D([-3 0 3; -10 0 10; -3 0 3]) of the PADDED image with BORDER_REFLECT_101
 // (A.cpp:446-450 applies filter2D to right_border).
-__global__ void k_features(const uint8_t* __restrict__ img, int H, int W, int pad_l, int pad_r,
-                           Feat* __restrict__ out) {
+// float form of the record for the streaming guided kernel: exact-integer gradients (optionally negated) + BGR
+struct __align__(16) FeatF { float g0, g1, g2; uint32_t bgr; };
+
+// FLOAT_OUT = false: Feat records; true: FeatF records with the gradients multiplied by `sign` (the streaming
+// kernel adds the target's negated gradients to the reference's).
+template <bool FLOAT_OUT>
+__device__ __forceinline__ void features_body(const uint8_t* __restrict__ img, int H, int W, int pad_l, int pad_r,
+                                              void* __restrict__ out_v, float sign) {
     int Wp = W + pad_l + pad_r;
     int xp = blockIdx.x * blockDim.x + threadIdx.x;
     int y = blockIdx.y;
@@ -44,12 +50,27 @@ __global__ void k_features(const uint8_t* __restrict__ img, int H, int W, int pa
         g[c] = v;
     }
     const uint8_t* px = img + ((size_t)y * W + xs[1]) * 3;
-    Feat f;
-    f.bgr = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16);
-    f.g01 = ((uint32_t)(uint16_t)(int16_t)g[0]) | ((uint32_t)(uint16_t)(int16_t)g[1] << 16);
-    f.g2 = (uint32_t)(uint16_t)(int16_t)g[2];
-    f.pad = 0;
-    out[(size_t)y * Wp + xp] = f;
+    const uint32_t bgr = (uint32_t)px[0] | ((uint32_t)px[1] << 8) | ((uint32_t)px[2] << 16);
+    if (FLOAT_OUT) {
+        FeatF f;
+        f.g0 = sign * (float)g[0]; f.g1 = sign * (float)g[1]; f.g2 = sign * (float)g[2];
+        f.bgr = bgr;
+        ((FeatF*)out_v)[(size_t)y * Wp + xp] = f;
+    } else {
+        Feat f;
+        f.bgr = bgr;
+        f.g01 = ((uint32_t)(uint16_t)(int16_t)g[0]) | ((uint32_t)(uint16_t)(int16_t)g[1] << 16);
+        f.g2 = (uint32_t)(uint16_t)(int16_t)g[2];
+        f.pad = 0;
+        ((Feat*)out_v)[(size_t)y * Wp + xp] = f;
+    }
+}
+__global__ void k_features(const uint8_t* __restrict__ img, int H, int W, int pad_l, int pad_r, Feat* __restrict__ out) {
+    features_body<false>(img, H, W, pad_l, pad_r, out, 1.0f);
+}
+__global__ void k_features_f(const uint8_t* __restrict__ img, int H, int W, int pad_l, int pad_r, float sign,
+                             FeatF* __restrict__ out) {
+    features_body<true>(img, H, W, pad_l, pad_r, out, sign);
 }
 
 // cvtColor(BGR2GRAY) u8: (3735 B + 19235 G + 9798 R + 2^14) >> 15, with optional REFLECT column padding
