@@ -43,7 +43,7 @@ __global__ void k_grid_splat(const uint8_t* __restrict__ lg, const uint8_t* __re
 
 // one recursive in-place 5-tap pass along a strided line of n+1 cells, n >= 3 (A.cpp:1936-2183).  The two edge
 // rules at either end are peeled, so the interior loop is branch-free; expressions keep the reference's order.
-template <typename ST>
+template <typename ST, bool BATCH>
 __device__ __forceinline__ void grid_pass_line(double* __restrict__ s, int* __restrict__ c, ST stride, int n) {
     // rolling registers: m2, m1 = already-updated v[i-2], v[i-1]; s0 = v[i]; p1, p2 = original v[i+1], v[i+2]
     double sm2, sm1, s0 = s[0], sp1 = s[stride], sp2 = s[2 * stride], sp3 = s[3 * stride];
@@ -66,11 +66,34 @@ __device__ __forceinline__ void grid_pass_line(double* __restrict__ s, int* __re
     ns = 0.2 * sm1 + 0.5 * s0 + 0.2 * sp1 + 0.1 * sp2;
     nc = 0.2 * cm1 + 0.5 * c0 + 0.2 * cp1 + 0.1 * cp2;
     GRID_STORE_SHIFT(1)
-    for (int i = 2; i <= n - 2; i++) {
-        if (i + 3 <= n) { sp3 = s[(ST)(i + 3) * stride]; cp3 = (double)c[(ST)(i + 3) * stride]; }
-        ns = 0.0625 * sm2 + 0.25 * sm1 + 0.375 * s0 + 0.25 * sp1 + 0.0625 * sp2;
-        nc = 0.0625 * cm2 + 0.25 * cm1 + 0.375 * c0 + 0.25 * cp1 + 0.0625 * cp2;
-        GRID_STORE_SHIFT(i)
+    // interior: the originals entering the window during the next 8 steps are loaded together (8 independent loads
+    // in flight per thread: the global y / x passes are latency-bound otherwise), before those cells are overwritten
+    if (!BATCH) {
+        for (int i = 2; i <= n - 2; i++) {
+            if (i + 3 <= n) { sp3 = s[(ST)(i + 3) * stride]; cp3 = (double)c[(ST)(i + 3) * stride]; }
+            ns = 0.0625 * sm2 + 0.25 * sm1 + 0.375 * s0 + 0.25 * sp1 + 0.0625 * sp2;
+            nc = 0.0625 * cm2 + 0.25 * cm1 + 0.375 * c0 + 0.25 * cp1 + 0.0625 * cp2;
+            GRID_STORE_SHIFT(i)
+        }
+    }
+    for (int i0 = 2; BATCH && i0 <= n - 2; i0 += 8) {
+        double in_s[8];
+        int in_c[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int k = i0 + 3 + u;
+            if (k <= n) { in_s[u] = s[(ST)k * stride]; in_c[u] = c[(ST)k * stride]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int i = i0 + u;
+            if (i <= n - 2) {
+                sp3 = in_s[u]; cp3 = (double)in_c[u];
+                ns = 0.0625 * sm2 + 0.25 * sm1 + 0.375 * s0 + 0.25 * sp1 + 0.0625 * sp2;
+                nc = 0.0625 * cm2 + 0.25 * cm1 + 0.375 * c0 + 0.25 * cp1 + 0.0625 * cp2;
+                GRID_STORE_SHIFT(i)
+            }
+        }
     }
     // i = n - 1
     ns = 0.1 * sm2 + 0.2 * sm1 + 0.5 * s0 + 0.2 * sp1;
@@ -104,7 +127,7 @@ __global__ void k_grid_pass(double* __restrict__ S, int* __restrict__ C, GridDim
     else if (axis == 1) { size_t xy = l / Wd; int w = (int)(l - xy * Wd); base = xy * Z * Wd + w; stride = Wd; n = g.nz; }
     else if (axis == 2) { size_t x = l / ((size_t)Z * Wd); size_t zw = l - x * Z * Wd; base = x * Y * Z * Wd + zw; stride = (size_t)Z * Wd; n = g.ny; }
     else { base = l; stride = (size_t)Y * Z * Wd; n = g.nx; }
-    grid_pass_line<size_t>(s + base, c + base, stride, n);
+    grid_pass_line<size_t, true>(s + base, c + base, stride, n);
 }
 
 // splat + w + z fused: the CTA builds the (z, w) planes it owns directly in shared memory from the ~(2 sS)^2
@@ -175,11 +198,11 @@ k_grid_build_wz(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, 
         for (int i = tid; i < np * Z * pitch; i += 128) ss[i] = (double)si[i];
         __syncthreads();
         for (int l = tid; l < np * Z; l += 128)             // w pass: line = (plane, z), unit stride
-            grid_pass_line<int>(ss + l * pitch, cc + l * pitch, 1, g.nw);
+            grid_pass_line<int, false>(ss + l * pitch, cc + l * pitch, 1, g.nw);
         __syncthreads();
         for (int l = tid; l < np * Wd; l += 128) {          // z pass: line = (plane, w), stride = pitch
             const int pl = l / Wd, w = l - pl * Wd;
-            grid_pass_line<int>(ss + pl * Z * pitch + w, cc + pl * Z * pitch + w, pitch, g.nz);
+            grid_pass_line<int, false>(ss + pl * Z * pitch + w, cc + pl * Z * pitch + w, pitch, g.nz);
         }
         __syncthreads();
         const size_t base = (size_t)p0 * cells;
