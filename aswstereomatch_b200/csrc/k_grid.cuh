@@ -231,12 +231,17 @@ __global__ void k_grid_slice(const uint8_t* __restrict__ lg, const uint8_t* __re
     // all 32 corner loads are issued before the first use (the gather is latency-bound otherwise)
     double vs[16];
     int vc[16];
+    // corner k = (X -/+ 1, Y -/+ 1, Z -/+ 1, Q -/+ 1): one in-range flag and one 32-bit offset per axis end
+    const int sY = g.nw + 1, sZ = sY * (g.nz + 1), sX = sZ * (g.ny + 1);    // strides of w.. are 1, sY(z), sZ(y), sX(x)
+    const bool okx[2] = {X - 1 >= 0 && X - 1 <= g.nx, X + 1 >= 0 && X + 1 <= g.nx};
+    const bool oky[2] = {Y - 1 >= 0 && Y - 1 <= g.ny, Y + 1 >= 0 && Y + 1 <= g.ny};
+    const bool okz[2] = {Z - 1 >= 0 && Z - 1 <= g.nz, Z + 1 >= 0 && Z + 1 <= g.nz};
+    const bool okq[2] = {Q - 1 >= 0 && Q - 1 <= g.nw, Q + 1 >= 0 && Q + 1 <= g.nw};
+    const int base = (X - 1) * sX + (Y - 1) * sZ + (Z - 1) * sY + (Q - 1);
 #pragma unroll
     for (int k = 0; k < 16; k++) {
-        int gx = X + ((k & 8) ? 1 : -1), gy = Y + ((k & 4) ? 1 : -1);
-        int gz = Z + ((k & 2) ? 1 : -1), gq = Q + ((k & 1) ? 1 : -1);
-        bool in = gx >= 0 && gx <= g.nx && gy >= 0 && gy <= g.ny && gz >= 0 && gz <= g.nz && gq >= 0 && gq <= g.nw;
-        size_t id = in ? gidx(g, gx, gy, gz, gq) : 0;
+        const bool in = okx[(k >> 3) & 1] && oky[(k >> 2) & 1] && okz[(k >> 1) & 1] && okq[k & 1];
+        const int id = base + ((k & 8) ? 2 * sX : 0) + ((k & 4) ? 2 * sZ : 0) + ((k & 2) ? 2 * sY : 0) + ((k & 1) ? 2 : 0);
         vs[k] = in ? __ldg(&s[id]) : 0.0;                               // map default-insert reads (0.0, 0)
         vc[k] = in ? __ldg(&c[id]) : 0;
     }
