@@ -371,7 +371,7 @@ template <int SIGN, bool XS_CLAMP>
 __device__ __forceinline__ void trad_lin_body(const float* __restrict__ RF, const float* __restrict__ TF,
                                               const int4* __restrict__ taps, const float* __restrict__ c2s, float a2,
                                               const TradGeom& g, int IWr, int IWt, int x0t, int y0t, int oxt, int x, int y,
-                                              int d_lo, double* num, double* den) {
+                                              int d_lo, float* num, float* den) {
     const int W = g.W, H = g.H, win = g.win, h = g.h;
     const int yc = min(y, H - 1), xc = min(x, W - 1);             // threads past the image edge compute a clamped copy
     const int rowc = yc - y0t + h, colc = xc - x0t + h;           // centre cell in the reference tile
@@ -425,12 +425,12 @@ __device__ __forceinline__ void trad_lin_body(const float* __restrict__ RF, cons
             }
         }
 #pragma unroll
-        for (int q = 0; q < TR_Q; q++) { num[q] += (double)fn[q]; den[q] += (double)fd[q]; }
+        for (int q = 0; q < TR_Q; q++) { num[q] = __fadd_rn(num[q], fn[q]); den[q] = __fadd_rn(den[q], fd[q]); }
     }
 }
 
 template <int SIGN>
-__global__ void __launch_bounds__(TR_TW * TR_TH)
+__global__ void __launch_bounds__(TR_TW * TR_TH, 3)
 k_trad_lin(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, const float* __restrict__ c2, float a2,
            TradGeom g, unsigned long long* __restrict__ keys, float* __restrict__ agg) {
     extern __shared__ __align__(16) float sm_tr[];
@@ -465,9 +465,10 @@ k_trad_lin(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, con
     }
     __syncthreads();
     const int x = x0t + threadIdx.x, y = y0t + threadIdx.y;
-    double num[TR_Q], den[TR_Q];
+    // fp32 over a window row, fp32 across rows (all terms are non-negative: ~1e-6 relative against the reference's double)
+    float num[TR_Q], den[TR_Q];
 #pragma unroll
-    for (int q = 0; q < TR_Q; q++) { num[q] = 0; den[q] = 0; }
+    for (int q = 0; q < TR_Q; q++) { num[q] = 0.0f; den[q] = 0.0f; }
     // does the candidate shift clamp the weighted pixel anywhere in this tile?
     const bool xs_clamp = SIGN > 0 ? (x0t - d_hi < 0) : (x0t + TR_TW - 1 + d_hi > W - 1);
     if (xs_clamp) trad_lin_body<SIGN, true>(RF, TF, taps, c2s, a2, g, IWr, IWt, x0t, y0t, oxt, x, y, d_lo, num, den);
@@ -478,7 +479,7 @@ k_trad_lin(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, con
 #pragma unroll
         for (int q = 0; q < TR_Q; q++) {
             if (q < nq) {
-                double E = num[q] / den[q];
+                double E = (double)num[q] / (double)den[q];
                 if (agg) agg[(size_t)(c0 + q) * H * W + p] = (float)E;
                 best = min(best, wta_key_d(E, d_lo + q));
             }
