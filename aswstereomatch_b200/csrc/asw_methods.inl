@@ -430,8 +430,11 @@ extern "C" asw_status asw_split_local_keys(asw_ctx* ctx, const asw_u8_image* L, 
     if (!dispatcher_args(algorithm, disp_type, win, min_d, num_d, &m))
         return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "algorithm outside the dense-matching hot path%s%s");
     ASW_TRY(method_check(ctx, m));
-    if (m.id != M_GF2) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "disparity split is implemented for GuidedF_2%s%s");
-    if (d_begin < 0 || d_end > num_d || d_begin > d_end) return asw_fail(ctx, ASW_ERR_BAD_ARG, "bad disparity range%s%s");
+    // [d_begin, d_end) indexes the candidates the method scans: num_d of them, or num_d + 1 for the methods whose
+    // reference loop runs to max_offset inclusive (traditional, geodesic, grid)
+    if (m.id != M_GF2 && m.id != M_TRAD && m.id != M_GEO && m.id != M_GRID && m.id != M_BLO1)
+        return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "disparity split is not implemented for this method%s%s");
+    if (d_begin < 0 || d_end > method_n_eval(m) || d_begin > d_end) return asw_fail(ctx, ASW_ERR_BAD_ARG, "bad disparity range%s%s");
     ASW_CUDA(ctx, cudaSetDevice(ctx->device));
     int H = L->rows, W = L->cols; size_t n = (size_t)H * W;
     uint8_t *dL, *dR;
@@ -439,8 +442,22 @@ extern "C" asw_status asw_split_local_keys(asw_ctx* ctx, const asw_u8_image* L, 
     unsigned long long* keys;
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
     ASW_TRY(init_keys(ctx, keys, n));
-    if (d_end > d_begin)
-        ASW_TRY(dev_guidedf2_keys(ctx, dL, dR, H, W, disp_type, m.p0, win, min_d, num_d, d_begin, d_end, keys, nullptr));
+    if (d_end > d_begin) {
+        if (m.id == M_GF2) {
+            ASW_TRY(dev_guidedf2_keys(ctx, dL, dR, H, W, disp_type, m.p0, win, min_d, num_d, d_begin, d_end, keys, nullptr));
+        } else {
+            // every candidate of these methods is independent of the range it is evaluated in (weights, distances and
+            // grids do not depend on it; BLO(1) keeps the full range's normaliser and crop geometry): the method runs on
+            // the sub-range and leaves its keys in WS_KEYS
+            float* tmp;
+            ASW_TRY(ws_get(ctx, WS_OUT, n, &tmp));
+            const int cnt = d_end - d_begin;
+            if (m.id == M_TRAD) ASW_TRY(dev_traditional(ctx, dL, dR, H, W, m.p0, m.p1, disp_type, win, min_d + d_begin, cnt - 1, tmp, nullptr));
+            else if (m.id == M_GEO) ASW_TRY(dev_geodesic(ctx, dL, dR, H, W, disp_type, win, min_d + d_begin, cnt - 1, tmp, nullptr));
+            else if (m.id == M_GRID) ASW_TRY(dev_bilateral_grid(ctx, dL, dR, H, W, m.p0, m.p1, min_d + d_begin, cnt - 1, tmp, nullptr));
+            else ASW_TRY(dev_blo1_range(ctx, dL, dR, H, W, m.p0, win, min_d, num_d, d_begin, d_end, tmp, nullptr));
+        }
+    }
     ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *device_keys = keys;
     return ASW_OK;

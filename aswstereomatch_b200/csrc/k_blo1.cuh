@@ -22,6 +22,7 @@ struct BloGeom {
     int x0_base, x0_step;        // padded target crop column for slice di: x0_base + x0_step * di
     int step, nl;                // level step, number of levels
     int last255;                 // 1 if the last level (255) is not a multiple of step
+    int di_lo, di_hi;            // slices [di_lo, di_hi) are aggregated by this launch (disparity-range split)
 };
 __device__ __forceinline__ int blo_level_value(const BloGeom& g, int li) {
     return (li == g.nl - 1 && g.last255) ? 255 : li * g.step;
@@ -97,7 +98,7 @@ k_blo1_aggregate(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpa
     uint8_t* Rt = Lt + IH * PP;                           // [IH][PP]
     __shared__ uint32_t need[(BLO_MAXLEV + 31) / 32];
     const int tid = threadIdx.x, x0t = blockIdx.x * BLO_TW, y0t = blockIdx.y * BLO_TH;
-    const int di = blockIdx.z;
+    const int di = g.di_lo + blockIdx.z;
     const int xoff = g.x0_base + g.x0_step * di;
     const size_t n = (size_t)g.H * g.W;
     const float* cd = cost + (size_t)di * n;
@@ -268,8 +269,8 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
     const float inv = 1.0f / (float)(WIN * WIN);
 
     for (int dd = 0; dd < dch; dd++) {
-        const int di = blockIdx.z * dch + dd;
-        if (di >= g.D) break;
+        const int di = g.di_lo + blockIdx.z * dch + dd;
+        if (di >= g.di_hi) break;
         const int xoff = g.x0_base + g.x0_step * di;
         const float* cd = cost + (size_t)di * n;
         float a[WIN], b[WIN], c[WIN];
@@ -379,13 +380,15 @@ static asw_status launch_blo1_agg2(asw_ctx* ctx, const uint8_t* gref, const uint
     int dch = 8;
     const char* e = getenv("ASW_BLO_DCH");
     if (e && atoi(e) > 0) dch = atoi(e);
-    dim3 grid(cdiv(g.W, SW), cdiv(g.H, TH), cdiv(g.D, dch));
+    dim3 grid(cdiv(g.W, SW), cdiv(g.H, TH), cdiv(g.di_hi - g.di_lo, dch));
     LAUNCH(ctx, "blo1_aggregate", (k_blo1_agg2<WIN><<<grid, BLO2_THREADS, smem, ctx->stream>>>(gref, gtgt, cost, Nk, g, dch, min_d, keys, agg_dev)));
     return ASW_OK;
 }
 
-static asw_status dev_blo1(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_r, int win,
-                           int min_d, int num_d, float* disp_dev, float* agg_dev) {
+// slices [di_lo, di_hi) of the num_d-slice problem (the whole range: dev_blo1).  agg_dev, if given, is the full
+// [num_d][H][W] volume.
+static asw_status dev_blo1_range(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_r, int win,
+                                 int min_d, int num_d, int di_lo, int di_hi, float* disp_dev, float* agg_dev) {
     size_t n = (size_t)H * W;
     BloGeom g;
     g.step = (int)(256 * rate_r);                                  // A.cpp:2549
@@ -402,6 +405,7 @@ static asw_status dev_blo1(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, i
     ViewGeom v = make_view(dL, dR, H, W, ASW_DISPARITY_LEFT, min_d, num_d);
     g.H = H; g.W = W; g.Wp = v.Wp; g.win = win; g.h = win / 2; g.D = num_d;
     g.x0_base = v.x0_base; g.x0_step = v.x0_step;
+    g.di_lo = di_lo; g.di_hi = di_hi;
     float* Nk;
     ASW_TRY(ws_get(ctx, WS_TMP0, n * 2, &Nk));
     int IW = BLO_TW + win - 1, IH = BLO_TH + win - 1, PP = IW | 1, HP = BLO_TW + 1;
@@ -425,8 +429,12 @@ static asw_status dev_blo1(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, i
         case 25: ASW_TRY(launch_blo1_agg2<25>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
         case 35: ASW_TRY(launch_blo1_agg2<35>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
         default:
-            LAUNCH(ctx, "blo1_aggregate_tiled", (k_blo1_aggregate<<<dim3(tiles.x, tiles.y, num_d), BLO_THREADS, smem_a, ctx->stream>>>(
+            LAUNCH(ctx, "blo1_aggregate_tiled", (k_blo1_aggregate<<<dim3(tiles.x, tiles.y, di_hi - di_lo), BLO_THREADS, smem_a, ctx->stream>>>(
                                                     gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)));
     }
     return keys_to_disp(ctx, keys, n, disp_dev);
+}
+static asw_status dev_blo1(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_r, int win,
+                           int min_d, int num_d, float* disp_dev, float* agg_dev) {
+    return dev_blo1_range(ctx, dL, dR, H, W, rate_r, win, min_d, num_d, 0, num_d, disp_dev, agg_dev);
 }

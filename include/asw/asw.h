@@ -159,7 +159,10 @@ asw_status asw_batch_download(asw_batch* b, int index, asw_f32_image* disparity)
  * Each rank evaluates candidates [d_begin, d_end) and gets per-pixel 64-bit keys
  * (48-bit orderable(cost) << 16 | d) in a device buffer; a MIN all-reduce over ranks (NCCL via
  * torch.distributed, or asw_keys_min_merge for peer buffers) then asw_keys_to_disparity
- * reproduces strict-< / lowest-d / NaN-never-wins exactly. */
+ * reproduces strict-< / lowest-d / NaN-never-wins exactly.
+ * Methods: GuidedF_2, traditional, geodesic, bilateral grid, BLO(1).  [d_begin, d_end) indexes the candidates the
+ * method scans: num_disparity of them (GuidedF_2, BLO(1)) or num_disparity + 1 (traditional, geodesic, grid).
+ * BLO(1) keeps the full range's normaliser (the reference takes it from the last disparity, A.cpp:2588). */
 asw_status asw_split_local_keys(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
                                 int algorithm_type, int disp_type, int win_size, int min_disparity,
                                 int num_disparity, int d_begin, int d_end, void** device_keys);

@@ -1,0 +1,99 @@
+"""Parity at BASELINE.json's full sizes for configs 1, 3a, 3b and 4 (config 2 and 5 sizes: test_gpu_guided*.py).
+
+Where the oracle finishes in seconds at full size it is compared directly (config 1; config 3a with few candidates: the
+grid dimensions, not the candidate count, are what the size changes).  For the windowed methods at 1280x720x128 the
+oracle runs on a horizontal BAND of the same pair instead: every value of an output row depends on the rows within the
+method's vertical reach only, so the oracle over rows [y0 - reach, y1 + reach) reproduces rows [y0, y1) of the full
+image exactly (the band's own top/bottom border handling never reaches them), at full width and with every candidate.
+The remaining rows are covered by size-independent properties: the disparity-range split reproduces the unsplit map,
+and the map recovers the synthetic ground truth."""
+import numpy as np
+import pytest
+
+import aswstereomatch_b200 as asw
+from aswstereomatch_b200 import sharding
+from aswstereomatch_b200.synth import make_pair
+from oracle import orc
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4
+AGREE = 0.999
+
+
+def slice_err(a, b):
+    """max over slices of |a - b| / max|b| (finite entries; the NaN / inf pattern must be identical)"""
+    a = a.astype(np.float64); b = b.astype(np.float64)
+    ok = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), ok)
+    s = np.maximum(np.abs(np.where(ok, b, 0)).reshape(b.shape[0], -1).max(axis=1), 1e-30)[:, None, None]
+    return float((np.abs(np.where(ok, a - b, 0)) / s).max())
+
+
+def split_agreement(ctx, L, R, alg, win, D, full, world=2):
+    """fraction of pixels on which the MIN-merged keys of `world` disjoint candidate ranges give the unsplit map"""
+    merged = None
+    for r in range(world):
+        lo, hi = sharding.split_range(D + 1 if alg in (asw.ADAPTIVE_WEIGHT, asw.ADAPTIVE_WEIGHT_GEODESIC, asw.ADAPTIVE_WEIGHT_BILATERAL_GRID) else D, r, world)
+        keys, _ = ctx.split_local_keys(L, R, alg, 0, win, 0, D, lo, hi)
+        merged = keys if merged is None else np.minimum(merged, keys)
+    return float((ctx.keys_to_disparity(merged) == full).mean())
+
+
+def test_config1_traditional_full_size(ctx):
+    """config 1: 384x288, 16 disparities (17 candidates), 35x35, gamma_c = 30, gamma_g = 20 -- the whole oracle"""
+    L, R, gt = make_pair(288, 384, 16, 1)
+    d, e = ctx.computeAdaptiveWeight(L, R, 30, 20, 0, 35, 0, 16, agg=True, strict=True)
+    d_ref, e_ref = orc.asw_traditional(L, R, 30, 20, 0, 35, 0, 16, agg=True)
+    assert e.shape == (17, 288, 384)
+    assert slice_err(e, e_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+    assert split_agreement(ctx, L, R, asw.ADAPTIVE_WEIGHT, 35, 16, d) == 1.0   # dispatcher literals: gamma_c = 30, gamma_g = 20
+
+
+def test_config3a_grid_full_dimensions(ctx):
+    """config 3a grid dimensions (1280x720, sS = sR = 10 -> 129 x 73 x 27 x 27 cells): bit-exact against the oracle for the
+    first candidates; all 129 candidates through the properties"""
+    L, R, gt = make_pair(720, 1280, 128, 3)
+    d, e = ctx.computeAdaptiveWeight_bilateralGrid(L, R, 0, 10, 10, 0, 2, agg=True, strict=True)
+    d_ref, e_ref = orc.asw_bilateral_grid(L, R, 0, 10, 10, 0, 2, agg=True)
+    fin = np.isfinite(e_ref)
+    assert np.array_equal(np.isnan(e), np.isnan(e_ref)) and np.array_equal(np.isfinite(e), fin)
+    assert np.array_equal(e[fin], e_ref[fin])
+    assert np.array_equal(d, d_ref)
+    full = ctx.computeAdaptiveWeight_bilateralGrid(L, R, 0, 10, 10, 0, 128, strict=True)
+    assert full.shape == (720, 1280) and full.min() >= 0 and full.max() <= 128
+    assert np.array_equal(full, ctx.stereoMatching(L, R, 0, asw.ADAPTIVE_WEIGHT_BILATERAL_GRID, 15, 0, 128, strict=True))   # dispatcher literals: sS = sR = 10
+    assert split_agreement(ctx, L, R, asw.ADAPTIVE_WEIGHT_BILATERAL_GRID, 15, 128, full, world=3) == 1.0
+
+
+def test_config3b_blo1_full_size_band(ctx):
+    """config 3b: 1280x720, 128 disparities, 35x35.  Vertical reach = 17 (box of M c) + 17 (box-SAD cost) rows."""
+    H, W, D, win = 720, 1280, 128, 35
+    L, R, gt = make_pair(H, W, D, 4)
+    d, q = ctx.computeAdaptiveWeight_BLO1(L, R, 0, 0.015, win, 0, D, agg=True, strict=True)
+    for y0, y1 in ((300, 304), (0, 3), (H - 3, H)):
+        lo, hi = max(0, y0 - 34), min(H, y1 + 34)
+        d_ref, q_ref = orc.asw_blo1(L[lo:hi], R[lo:hi], 0, 0.015, win, 0, D, agg=True)
+        rows = slice(y0 - lo, y1 - lo)
+        assert slice_err(q[:, y0:y1], q_ref[:, rows]) <= REL_TOL
+        assert (d[y0:y1] == d_ref[rows]).mean() >= AGREE
+    assert np.mean(np.abs(d - gt) <= 1) > 0.5
+    assert split_agreement(ctx, L, R, asw.ADAPTIVE_WEIGHT_BLO1, win, D, d) == 1.0
+
+
+def test_config4_geodesic_full_size_band(ctx):
+    """config 4: 1280x720, 128 disparities (129 candidates), 35x35.  Vertical reach = 17 (aggregation window) + 18 (the
+    geodesic DP's padded window around every tap... of the pixel itself: h + 1) rows."""
+    H, W, D, win = 720, 1280, 128, 35
+    L, R, gt = make_pair(H, W, D, 5)
+    d, e = ctx.computeAdaptiveWeight_geodesic(L, R, 0, win, 0, D, agg=True, strict=True)
+    y0, y1 = 400, 402
+    lo, hi = y0 - 18, y1 + 18
+    d_ref, e_ref = orc.asw_geodesic(L[lo:hi], R[lo:hi], 0, win, 0, D, agg=True)
+    rows = slice(y0 - lo, y1 - lo)
+    assert slice_err(e[:, y0:y1], e_ref[:, rows]) <= REL_TOL
+    assert (d[y0:y1] == d_ref[rows]).mean() >= AGREE
+    # the candidate remainder (d = 128) is summed by another kernel in the unsplit run than in rank 1's: equal costs up to
+    # rounding, so a pixel whose two best candidates are within 1e-6 of each other may flip
+    assert split_agreement(ctx, L, R, asw.ADAPTIVE_WEIGHT_GEODESIC, win, D, d) >= 0.9999
