@@ -290,15 +290,27 @@ static int gf_chunk_slices(size_t n) {
 
 // GuidedF_2 for one view, fast path.  keys must be initialised by the caller (allows d-range splits).
 // d_lo/d_hi: slice index range [d_lo, d_hi) evaluated (labels = min_d + index).
+// q' workspace budget of the streaming path (4 B per evaluation) and the slices one chunk of it holds
+static const size_t GFS_Q_BUDGET = (size_t)8 << 30;
+static int gfs_chunk_slices(int H, int W, int win, int span) {
+    const int QW = GFS_IW - 2 * (win - 1);
+    const size_t per_slice = (size_t)H * (cdiv(W, QW) * QW);
+    return (int)std::min<size_t>((size_t)span, std::max<size_t>(GFS_NS, GFS_Q_BUDGET / (per_slice * 4) / GFS_NS * GFS_NS));
+}
+static bool gfs_streaming(int H, int W, int win) {
+    return gfs_supported(H, W, win) && !getenv("ASW_GF_TILED") && !getenv("ASW_GF_GENERIC");
+}
+// disp_direct (optional): when the range is the method's whole range and one chunk holds it, the streaming path's WTA
+// pass writes the disparity map itself; *direct_done tells the caller (who then needs neither keys nor keys_to_disp).
 static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type,
                                     double eps, int win, int min_d, int num_d, int d_lo, int d_hi,
-                                    unsigned long long* keys, float* agg_dev) {
+                                    unsigned long long* keys, float* agg_dev, float* disp_direct = nullptr) {
     size_t n = (size_t)H * W;
     ViewGeom v = make_view(dL, dR, H, W, disp_type, min_d, num_d);
     Feat *fref, *ftgt;
     ASW_TRY(ws_get(ctx, WS_FEAT_REF, n, &fref));
     ASW_TRY(ws_get(ctx, WS_FEAT_TGT, (size_t)H * v.Wp, &ftgt));
-    const bool streaming = gfs_supported(H, W, win) && !getenv("ASW_GF_TILED") && !getenv("ASW_GF_GENERIC");
+    const bool streaming = gfs_streaming(H, W, win);
     GuidePrep gp;
     if (!streaming) {
         LAUNCH(ctx, "features", (k_features<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(v.ref, H, W, 0, 0, fref)));
@@ -337,18 +349,18 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
         GfsGeom g;
         g.H = H; g.W = W; g.Wp = v.Wp; g.Wq = cdiv(W, QW) * QW; g.x0_step = v.x0_step; g.D = 0; g.nbands = 2;
         size_t per_slice = (size_t)H * g.Wq;
-        size_t budget = (size_t)8 << 30;                   // q' workspace budget (4 B per evaluation)
         int span = d_hi - d_lo;
-        int chunk = (int)std::min<size_t>((size_t)span, std::max<size_t>(GFS_NS, budget / (per_slice * 4) / GFS_NS * GFS_NS));
+        int chunk = gfs_chunk_slices(H, W, win, span);
+        if (chunk < span) disp_direct = nullptr;
         float* qv;
         ASW_TRY(ws_get(ctx, WS_AB, per_slice * (size_t)chunk, &qv));
         for (int c0 = d_lo; c0 < d_hi; c0 += chunk) {
             int cn = (d_hi - c0 < chunk) ? d_hi - c0 : chunk;
             g.x0_base = v.x0_base + v.x0_step * c0;
             float* agg_c = agg_dev ? agg_dev + (size_t)(c0 - d_lo) * n : nullptr;
-            if (win == 9) ASW_TRY(gfs_launch<9>(ctx, rff, tff, gp.Gi, gmom, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
-            else if (win == 7) ASW_TRY(gfs_launch<7>(ctx, rff, tff, gp.Gi, gmom, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
-            else ASW_TRY(gfs_launch<5>(ctx, rff, tff, gp.Gi, gmom, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c));
+            if (win == 9) ASW_TRY(gfs_launch<9>(ctx, rff, tff, gp.Gi, gmom, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c, disp_direct));
+            else if (win == 7) ASW_TRY(gfs_launch<7>(ctx, rff, tff, gp.Gi, gmom, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c, disp_direct));
+            else ASW_TRY(gfs_launch<5>(ctx, rff, tff, gp.Gi, gmom, gp.mm, g, tp, qv, slice_mm + 2 * c0, aff + c0, cn, min_d + c0, keys, agg_c, disp_direct));
         }
         return ASW_OK;
     }
@@ -410,6 +422,8 @@ static asw_status dev_guidedf2(asw_ctx* ctx, const uint8_t* dL, const uint8_t* d
     size_t n = (size_t)H * W;
     unsigned long long* keys;
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
+    if (gfs_streaming(H, W, win) && gfs_chunk_slices(H, W, win, num_d) >= num_d)     // one WTA launch sees every candidate
+        return dev_guidedf2_keys(ctx, dL, dR, H, W, disp_type, eps, win, min_d, num_d, 0, num_d, keys, agg_dev, disp_dev);
     ASW_TRY(init_keys(ctx, keys, n));
     ASW_TRY(dev_guidedf2_keys(ctx, dL, dR, H, W, disp_type, eps, win, min_d, num_d, 0, num_d, keys, agg_dev));
     return keys_to_disp(ctx, keys, n, disp_dev);

@@ -532,10 +532,12 @@ __global__ void k_gfs_affine(const uint32_t* __restrict__ slice_mm, int D, float
 // One thread = 4 adjacent pixels; the D loads of a thread are independent (unrolled by 8).
 // AGG = false (the production path) has no store in the loop, and the loads of 8 slices are issued before the
 // first use: 128 bytes in flight per thread.
-template <bool AGG>
+// DIRECT: the launch covers the method's whole candidate range, so the winner is final: the disparity map is written
+// straight away (0 where every candidate is NaN / inf, as k_keys_to_disp) and no key buffer is touched.
+template <bool AGG, bool DIRECT>
 __global__ void __launch_bounds__(128)
 k_gfs_wta(const float* __restrict__ qv, const float2* __restrict__ aff, int D, int H, int W, int Wq, int d_label0,
-          unsigned long long* __restrict__ keys, float* __restrict__ agg) {
+          unsigned long long* __restrict__ keys, float* __restrict__ agg, float* __restrict__ disp) {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     if (x4 >= W) return;
     const size_t slice = (size_t)Wq;                         // q' is [H][D][Wq]: the D slices of a row are contiguous
@@ -564,7 +566,9 @@ k_gfs_wta(const float* __restrict__ qv, const float2* __restrict__ aff, int D, i
     }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        if (x4 + k < W && best[k] < __int_as_float(0x7f800000)) {
+        if (DIRECT) {
+            if (x4 + k < W) disp[(size_t)y * W + x4 + k] = best[k] < __int_as_float(0x7f800000) ? (float)(d_label0 + bd[k]) : 0.0f;
+        } else if (x4 + k < W && best[k] < __int_as_float(0x7f800000)) {
             unsigned long long* kp = keys + (size_t)y * W + x4 + k;
             *kp = min(*kp, wta_key(best[k], d_label0 + bd[k]));
         }
@@ -579,7 +583,7 @@ static inline bool gfs_supported(int H, int W, int win) {
 template <int K>
 static asw_status gfs_launch(asw_ctx* ctx, const FeatF* fref, const FeatF* ftgt, const float4* Gi, const GfsMoments* Gmom,
                              const int* guide_mm, GfsGeom g, const TadParams& tp, float* qv, uint32_t* slice_mm, float2* aff,
-                             int cn, int d_label0, unsigned long long* keys, float* agg) {
+                             int cn, int d_label0, unsigned long long* keys, float* agg, float* disp_direct) {
     constexpr int QW = GfsLayout<K>::QW;
     const size_t smem = GfsLayout<K>::bytes;
     cudaFuncSetAttribute(k_gfs_filter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -596,12 +600,15 @@ static asw_status gfs_launch(asw_ctx* ctx, const FeatF* fref, const FeatF* ftgt,
     LAUNCH(ctx, "gfs_filter", (k_gfs_filter<K><<<dim3(strips, groups, nb), 2 * GFS_THREADS, smem, ctx->stream>>>(
                                   fref, ftgt, Gi, Gmom, guide_mm, g, ts, tp.c0, qv, slice_mm)));
     LAUNCH(ctx, "gfs_affine", (k_gfs_affine<<<cdiv(cn, 128), 128, 0, ctx->stream>>>(slice_mm, cn, tp.c0, aff)));
-    if (agg) {
-        LAUNCH(ctx, "gfs_wta", (k_gfs_wta<true><<<dim3(cdiv(cdiv(g.W, 4), 128), g.H), 128, 0, ctx->stream>>>(
-                                   qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg)));
+    const dim3 wgrid(cdiv(cdiv(g.W, 4), 128), g.H);
+    if (disp_direct && agg) {
+        LAUNCH(ctx, "gfs_wta", (k_gfs_wta<true, true><<<wgrid, 128, 0, ctx->stream>>>(qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg, disp_direct)));
+    } else if (disp_direct) {
+        LAUNCH(ctx, "gfs_wta", (k_gfs_wta<false, true><<<wgrid, 128, 0, ctx->stream>>>(qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg, disp_direct)));
+    } else if (agg) {
+        LAUNCH(ctx, "gfs_wta", (k_gfs_wta<true, false><<<wgrid, 128, 0, ctx->stream>>>(qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg, nullptr)));
     } else {
-        LAUNCH(ctx, "gfs_wta", (k_gfs_wta<false><<<dim3(cdiv(cdiv(g.W, 4), 128), g.H), 128, 0, ctx->stream>>>(
-                                   qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg)));
+        LAUNCH(ctx, "gfs_wta", (k_gfs_wta<false, false><<<wgrid, 128, 0, ctx->stream>>>(qv, aff, cn, g.H, g.W, g.Wq, d_label0, keys, agg, nullptr)));
     }
     return ASW_OK;
 }
