@@ -249,6 +249,12 @@ __global__ void k_init_slice_mm(uint32_t* mm, int D) {
     if (i < D) { mm[2 * i] = 0xFFFFFFFFu; mm[2 * i + 1] = 0u; }
 }
 __global__ void k_init_mm_u8(int* mm) { mm[0] = 255; mm[1] = 0; }
+// both of the above in one launch (streaming guided path)
+__global__ void k_gfs_init(uint32_t* slice_mm, int D, int* guide_mm) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < D) { slice_mm[2 * i] = 0xFFFFFFFFu; slice_mm[2 * i + 1] = 0u; }
+    if (i == 0) { guide_mm[0] = 255; guide_mm[1] = 0; }
+}
 
 // guidance moments for a C-channel u8 guide: planes I (C), mean_I (C), den (C) + packed records for C == 3
 struct GuidePrep { float* I; float* mI; float* den; float4 *Gi, *Gm, *Gd; const int* mm; };
@@ -319,7 +325,7 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
     }
     uint32_t* slice_mm;
     ASW_TRY(ws_get(ctx, WS_SLICE_MM, (size_t)2 * num_d, &slice_mm));
-    LAUNCH(ctx, "init_slice_mm", (k_init_slice_mm<<<cdiv(num_d, 128), 128, 0, ctx->stream>>>(slice_mm, num_d)));
+    if (!streaming) LAUNCH(ctx, "init_slice_mm", (k_init_slice_mm<<<cdiv(num_d, 128), 128, 0, ctx->stream>>>(slice_mm, num_d)));
     TadParams tp = make_tad_params(0.4, 10, 50);                                     // A.cpp:2990
     if (streaming) {
         // streaming kernel (k_guided_stream.cuh): cost, both box levels and q' on chip; 4 B per evaluation to HBM
@@ -337,7 +343,7 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
         LAUNCH(ctx, "features", (k_features_f<<<dim3(cdiv(v.Wp, 128), H), 128, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, -1.0f, tff)));
         {
             // guidance: global min / max (cv::normalize is over all channels), then the fused moments kernel
-            LAUNCH(ctx, "init_mm", (k_init_mm_u8<<<1, 1, 0, ctx->stream>>>(gmm)));
+            LAUNCH(ctx, "gfs_init", (k_gfs_init<<<cdiv(num_d, 128), 128, 0, ctx->stream>>>(slice_mm, num_d, gmm)));
             LAUNCH(ctx, "minmax_u8", (k_minmax_u8<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(v.ref, n * 3, gmm)));
             const int strips_g = cdiv(W, GFS_GM_COLS - (win - 1));
             const int bands_g = std::max(1, std::min(cdiv(H, 2 * win), cdiv(4 * ctx->sm_count, strips_g)));
@@ -509,17 +515,27 @@ static asw_status dev_guidedf(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR
 static asw_status dev_lr_refine(asw_ctx* ctx, const uint8_t* dL, const float* dl, const float* dr, int H, int W, float tol,
                                 int win, double rate_s, double rate_r, uint8_t* valid, float* filled, float* out) {
     dim3 grid(cdiv(W, 128), H);
-    LAUNCH(ctx, "lr_check", (k_lr_check<<<grid, 128, 0, ctx->stream>>>(dl, dr, H, W, tol, valid)));
-    LAUNCH(ctx, "fill_invalid", (k_fill_invalid<<<grid, 128, 0, ctx->stream>>>(dl, valid, H, W, filled)));
     double alpha_r = (1.0 / rate_r) * (-1);
     float alpha_s = (float)((1.0 / rate_s) * (-1));
     const size_t ne = (size_t)win * win, n = (size_t)H * W;
     const int bt = (ne * (2 * 64 + 1)) * sizeof(float) <= 96 * 1024 ? 64 : (ne * (2 * 32 + 1)) * sizeof(float) <= 96 * 1024 ? 32 : 0;
-    if (bt && n < ((size_t)1 << 31) && !getenv("ASW_REFINE_DENSE")) {
+    const bool listed = bt && n < ((size_t)1 << 31) && !getenv("ASW_REFINE_DENSE");
+    if (listed && W <= 48 * 1024) {
         int* list;
         ASW_TRY(ws_get(ctx, WS_REFINE_LIST, n + 1, &list));               // list[0] = count
         ASW_CUDA(ctx, cudaMemsetAsync(list, 0, sizeof(int), ctx->stream));
-        LAUNCH(ctx, "refine_compact", (k_refine_compact<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(filled, valid, (int)n, out, list + 1, list)));
+        LAUNCH(ctx, "lr_fill_compact", (k_lr_fill_compact<<<H, 256, W, ctx->stream>>>(dl, dr, H, W, tol, valid, filled, out, list + 1, list)));
+    } else {
+        LAUNCH(ctx, "lr_check", (k_lr_check<<<grid, 128, 0, ctx->stream>>>(dl, dr, H, W, tol, valid)));
+        LAUNCH(ctx, "fill_invalid", (k_fill_invalid<<<grid, 128, 0, ctx->stream>>>(dl, valid, H, W, filled)));
+    }
+    if (listed) {
+        int* list;
+        ASW_TRY(ws_get(ctx, WS_REFINE_LIST, n + 1, &list));               // list[0] = count
+        if (W > 48 * 1024) {
+            ASW_CUDA(ctx, cudaMemsetAsync(list, 0, sizeof(int), ctx->stream));
+            LAUNCH(ctx, "refine_compact", (k_refine_compact<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(filled, valid, (int)n, out, list + 1, list)));
+        }
         const size_t smem = ne * (2 * bt + 1) * sizeof(float);
         const unsigned blocks = (unsigned)std::min<size_t>((n + bt - 1) / bt, (size_t)ctx->sm_count * 16);
         if (bt == 64) {

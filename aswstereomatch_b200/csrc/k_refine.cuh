@@ -177,3 +177,34 @@ k_wmedian_refine_list(const uint8_t* __restrict__ img, const float* __restrict__
         out[p] = result;
     }
 }
+
+// LR check + fill + compaction of one image row per CTA (the three steps of k_lr_check, k_fill_invalid and
+// k_refine_compact in one launch: the row's mask stays in shared memory between them).
+__global__ void __launch_bounds__(256)
+k_lr_fill_compact(const float* __restrict__ dl, const float* __restrict__ dr, int H, int W, float tol,
+                  uint8_t* __restrict__ valid, float* __restrict__ filled, float* __restrict__ out,
+                  int* __restrict__ list, int* __restrict__ count) {
+    extern __shared__ uint8_t sm_valid[];
+    const int y = blockIdx.x;
+    const float* row = dl + (size_t)y * W;
+    const float* rrow = dr + (size_t)y * W;
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        const float d = row[x];
+        const uint8_t v = fabsf(d - rrow[max(0, x - (int)d)]) <= tol ? 1 : 0;
+        sm_valid[x] = v;
+        valid[(size_t)y * W + x] = v;
+    }
+    __syncthreads();
+    for (int x = threadIdx.x; x < W; x += blockDim.x) {
+        const size_t p = (size_t)y * W + x;
+        float r = row[x];
+        if (sm_valid[x]) { filled[p] = r; out[p] = r; continue; }
+        int xl = x - 1; while (xl >= 0 && !sm_valid[xl]) xl--;
+        int xr = x + 1; while (xr < W && !sm_valid[xr]) xr++;
+        if (xl >= 0 && xr < W) r = fminf(row[xl], row[xr]);
+        else if (xl >= 0) r = row[xl];
+        else if (xr < W) r = row[xr];
+        filled[p] = r;
+        list[atomicAdd(count, 1)] = (int)p;
+    }
+}
