@@ -141,6 +141,7 @@ __global__ void k_grid_pass(double* __restrict__ S, int* __restrict__ C, GridDim
 //   xr[kx]   = first pixel column whose cvRound(x / sS) is kx, xr[X + kx] = how many (keys are monotone, so the
 //              pixels of a spatial key are one contiguous run); yr likewise for rows
 // so neither kernel executes a double-precision division per pixel.
+#define GRID_CONV_MAX 24      // cells of one CTA iteration / 128 threads, upper bound (host-checked)
 struct GridTables {
     const int* klut;             // [256]
     const int* xr;               // [2 * X]
@@ -158,7 +159,7 @@ k_grid_build_wz(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, 
     const int X = g.nx + 1, Y = g.ny + 1, Z = g.nz + 1, Wd = g.nw + 1, pitch = Wd | 1, cells = Z * Wd, XY = X * Y;
     double* ss = sm_grid;                                   // [PL][Z][pitch]
     int* cc = (int*)(ss + (size_t)PL * Z * pitch);          // [PL][Z][pitch]
-    int* si = cc + (size_t)PL * Z * pitch;                  // [PL][Z][pitch] integer sums while splatting
+    int* si = (int*)ss;                                     // integer sums while splatting, aliased onto the double sums
     __shared__ int klut[256];
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += 128) klut[i] = tb.klut[i];
@@ -195,7 +196,14 @@ k_grid_build_wz(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, 
             }
         }
         __syncthreads();
-        for (int i = tid; i < np * Z * pitch; i += 128) ss[i] = (double)si[i];
+        {   // int -> double in place (different element sizes): through registers, with a barrier in between
+            int tmp[GRID_CONV_MAX];
+#pragma unroll
+            for (int j = 0; j < GRID_CONV_MAX; j++) { const int i = tid + j * 128; if (i < np * Z * pitch) tmp[j] = si[i]; }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < GRID_CONV_MAX; j++) { const int i = tid + j * 128; if (i < np * Z * pitch) ss[i] = (double)tmp[j]; }
+        }
         __syncthreads();
         for (int l = tid; l < np * Z; l += 128)             // w pass: line = (plane, z), unit stride
             grid_pass_line<int, false>(ss + l * pitch, cc + l * pitch, 1, g.nw);
@@ -332,10 +340,14 @@ static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint
         // splat + w + z fused through shared memory when a few (z, w) planes fit; otherwise zero-fill, global splat
         // and one launch per axis
         const int Zd = g.nz + 1, Wdd = g.nw + 1;
-        const size_t plane_bytes = (size_t)Zd * (Wdd | 1) * 16;       // double sum + int count + int splat sum
+        const size_t plane_bytes = (size_t)Zd * (Wdd | 1) * 12;       // double sum (the int splat sum aliases it) + int count
         int first_axis = 0;
-        if (plane_bytes <= 96 * 1024 && !getenv("ASW_GRID_UNFUSED")) {
-            int PL = std::max(1, std::min(128 / std::max(Zd, Wdd), (int)((96 * 1024) / plane_bytes)));
+        // planes per CTA iteration: one line per thread in the w / z passes, and the in-place int -> double conversion
+        // holds a CTA iteration's cells in GRID_CONV_MAX registers per thread
+        const int PL_max = std::min(std::min(128 / std::max(Zd, Wdd), (int)((96 * 1024) / plane_bytes)),
+                                    (int)((size_t)GRID_CONV_MAX * 128 / ((size_t)Zd * (Wdd | 1))));
+        if (PL_max >= 1 && !getenv("ASW_GRID_UNFUSED")) {
+            int PL = PL_max;
             size_t smem = plane_bytes * PL + 16;
             int n_planes = (g.nx + 1) * (g.ny + 1) * nb;
             cudaFuncSetAttribute(k_grid_build_wz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
