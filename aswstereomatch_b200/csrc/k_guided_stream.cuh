@@ -33,34 +33,13 @@
 #define GFS_NS 4
 #define GFS_THREADS 256
 
-// float feature record: gradients as exact-integer floats (|g| <= 4080), colour bytes last so that (g0, g1) sits in
-// an aligned register pair.  The target plane stores NEGATED gradients: |ga - gb| = |ga + (-gb)| is one FADD2 + FADD.
-
-__global__ void k_feat_to_float(const Feat* __restrict__ in, size_t n, float sign, FeatF* __restrict__ out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Feat f = in[i];
-    FeatF o;
-    o.g0 = sign * (float)(int)(int16_t)(f.g01 & 0xFFFF);
-    o.g1 = sign * (float)(int)(int16_t)(f.g01 >> 16);
-    o.g2 = sign * (float)(int)(int16_t)(f.g2 & 0xFFFF);
-    o.bgr = f.bgr;
-    out[i] = o;
-}
+// float feature record (FeatF, k_prep.cuh): gradients as exact-integer floats (|g| <= 4080), colour bytes last so that
+// (g0, g1) sits in an aligned register pair.  The target plane stores NEGATED gradients: |ga - gb| = |ga + (-gb)| is one
+// FADD2 + FADD.  k_features_f writes the records straight from the images.
 
 // guidance record for the (a,b) epilogue, 32 bytes per pixel: {-mean_I0, -mean_I1, -mean_I2, rd2, rd0, rd1, -, -} with
 // rd_c = (1/K^2) / (var_c + eps): the level-2 box normalisation is folded into a.
 struct __align__(16) GfsMoments { float4 nm; float4 rd; };
-__global__ void k_gfs_pack_guide(const float4* __restrict__ Gm, const float4* __restrict__ Gd, size_t n, float inv,
-                                 GfsMoments* __restrict__ out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 m = Gm[i], d = Gd[i];
-    GfsMoments r;
-    r.nm = make_float4(-m.x, -m.y, -m.z, __fdiv_rn(inv, d.z));
-    r.rd = make_float4(__fdiv_rn(inv, d.x), __fdiv_rn(inv, d.y), 0.0f, 0.0f);
-    out[i] = r;
-}
 
 // Fused guidance preparation of the streaming path (replaces guide_normalize + box_f32 over 6 planes + guide_finish +
 // gfs_pack_guide): I = normalize(guide) (A.cpp:2774), mean_I = box(I), corr_II = box(I*I) (A.cpp:2778, 2796),
