@@ -208,11 +208,14 @@ k_blo1_aggregate(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpa
 #define BLO2_PITCH 132
 #define BLO2_THREADS 256
 
-template <int WIN>
+// NORM = true computes the normalisers instead: the same sums with c = 1 over the slice [di_lo, di_lo + 1) (the host
+// passes the LAST disparity, A.cpp:2588), written as box means into the per-pixel pair plane Nk_out = {N at the pixel's
+// lower level, N at the next level} (7 MB at 1280x720 instead of nl full-resolution planes).
+template <int WIN, bool NORM>
 __global__ void __launch_bounds__(BLO2_THREADS, 2)
 k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, const float* __restrict__ cost,
-            const float* __restrict__ Nk, BloGeom g, int dch, int d_label0, unsigned long long* __restrict__ keys,
-            float* __restrict__ agg) {
+            const float* __restrict__ Nk, float* __restrict__ Nk_out, BloGeom g, int dch, int d_label0,
+            unsigned long long* __restrict__ keys, float* __restrict__ agg) {
     constexpr int TH = WIN + 1, SW = BLO2_COLS - (WIN - 1), NPIX = TH * SW, h = WIN / 2, PITCH = BLO2_PITCH;
     extern __shared__ float sm_blo2[];
     // running sums of the two blocks, each preceded by a row of zeros: [Z][U0: WIN rows][Z][U1: WIN rows]
@@ -281,7 +284,7 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
             int l = lg[(size_t)sy * g.W + sx], rr = rpad[(size_t)sy * g.Wp + xoff + sx];
             a[i] = (float)(l * rr);
             b[i] = (float)(l + rr);
-            c[i] = __ldg(&cd[(size_t)sy * g.W + sx]);
+            c[i] = NORM ? 1.0f : __ldg(&cd[(size_t)sy * g.W + sx]);
         }
         for (int li = 0; li < g.nl; li++) {
             if (!((need[li >> 5] >> (li & 31)) & 1u)) continue;   // block-uniform
@@ -291,7 +294,7 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
             const int e1 = lstart[li], e0 = li > 0 ? lstart[li - 1] : e1, e2 = lstart[li + 1];   // level li-1 | level li
             float nk_pre = 0.0f;
             const int rt = BLO2_THREADS - 1 - tid;                 // consumers are taken by the highest threads first:
-            if (e0 + rt < e2) {                                    // the scan keeps the lowest 4 * TH threads busy
+            if (!NORM && e0 + rt < e2) {                           // the scan keeps the lowest 4 * TH threads busy
                 const uint32_t e = list[e0 + rt];
                 const int pix = e & 0xFFFF, o = pix / SW, xo = pix - o * SW;
                 nk_pre = __ldg(&Nk[((size_t)(y0 + o) * g.W + (x0 + xo)) * 2 + (e0 + rt < e1 ? 1 : 0)]);
@@ -339,6 +342,7 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
                 if (xo > 0) { sum -= q[xo - 1]; s = (xo - 1) >> 5; }
                 for (; s < segr; s++) sum += q[s * 32 + 31];
                 const size_t p = (size_t)(y0 + o) * g.W + (x0 + xo);
+                if (NORM) { Nk_out[p * 2 + (role_hi ? 1 : 0)] = sum * inv; continue; }   // N_k = box(M_{D-1})  (A.cpp:2588)
                 const float nk = t < e0 + BLO2_THREADS ? nk_pre : __ldg(&Nk[p * 2 + (role_hi ? 1 : 0)]);
                 const float jb = __fdiv_rn(sum * inv, nk);                        // A.cpp:2594
                 float cst;
@@ -357,7 +361,7 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
         }
         __syncthreads();
     }
-    for (int p = tid; p < NPIX; p += BLO2_THREADS) {
+    for (int p = tid; !NORM && p < NPIX; p += BLO2_THREADS) {
         int o = p / SW, xo = p - o * SW, y = y0 + o, x = x0 + xo;
         if (x < g.W && y < g.H && bestk[p] != WTA_KEY_EMPTY) {
             // back to the library's key format (orderable double cost | d)
@@ -371,17 +375,24 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
 }
 
 template <int WIN>
-static asw_status launch_blo1_agg2(asw_ctx* ctx, const uint8_t* gref, const uint8_t* gtgt, const float* cost, const float* Nk,
+static asw_status launch_blo1_agg2(asw_ctx* ctx, const uint8_t* gref, const uint8_t* gtgt, const float* cost, float* Nk,
                                    const BloGeom& g, int min_d, unsigned long long* keys, float* agg_dev) {
     constexpr int TH = WIN + 1, SW = BLO2_COLS - (WIN - 1), NPIX = TH * SW;
     size_t smem = ((size_t)(2 * WIN + 2) * BLO2_PITCH + (size_t)TH * BLO2_PITCH + NPIX) * sizeof(float) +
                   (size_t)NPIX * sizeof(uint32_t) + (size_t)NPIX * sizeof(unsigned long long);
-    cudaFuncSetAttribute(k_blo1_agg2<WIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_blo1_agg2<WIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_blo1_agg2<WIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int dch = 8;
     const char* e = getenv("ASW_BLO_DCH");
     if (e && atoi(e) > 0) dch = atoi(e);
+    {   // normalisers: the same kernel on the last disparity with unit costs
+        BloGeom gn = g;
+        gn.di_lo = g.D - 1; gn.di_hi = g.D;
+        dim3 grid(cdiv(g.W, SW), cdiv(g.H, TH), 1);
+        LAUNCH(ctx, "blo1_norm", (k_blo1_agg2<WIN, true><<<grid, BLO2_THREADS, smem, ctx->stream>>>(gref, gtgt, cost, Nk, Nk, gn, 1, min_d, keys, nullptr)));
+    }
     dim3 grid(cdiv(g.W, SW), cdiv(g.H, TH), cdiv(g.di_hi - g.di_lo, dch));
-    LAUNCH(ctx, "blo1_aggregate", (k_blo1_agg2<WIN><<<grid, BLO2_THREADS, smem, ctx->stream>>>(gref, gtgt, cost, Nk, g, dch, min_d, keys, agg_dev)));
+    LAUNCH(ctx, "blo1_aggregate", (k_blo1_agg2<WIN, false><<<grid, BLO2_THREADS, smem, ctx->stream>>>(gref, gtgt, cost, Nk, nullptr, g, dch, min_d, keys, agg_dev)));
     return ASW_OK;
 }
 
@@ -415,12 +426,14 @@ static asw_status dev_blo1_range(asw_ctx* ctx, const uint8_t* dL, const uint8_t*
     cudaFuncSetAttribute(k_blo1_norm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_n);
     cudaFuncSetAttribute(k_blo1_aggregate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a);
     dim3 tiles(cdiv(W, BLO_TW), cdiv(H, BLO_TH));
-    LAUNCH(ctx, "blo1_norm", (k_blo1_norm<<<dim3(tiles.x, tiles.y, g.nl), BLO_THREADS, smem_n, ctx->stream>>>(gref, gtgt, g, Nk)));
     unsigned long long* keys;
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
     ASW_TRY(init_keys(ctx, keys, n));
     const char* tiled = getenv("ASW_BLO_TILED");
     const bool generic = tiled && atoi(tiled) == 1;
+    const bool templated = !generic && (win == 5 || win == 7 || win == 9 || win == 15 || win == 25 || win == 35);
+    if (!templated)   // exact integer normalisers for the tiled fallback (the register-resident kernel computes its own)
+        LAUNCH(ctx, "blo1_norm", (k_blo1_norm<<<dim3(tiles.x, tiles.y, g.nl), BLO_THREADS, smem_n, ctx->stream>>>(gref, gtgt, g, Nk)));
     switch (generic ? 0 : win) {
         case 5: ASW_TRY(launch_blo1_agg2<5>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
         case 7: ASW_TRY(launch_blo1_agg2<7>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
