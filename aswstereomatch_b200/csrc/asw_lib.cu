@@ -468,7 +468,17 @@ static asw_status dev_cost_sad_box(asw_ctx* ctx, const uint8_t* dL, const uint8_
         int bands = std::max(1, std::min(cdiv(H, 4 * win), cdiv(4 * ctx->sm_count, cdiv(W, SADBOX_COLS - (win - 1)) * num_d)));
         int band_rows = cdiv(cdiv(H, bands), 4) * 4;
         dim3 grid(cdiv(W, SADBOX_COLS - (win - 1)), cdiv(H, band_rows), num_d);
-        LAUNCH(ctx, "sad_box", (k_sad_box_u8<4><<<grid, SADBOX_COLS, 0, ctx->stream>>>(gref, gtgt, H, W, v.Wp, v.x0_base, v.x0_step, win, band_rows, vol)));
+#define SAD_BOX_LAUNCH(WT) LAUNCH(ctx, "sad_box", (k_sad_box_u8<4, WT><<<grid, SADBOX_COLS, 0, ctx->stream>>>(gref, gtgt, H, W, v.Wp, v.x0_base, v.x0_step, win, band_rows, vol)))
+        switch (win) {
+            case 5: SAD_BOX_LAUNCH(5); break;
+            case 7: SAD_BOX_LAUNCH(7); break;
+            case 9: SAD_BOX_LAUNCH(9); break;
+            case 15: SAD_BOX_LAUNCH(15); break;
+            case 25: SAD_BOX_LAUNCH(25); break;
+            case 35: SAD_BOX_LAUNCH(35); break;
+            default: SAD_BOX_LAUNCH(0); break;
+        }
+#undef SAD_BOX_LAUNCH
     } else {
         float* ad;
         ASW_TRY(ws_get(ctx, WS_VOL1, n * num_d, &ad));

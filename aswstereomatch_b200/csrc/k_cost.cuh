@@ -101,11 +101,14 @@ __global__ void k_gray_absdiff(const uint8_t* __restrict__ ref, const uint8_t* _
 // down a band of rows keeping the vertical window sum in a register (one row in, one row out); the
 // horizontal sums run over shared memory, RB rows per barrier.  Nothing but the result reaches HBM.
 #define SADBOX_COLS 256
-template <int RB>
+#define SADBOX_PITCH 264         // row pitch of the staged vertical sums (8 pad columns for the last quad's loads)
+// WIN_T > 0: window side as a template constant (quad path, fully static indexing); WIN_T = 0: any window
+template <int RB, int WIN_T>
 __global__ void __launch_bounds__(SADBOX_COLS)
 k_sad_box_u8(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, int H, int W, int Wp, int x0_base,
-             int x0_step, int win, int band_rows, float* __restrict__ vol) {
-    __shared__ int vs[2][RB][SADBOX_COLS];
+             int x0_step, int win_rt, int band_rows, float* __restrict__ vol) {
+    const int win = WIN_T > 0 ? WIN_T : win_rt;
+    __shared__ __align__(16) int vs[2][RB][SADBOX_PITCH];
     const int h = win / 2, SW = SADBOX_COLS - (win - 1);
     const int cx = threadIdx.x, x0 = blockIdx.x * SW, di = blockIdx.z;
     const int sx = border_idx(x0 - h + cx, W, 1);
@@ -119,8 +122,13 @@ k_sad_box_u8(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, i
     int s = 0;
     for (int j = -h; j < h; j++) s += ad(y_begin + j);
     const double scale = 1.0 / ((double)win * win);
-    const bool writer = cx < SW && x0 + cx < W;
-    float* out = vol + (size_t)di * H * W + x0 + cx;
+    // horizontal phase: one thread per (row of the batch, quad of 4 adjacent output columns): the 4 + win - 1 vertical
+    // sums it needs arrive as aligned 16-byte loads, the 4 window sums slide over them (templated windows; any other
+    // window takes one output per thread)
+    constexpr bool quads = WIN_T > 0;
+    const int nquad = (SW + 3) / 4;
+    const int hr = cx / nquad, hq = cx - hr * nquad;
+    float* plane = vol + (size_t)di * H * W;
     int buf = 0;
     for (int y = y_begin; y < y_end; y += RB) {
 #pragma unroll
@@ -130,13 +138,30 @@ k_sad_box_u8(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, i
             s -= ad(y + r - h);
         }
         __syncthreads();
-        if (writer) {
+        if (quads) {
+            if (hr < RB && y + hr < y_end) {
+                constexpr int NV = ((WIN_T + 3 + 3) / 4) * 4;             // 4 + WIN - 1 values, rounded up to whole int4
+                int v[NV > 0 ? NV : 4];
+                const int4* src = (const int4*)&vs[buf][hr][4 * hq];
+#pragma unroll
+                for (int m = 0; m < NV / 4; m++) { const int4 t = src[m]; v[4 * m] = t.x; v[4 * m + 1] = t.y; v[4 * m + 2] = t.z; v[4 * m + 3] = t.w; }
+                int acc = 0;
+#pragma unroll
+                for (int j = 0; j < WIN_T; j++) acc += v[j];
+                float* out = plane + (size_t)(y + hr) * W + x0 + 4 * hq;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    if (i > 0) acc += v[i - 1 + WIN_T] - v[i - 1];
+                    if (4 * hq + i < SW && x0 + 4 * hq + i < W) out[i] = (float)((double)acc * scale);
+                }
+            }
+        } else if (cx < SW && x0 + cx < W) {
 #pragma unroll
             for (int r = 0; r < RB; r++) {
                 if (y + r < y_end) {
                     int acc = 0;
                     for (int j = 0; j < win; j++) acc += vs[buf][r][cx + j];
-                    out[(size_t)(y + r) * W] = (float)((double)acc * scale);
+                    plane[(size_t)(y + r) * W + x0 + cx] = (float)((double)acc * scale);
                 }
             }
         }
