@@ -82,6 +82,107 @@ k_wm_aggregate(const uint32_t* __restrict__ lpk, const uint32_t* __restrict__ rp
     atomicMin(&keys[p], wta_key(result, d_label0 + off));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path.  The reference itself precomputes one colour-weight window per pixel of either image
+// (computeColorWeightGau, A.cpp:3139-3205) and re-uses it for every candidate; so do we:
+//   k_wm_weights    W[t][y][x] = exp(-L1(I(neighbour t), I(y,x)) / rateR) for both images (the right one on its padded
+//                   width, REFLECT inside the padded image as A.cpp:3156), one double-precision exp per entry, once
+//   k_wm_aggregate2 per (d, y, x): keys (value bits << 32 | window index) of the win^2 costs go into a binary min-heap
+//                   in shared memory (thread-private column: bank = thread, no conflicts) next to their weights (wL * spatial) * wR,
+//                   elements are popped in exactly the reference's stable ascending order,
+//                   partial sums in double, stop at the first element that crosses half the total (A.cpp:3276-3304).
+// O(n + k log n) per evaluation instead of O(k n) extraction scans and 3 exps per element per candidate.
+// ---------------------------------------------------------------------------------------------
+// img: packed BGRx [H][W]; out: [n][H][Wout]; the centre of output column xo is image column reflect(xo - pad, W),
+// neighbour columns reflect inside the padded width Wout first (pad = 0, Wout = W for the left image)
+__global__ void k_wm_weights(const uint32_t* __restrict__ img, int H, int W, int Wout, int pad, int win, double alpha_r,
+                             float* __restrict__ out) {
+    const int xo = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, t = blockIdx.z;
+    if (xo >= Wout) return;
+    const int h = win / 2, wy = t / win, wx = t - wy * win;
+    const uint32_t c = img[(size_t)y * W + border_idx(xo - pad, W, 0)];
+    const int sy = border_idx(y - h + wy, H, 0);
+    const int xb = border_idx(xo - h + wx, Wout, 0);
+    const uint32_t q = img[(size_t)sy * W + border_idx(xb - pad, W, 0)];
+    float d0 = (float)abs((int)(q & 0xFF) - (int)(c & 0xFF)), d1 = (float)abs((int)((q >> 8) & 0xFF) - (int)((c >> 8) & 0xFF));
+    float d2 = (float)abs((int)((q >> 16) & 0xFF) - (int)((c >> 16) & 0xFF));
+    out[((size_t)t * H + y) * Wout + xo] = (float)exp((double)(float)fma((double)__fadd_rn(d0, d1), alpha_r, __dmul_rn((double)d2, alpha_r)));
+}
+
+template <int BT>
+__global__ void __launch_bounds__(BT)
+k_wm_aggregate2(const float* __restrict__ WL, const float* __restrict__ WR, const float* __restrict__ cost, WmGeom g,
+                float alpha_s, int d_label0, unsigned long long* __restrict__ keys, float* __restrict__ agg) {
+    extern __shared__ unsigned long long sm_wm2[];
+    const int win = g.win, h = g.h, n = win * win, W = g.W, H = g.H, Wr = W + g.max_off;
+    unsigned long long* heap = sm_wm2 + threadIdx.x;         // heap[i * BT]: thread-private column
+    float* wts = (float*)(sm_wm2 + (size_t)n * BT) + threadIdx.x;   // wts[t * BT]: the window's weights, thread-private column
+    float* wsp = (float*)(sm_wm2 + (size_t)n * BT) + (size_t)n * BT;   // [n] spatial weights
+    for (int e = threadIdx.x; e < n; e += BT) {
+        int wy = e / win, wx = e - wy * win;
+        float dist2 = __fadd_rn((float)((wx - h) * (wx - h)), (float)((wy - h) * (wy - h)));
+        wsp[e] = (float)exp((double)__fmul_rn(dist2, alpha_s));                  // A.cpp:3219-3225
+    }
+    __syncthreads();
+    const int x = blockIdx.x * BT + threadIdx.x, y = blockIdx.y, off = blockIdx.z;
+    if (x >= W) return;
+    const size_t p = (size_t)y * W + x;
+    const int xr = x - off + g.D - 1;                        // weightWinsR[y][x - offset + numDisparity - 1]
+    const float* wl = WL + p;                                // + t * H * W
+    const float* wr = WR + (size_t)y * Wr + xr;              // + t * H * Wr
+    const size_t sl = (size_t)H * W, sr = (size_t)H * Wr;
+    const float* cs = cost + (size_t)off * sl;
+    double total = 0;
+    for (int t0 = 0; t0 < n; t0 += 8) {                      // 8 window elements per round: their 24 loads issued together
+        float a[8], b[8], v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int t = min(t0 + u, n - 1), wy = t / win, wx = t - wy * win;
+            a[u] = __ldg(&wl[t * sl]);
+            b[u] = __ldg(&wr[t * sr]);
+            v[u] = cs[(size_t)border_idx(y - h + wy, H, 0) * W + border_idx(x - h + wx, W, 0)];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int t = t0 + u;
+            if (t < n) {
+                const float w = __fmul_rn(__fmul_rn(a[u], wsp[t]), b[u]);                          // wL.mul(dist).mul(wR)
+                wts[t * BT] = w;
+                heap[t * BT] = ((unsigned long long)__float_as_uint(v[u]) << 32) | (unsigned)t;   // costs are >= 0: bit order = value order
+                total += (double)w;                                                                // cv::sum, double, window order
+            }
+        }
+    }
+    // heapify (min-heap): sift down from the last parent
+    auto sift = [&](int i, int len, unsigned long long key) {
+        for (;;) {
+            int c = 2 * i + 1;
+            if (c >= len) break;
+            unsigned long long kc = heap[c * BT];
+            if (c + 1 < len) { unsigned long long k2 = heap[(c + 1) * BT]; if (k2 < kc) { kc = k2; c++; } }
+            if (kc >= key) break;
+            heap[i * BT] = kc;
+            i = c;
+        }
+        heap[i * BT] = key;
+    };
+    for (int i = n / 2 - 1; i >= 0; i--) sift(i, n, heap[i * BT]);
+    const double half = total / 2;
+    double partial = 0;
+    float prev_v = 0.0f, result = 0.0f;
+    bool first = true;
+    for (int len = n; len > 0; len--) {
+        const unsigned long long top = heap[0];
+        const float bv = __uint_as_float((unsigned)(top >> 32));
+        partial += (double)wts[(int)(top & 0xFFFFFFFFu) * BT];
+        if (partial > half) { result = first ? bv : prev_v; break; }
+        first = false; prev_v = bv;
+        if (len > 1) sift(0, len - 1, heap[(len - 1) * BT]);
+    }
+    if (agg) agg[(size_t)off * sl + p] = result;
+    atomicMin(&keys[p], wta_key(result, d_label0 + off));
+}
+
 static asw_status dev_weighted_median(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int win,
                                       double rate_s, double rate_r, int min_d, int num_d, float* disp_dev, float* agg_dev) {
     if (win > WM_MAXWIN)
@@ -112,6 +213,21 @@ static asw_status dev_weighted_median(asw_ctx* ctx, const uint8_t* dL, const uin
     g.H = H; g.W = W; g.win = win; g.h = win / 2; g.D = num_d; g.max_off = v.max_off;
     double alpha_r = (1.0 / rate_r) * (-1);
     float alpha_s = (float)((1.0 / rate_s) * (-1));
+    const int nn = win * win, Wr = W + v.max_off;
+    const size_t planes = (size_t)nn * H * ((size_t)W + Wr) * sizeof(float);
+    if (!getenv("ASW_WM_SCAN") && planes <= ((size_t)6 << 30)) {
+        float *WLp, *WRp;
+        ASW_TRY(ws_get(ctx, WS_GEO_L, (size_t)nn * H * W, &WLp));
+        ASW_TRY(ws_get(ctx, WS_GEO_R, (size_t)nn * H * Wr, &WRp));
+        LAUNCH(ctx, "wm_weights", (k_wm_weights<<<dim3(cdiv(W, 128), H, nn), 128, 0, ctx->stream>>>(pl, H, W, W, 0, win, alpha_r, WLp)));
+        LAUNCH(ctx, "wm_weights", (k_wm_weights<<<dim3(cdiv(Wr, 128), H, nn), 128, 0, ctx->stream>>>(pr, H, W, Wr, v.max_off, win, alpha_r, WRp)));
+        constexpr int BT = 32;
+        const size_t smem = (size_t)nn * BT * (sizeof(unsigned long long) + sizeof(float)) + (size_t)nn * sizeof(float);
+        cudaFuncSetAttribute(k_wm_aggregate2<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        LAUNCH(ctx, "wm_aggregate", (k_wm_aggregate2<BT><<<dim3(cdiv(W, BT), H, num_d), BT, smem, ctx->stream>>>(
+                                        WLp, WRp, cost, g, alpha_s, min_d, keys, agg_dev)));
+        return keys_to_disp(ctx, keys, n, disp_dev);
+    }
     LAUNCH(ctx, "wm_aggregate", (k_wm_aggregate<<<dim3(cdiv(W, 64), H, num_d), 64, 0, ctx->stream>>>(
                                     pl, pr, cost, g, alpha_r, alpha_s, min_d, keys, agg_dev)));
     return keys_to_disp(ctx, keys, n, disp_dev);
