@@ -173,21 +173,25 @@ k_geo_aggregate_q(const float* __restrict__ dref, const float* __restrict__ dtgt
     double num[GEO_Q], den[GEO_Q];
 #pragma unroll
     for (int q = 0; q < GEO_Q; q++) { num[q] = 0; den[q] = 0; }
+    const float* dl_p = dref + p;                                   // tap-major planes: + tap * n
     for (int j = 0; j < win; j++) {
-        int ny = clampi(y - h + j, 0, H - 1);
+        const int ny = clampi(y - h + j, 0, H - 1);
+        const uint32_t* prow = pref + (size_t)ny * W;
+        const uint32_t* trow = ptgt + (size_t)ny * W;
         float fn[GEO_Q], fd[GEO_Q];
 #pragma unroll
         for (int q = 0; q < GEO_Q; q++) { fn[q] = 0; fd[q] = 0; }
+#pragma unroll 5
         for (int i = 0; i < win; i++) {
-            int nx = clampi(x - h + i, 0, W - 1);
-            size_t tap = (size_t)(j * win + i) * n;
-            float dl = dref[tap + p];
-            uint32_t cr = pref[(size_t)ny * W + nx];
+            const int nx = clampi(x - h + i, 0, W - 1);
+            const size_t tap = (size_t)(j * win + i) * n;
+            const float dl = __ldg(dl_p + tap);
+            const uint32_t cr = __ldg(prow + nx);
 #pragma unroll
             for (int q = 0; q < GEO_Q; q++) {
-                int nxs = g.sign > 0 ? max(0, nx - dq[q]) : min(nx + dq[q], W - 1);
-                float cd = (float)__vsadu4(cr, ptgt[(size_t)ny * W + nxs]);     // getColorDist (A.cpp:1321-1326)
-                float t = __fmul_rn(dl, dtgt[tap + pt[q]]);                     // float * float (A.cpp:1488-1489)
+                const int nxs = g.sign > 0 ? max(0, nx - dq[q]) : min(nx + dq[q], W - 1);
+                const float cd = (float)__vsadu4(cr, __ldg(trow + nxs));        // getColorDist (A.cpp:1321-1326)
+                const float t = __fmul_rn(dl, __ldg(dtgt + tap + pt[q]));       // float * float (A.cpp:1488-1489)
                 fn[q] = __fadd_rn(fn[q], __fmul_rn(t, cd));
                 fd[q] = __fadd_rn(fd[q], t);
             }
