@@ -43,8 +43,10 @@ __global__ void k_grid_splat(const uint8_t* __restrict__ lg, const uint8_t* __re
 
 // one recursive in-place 5-tap pass along a strided line of n+1 cells, n >= 3 (A.cpp:1936-2183).  The two edge
 // rules at either end are peeled, so the interior loop is branch-free; expressions keep the reference's order.
-template <typename ST, bool BATCH>
-__device__ __forceinline__ void grid_pass_line(double* __restrict__ s, int* __restrict__ c, ST stride, int n) {
+// CT: storage type of the counts (int in shared memory; int or uint16_t in HBM: a count never exceeds the pixels of one
+// spatial cell, and 10-byte instead of 12-byte cells are 17 % less traffic for the HBM-bound passes).
+template <typename ST, bool BATCH, typename CT>
+__device__ __forceinline__ void grid_pass_line(double* __restrict__ s, CT* __restrict__ c, ST stride, int n) {
     // rolling registers: m2, m1 = already-updated v[i-2], v[i-1]; s0 = v[i]; p1, p2 = original v[i+1], v[i+2]
     double sm2, sm1, s0 = s[0], sp1 = s[stride], sp2 = s[2 * stride], sp3 = s[3 * stride];
     double cm2, cm1, c0 = (double)c[0], cp1 = (double)c[stride], cp2 = (double)c[2 * stride], cp3 = (double)c[3 * stride];
@@ -53,7 +55,7 @@ __device__ __forceinline__ void grid_pass_line(double* __restrict__ s, int* __re
 #define GRID_STORE_SHIFT(i)                                                   \
     nci = (int)nc; /* pair<double,double> -> pair<double,int>: truncation */ \
     s[(ST)(i) * stride] = ns;                                                 \
-    c[(ST)(i) * stride] = nci;                                                \
+    c[(ST)(i) * stride] = (CT)nci;                                            \
     sm2 = sm1; sm1 = ns; s0 = sp1; sp1 = sp2; sp2 = sp3;                      \
     cm2 = cm1; cm1 = (double)nci; c0 = cp1; cp1 = cp2; cp2 = cp3;
     // i = 0
@@ -78,7 +80,7 @@ __device__ __forceinline__ void grid_pass_line(double* __restrict__ s, int* __re
     }
     for (int i0 = 2; BATCH && i0 <= n - 2; i0 += 8) {
         double in_s[8];
-        int in_c[8];
+        CT in_c[8];
 #pragma unroll
         for (int u = 0; u < 8; u++) {
             const int k = i0 + 3 + u;
@@ -104,13 +106,14 @@ __device__ __forceinline__ void grid_pass_line(double* __restrict__ s, int* __re
     nc = 0.1 * cm2 + 0.3 * cm1 + 0.6 * c0;
     nci = (int)nc;
     s[(ST)n * stride] = ns;
-    c[(ST)n * stride] = nci;
+    c[(ST)n * stride] = (CT)nci;
 #undef GRID_STORE_SHIFT
 }
 
 // axis: 0 = w, 1 = z, 2 = y, 3 = x.  One thread per line; thread index ordered so that adjacent threads
 // touch adjacent memory where the axis allows it (y and x passes are fully coalesced).
-__global__ void k_grid_pass(double* __restrict__ S, int* __restrict__ C, GridDims g, int axis, int n_grids) {
+template <typename CT>
+__global__ void k_grid_pass(double* __restrict__ S, CT* __restrict__ C, GridDims g, int axis, int n_grids) {
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int X = g.nx + 1, Y = g.ny + 1, Z = g.nz + 1, Wd = g.nw + 1;
     size_t lines;
@@ -121,13 +124,13 @@ __global__ void k_grid_pass(double* __restrict__ S, int* __restrict__ C, GridDim
     if (t >= lines * n_grids) return;
     size_t gi = t / lines, l = t - gi * lines;
     double* s = S + gi * g.cells;
-    int* c = C + gi * g.cells;
+    CT* c = C + gi * g.cells;
     size_t base, stride; int n;
     if (axis == 0) { base = l * Wd; stride = 1; n = g.nw; }                                   // (x,y,z) fixed
     else if (axis == 1) { size_t xy = l / Wd; int w = (int)(l - xy * Wd); base = xy * Z * Wd + w; stride = Wd; n = g.nz; }
     else if (axis == 2) { size_t x = l / ((size_t)Z * Wd); size_t zw = l - x * Z * Wd; base = x * Y * Z * Wd + zw; stride = (size_t)Z * Wd; n = g.ny; }
     else { base = l; stride = (size_t)Y * Z * Wd; n = g.nx; }
-    grid_pass_line<size_t, true>(s + base, c + base, stride, n);
+    grid_pass_line<size_t, true, CT>(s + base, c + base, stride, n);
 }
 
 // splat + w + z fused: the CTA builds the (z, w) planes it owns directly in shared memory from the ~(2 sS)^2
@@ -152,9 +155,10 @@ struct GridTables {
     int max_run;                 // longest pixel run of a spatial key (both axes)
 };
 
+template <typename CT>
 __global__ void __launch_bounds__(128)
 k_grid_build_wz(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, int H, int W, int d_first,
-                double* __restrict__ S, int* __restrict__ C, GridDims g, GridTables tb, int n_planes, int PL) {
+                double* __restrict__ S, CT* __restrict__ C, GridDims g, GridTables tb, int n_planes, int PL) {
     extern __shared__ double sm_grid[];
     const int X = g.nx + 1, Y = g.ny + 1, Z = g.nz + 1, Wd = g.nw + 1, pitch = Wd | 1, cells = Z * Wd, XY = X * Y;
     double* ss = sm_grid;                                   // [PL][Z][pitch]
@@ -206,31 +210,32 @@ k_grid_build_wz(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, 
         }
         __syncthreads();
         for (int l = tid; l < np * Z; l += 128)             // w pass: line = (plane, z), unit stride
-            grid_pass_line<int, false>(ss + l * pitch, cc + l * pitch, 1, g.nw);
+            grid_pass_line<int, false, int>(ss + l * pitch, cc + l * pitch, 1, g.nw);
         __syncthreads();
         for (int l = tid; l < np * Wd; l += 128) {          // z pass: line = (plane, w), stride = pitch
             const int pl = l / Wd, w = l - pl * Wd;
-            grid_pass_line<int, false>(ss + pl * Z * pitch + w, cc + pl * Z * pitch + w, pitch, g.nz);
+            grid_pass_line<int, false, int>(ss + pl * Z * pitch + w, cc + pl * Z * pitch + w, pitch, g.nz);
         }
         __syncthreads();
         const size_t base = (size_t)p0 * cells;
         for (int row = tid >> 5; row < np * Z; row += 4)     // one (plane, z) row per warp: no index divisions
             for (int w = tid & 31; w < Wd; w += 32) {
                 S[base + row * Wd + w] = ss[row * pitch + w];
-                C[base + row * Wd + w] = cc[row * pitch + w];
+                C[base + row * Wd + w] = (CT)cc[row * pitch + w];
             }
         __syncthreads();
     }
 }
 
+template <typename CT>
 __global__ void k_grid_slice(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, int H, int W, int d_first,
-                             int cand_first, GridDims g, GridTables tb, const double* __restrict__ S, const int* __restrict__ C,
+                             int cand_first, GridDims g, GridTables tb, const double* __restrict__ S, const CT* __restrict__ C,
                              unsigned long long* __restrict__ keys, float* __restrict__ agg) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     int d = d_first + blockIdx.z;
     const double* s = S + (size_t)blockIdx.z * g.cells;
-    const int* c = C + (size_t)blockIdx.z * g.cells;
+    const CT* c = C + (size_t)blockIdx.z * g.cells;
     double x_ = __ldg(&tb.xq[x]), y_ = __ldg(&tb.yq[y]);                                      // x / sS, y / sS (A.cpp:2290-2293)
     double cl = __ldg(&tb.gq[lg[(size_t)y * W + x]]);                                         // L / sR
     double cr = __ldg(&tb.gq[rg[(size_t)y * W + max(0, x - d)]]);                             // R(max(0, x-d)) / sR
@@ -251,7 +256,7 @@ __global__ void k_grid_slice(const uint8_t* __restrict__ lg, const uint8_t* __re
         const bool in = okx[(k >> 3) & 1] && oky[(k >> 2) & 1] && okz[(k >> 1) & 1] && okq[k & 1];
         const int id = base + ((k & 8) ? 2 * sX : 0) + ((k & 4) ? 2 * sZ : 0) + ((k & 2) ? 2 * sY : 0) + ((k & 1) ? 2 : 0);
         vs[k] = in ? __ldg(&s[id]) : 0.0;                               // map default-insert reads (0.0, 0)
-        vc[k] = in ? __ldg(&c[id]) : 0;
+        vc[k] = in ? (int)__ldg(&c[id]) : 0;
     }
     double val[2];
 #pragma unroll
@@ -272,6 +277,44 @@ __global__ void k_grid_slice(const uint8_t* __restrict__ lg, const uint8_t* __re
     size_t p = (size_t)y * W + x;
     if (agg) agg[(size_t)(cand_first + blockIdx.z) * H * W + p] = (float)E;
     atomicMin(&keys[p], wta_key_d(E, d));
+}
+
+// the candidate batches of one call; CT = storage type of the counts in HBM (uint16_t needs the fused build)
+template <typename CT>
+static asw_status grid_batches(asw_ctx* ctx, const uint8_t* gl, const uint8_t* gr, int H, int W, int min_d, int n_cand, int batch,
+                               const GridDims& g, const GridTables& tb, double* S, CT* C, unsigned long long* keys, float* agg_dev) {
+    for (int c0 = 0; c0 < n_cand; c0 += batch) {
+        int nb = n_cand - c0 < batch ? n_cand - c0 : batch;
+        // splat + w + z fused through shared memory when a few (z, w) planes fit; otherwise zero-fill, global splat
+        // and one launch per axis
+        const int Zd = g.nz + 1, Wdd = g.nw + 1;
+        const size_t plane_bytes = (size_t)Zd * (Wdd | 1) * 12;       // double sum (the int splat sum aliases it) + int count
+        int first_axis = 0;
+        // planes per CTA iteration: one line per thread in the w / z passes, and the in-place int -> double conversion
+        // holds a CTA iteration's cells in GRID_CONV_MAX registers per thread
+        const int PL_max = std::min(std::min(128 / std::max(Zd, Wdd), (int)((96 * 1024) / plane_bytes)),
+                                    (int)((size_t)GRID_CONV_MAX * 128 / ((size_t)Zd * (Wdd | 1))));
+        if (PL_max >= 1 && !getenv("ASW_GRID_UNFUSED")) {
+            int PL = PL_max;
+            size_t smem = plane_bytes * PL + 16;
+            int n_planes = (g.nx + 1) * (g.ny + 1) * nb;
+            cudaFuncSetAttribute(k_grid_build_wz<CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            unsigned blocks = (unsigned)std::min<size_t>((size_t)(n_planes + PL - 1) / PL, (size_t)ctx->sm_count * 32);
+            LAUNCH(ctx, "grid_build_wz", (k_grid_build_wz<CT><<<blocks, 128, smem, ctx->stream>>>(gl, gr, H, W, min_d + c0, S, C, g, tb, n_planes, PL)));
+            first_axis = 2;
+        } else {
+            ASW_CUDA(ctx, cudaMemsetAsync(S, 0, g.cells * nb * sizeof(double), ctx->stream));      // A.cpp:1874-1892
+            ASW_CUDA(ctx, cudaMemsetAsync(C, 0, g.cells * nb * sizeof(CT), ctx->stream));
+            LAUNCH(ctx, "grid_splat", (k_grid_splat<<<dim3(cdiv(W, 128), H, nb), 128, 0, ctx->stream>>>(gl, gr, H, W, min_d + c0, g, S, (int*)C)));
+        }
+        for (int axis = first_axis; axis < 4; axis++) {
+            size_t lines = g.cells / (size_t)((axis == 0 ? g.nw : axis == 1 ? g.nz : axis == 2 ? g.ny : g.nx) + 1) * nb;
+            static const char* pass_name[4] = {"grid_pass_w", "grid_pass_z", "grid_pass_y", "grid_pass_x"};
+            LAUNCH(ctx, pass_name[axis], (k_grid_pass<CT><<<(unsigned)((lines + 127) / 128), 128, 0, ctx->stream>>>(S, C, g, axis, nb)));
+        }
+        LAUNCH(ctx, "grid_slice", (k_grid_slice<CT><<<dim3(cdiv(W, 128), H, nb), 128, 0, ctx->stream>>>(gl, gr, H, W, min_d + c0, c0, g, tb, S, C, keys, agg_dev)));
+    }
+    return ASW_OK;
 }
 
 static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_s,
@@ -335,36 +378,17 @@ static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint
     GridTables tb;
     tb.klut = d_ti; tb.xr = d_ti + 256; tb.yr = tb.xr + 2 * GX;
     tb.xq = d_td; tb.yq = d_td + W; tb.gq = tb.yq + H; tb.max_run = max_run;
-    for (int c0 = 0; c0 < n_cand; c0 += batch) {
-        int nb = n_cand - c0 < batch ? n_cand - c0 : batch;
-        // splat + w + z fused through shared memory when a few (z, w) planes fit; otherwise zero-fill, global splat
-        // and one launch per axis
+    {
         const int Zd = g.nz + 1, Wdd = g.nw + 1;
-        const size_t plane_bytes = (size_t)Zd * (Wdd | 1) * 12;       // double sum (the int splat sum aliases it) + int count
-        int first_axis = 0;
-        // planes per CTA iteration: one line per thread in the w / z passes, and the in-place int -> double conversion
-        // holds a CTA iteration's cells in GRID_CONV_MAX registers per thread
+        const size_t plane_bytes = (size_t)Zd * (Wdd | 1) * 12;
         const int PL_max = std::min(std::min(128 / std::max(Zd, Wdd), (int)((96 * 1024) / plane_bytes)),
                                     (int)((size_t)GRID_CONV_MAX * 128 / ((size_t)Zd * (Wdd | 1))));
-        if (PL_max >= 1 && !getenv("ASW_GRID_UNFUSED")) {
-            int PL = PL_max;
-            size_t smem = plane_bytes * PL + 16;
-            int n_planes = (g.nx + 1) * (g.ny + 1) * nb;
-            cudaFuncSetAttribute(k_grid_build_wz, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            unsigned blocks = (unsigned)std::min<size_t>((size_t)(n_planes + PL - 1) / PL, (size_t)ctx->sm_count * 32);
-            LAUNCH(ctx, "grid_build_wz", (k_grid_build_wz<<<blocks, 128, smem, ctx->stream>>>(gl, gr, H, W, min_d + c0, S, C, g, tb, n_planes, PL)));
-            first_axis = 2;
-        } else {
-            ASW_CUDA(ctx, cudaMemsetAsync(S, 0, g.cells * nb * sizeof(double), ctx->stream));      // A.cpp:1874-1892
-            ASW_CUDA(ctx, cudaMemsetAsync(C, 0, g.cells * nb * sizeof(int), ctx->stream));
-            LAUNCH(ctx, "grid_splat", (k_grid_splat<<<dim3(cdiv(W, 128), H, nb), 128, 0, ctx->stream>>>(gl, gr, H, W, min_d + c0, g, S, C)));
-        }
-        for (int axis = first_axis; axis < 4; axis++) {
-            size_t lines = g.cells / (size_t)((axis == 0 ? g.nw : axis == 1 ? g.nz : axis == 2 ? g.ny : g.nx) + 1) * nb;
-            static const char* pass_name[4] = {"grid_pass_w", "grid_pass_z", "grid_pass_y", "grid_pass_x"};
-            LAUNCH(ctx, pass_name[axis], (k_grid_pass<<<(unsigned)((lines + 127) / 128), 128, 0, ctx->stream>>>(S, C, g, axis, nb)));
-        }
-        LAUNCH(ctx, "grid_slice", (k_grid_slice<<<dim3(cdiv(W, 128), H, nb), 128, 0, ctx->stream>>>(gl, gr, H, W, min_d + c0, c0, g, tb, S, C, keys, agg_dev)));
+        const bool fused = PL_max >= 1 && !getenv("ASW_GRID_UNFUSED");
+        // 16-bit counts: a count never exceeds the pixels of one spatial cell (every pass is a convex combination)
+        if (fused && (size_t)max_run * max_run <= 65535 && !getenv("ASW_GRID_C32"))
+            ASW_TRY((grid_batches<uint16_t>(ctx, gl, gr, H, W, min_d, n_cand, batch, g, tb, S, (uint16_t*)C, keys, agg_dev)));
+        else
+            ASW_TRY((grid_batches<int>(ctx, gl, gr, H, W, min_d, n_cand, batch, g, tb, S, C, keys, agg_dev)));
     }
     return keys_to_disp(ctx, keys, n, disp_dev);
 }
