@@ -195,7 +195,7 @@ __device__ __forceinline__ void gfs_bulk_g2s(void* dst, const void* src, uint32_
 
 // Horizontal sliding run of 8 window sums with the loads issued GFS_PF outputs ahead of their use (a filter warp
 // has one other warp per scheduler to hide behind, so the shared-memory latency must be covered inside the thread).
-#define GFS_PF 3
+#define GFS_PF 5
 template <int K>
 __device__ __forceinline__ float4 gfs_tree_sum(const float4* w) {
     float4 t = p4add(w[0], w[1]);
