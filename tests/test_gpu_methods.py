@@ -191,3 +191,43 @@ def test_weighted_median_dispatcher_and_limits(ctx):
     assert (d == orc.stereo_matching(L, R, 0, asw.ADAPTIVE_WEIGHT_MEDIAN, 7, 0, 6)).mean() >= AGREE
     assert ctx.computeAdaptiveWeight_WeightedMedian(L, R, 0, 8, 10, 10, 0, 6).size == 0      # even window (A.cpp:3238-3241)
     assert ctx.computeAdaptiveWeight_WeightedMedian(L, R, 1, 7, 10, 10, 0, 6).size == 0      # RIGHT: UB in the reference
+
+
+@pytest.mark.parametrize("env,alg", [("ASW_GRID_C32", "grid"), ("ASW_GRID_UNFUSED", "grid"), ("ASW_WM_SCAN", "wm"),
+                                     ("ASW_TRAD_FAST", "trad"), ("ASW_BLO_TILED", "blo1"), ("ASW_GEO_DIAG_REM", "geo"),
+                                     ("ASW_GEO_GENERIC", "geo"), ("ASW_REFINE_DENSE", "refine")])
+def test_selectable_fallback_paths(ctx, env, alg):
+    """every kernel the default path replaced stays selectable through an environment switch and keeps agreeing with the
+    oracle (32-bit grid counts / global splat, scan-based weighted median, clamped traditional kernel, tiled BLO(1),
+    diagonal-kernel remainder and thread-per-pixel geodesic, dense weighted-median refine)"""
+    import os
+    L, R, _ = make_pair(48, 72, 33 if alg == "geo" else 8, 41)
+    os.environ[env] = "1"
+    try:
+        if alg == "grid":
+            d, e = ctx.computeAdaptiveWeight_bilateralGrid(L, R, 0, 10, 10, 0, 8, agg=True, strict=True)
+            d_ref, e_ref = orc.asw_bilateral_grid(L, R, 0, 10, 10, 0, 8, agg=True)
+            fin = np.isfinite(e_ref)
+            assert np.array_equal(np.isfinite(e), fin) and np.array_equal(e[fin], e_ref[fin]) and np.array_equal(d, d_ref)
+        elif alg == "wm":
+            d, q = ctx.computeAdaptiveWeight_WeightedMedian(L, R, 0, 5, 10, 10, 0, 8, agg=True, strict=True)
+            d_ref, q_ref = orc.asw_weighted_median(L, R, 0, 5, 10, 10, 0, 8, agg=True)
+            assert np.array_equal(q, q_ref) and np.array_equal(d, d_ref)
+        elif alg == "trad":
+            d, e = ctx.computeAdaptiveWeight(L, R, 30, 20, 0, 9, 0, 8, agg=True, strict=True)
+            d_ref, e_ref = orc.asw_traditional(L, R, 30, 20, 0, 9, 0, 8, agg=True)
+            assert rel_err(e, e_ref) <= REL_TOL and (d == d_ref).mean() >= AGREE
+        elif alg == "blo1":
+            d, q = ctx.computeAdaptiveWeight_BLO1(L, R, 0, 0.015, 9, 0, 8, agg=True, strict=True)
+            d_ref, q_ref = orc.asw_blo1(L, R, 0, 0.015, 9, 0, 8, agg=True)
+            assert rel_err(q, q_ref) <= REL_TOL and (d == d_ref).mean() >= AGREE
+        elif alg == "geo":
+            d, e = ctx.computeAdaptiveWeight_geodesic(L, R, 0, 7, 0, 33, agg=True, strict=True)
+            d_ref, e_ref = orc.asw_geodesic(L, R, 0, 7, 0, 33, agg=True)
+            assert rel_err(e, e_ref) <= REL_TOL and (d == d_ref).mean() >= AGREE
+        else:
+            out = ctx.guidedf2_lr_refine(L, R, 1e-4, 9, 0, 8)
+            ref, _ = orc.guidedf2_lr_refine(L, R, 1e-4, 9, 0, 8)
+            assert (out == ref).mean() >= 0.995
+    finally:
+        del os.environ[env]
