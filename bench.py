@@ -119,6 +119,7 @@ def run_reference(args, rank, world):
     from aswstereomatch_b200.synth import make_pair
     from oracle import orc
     orc.build()
+    orc.set_num_threads(os.cpu_count() or 1)       # all host threads (torchrun presets OMP_NUM_THREADS=1)
     h, w, d = 540, 960, 128
     L, R, _ = make_pair(h, w, d, 1000)
     for _ in range(args.warmup):
