@@ -389,7 +389,7 @@ static asw_status launch_blo1_agg2(asw_ctx* ctx, const uint8_t* gref, const uint
         BloGeom gn = g;
         gn.di_lo = g.D - 1; gn.di_hi = g.D;
         dim3 grid(cdiv(g.W, SW), cdiv(g.H, TH), 1);
-        LAUNCH(ctx, "blo1_norm", (k_blo1_agg2<WIN, true><<<grid, BLO2_THREADS, smem, ctx->stream>>>(gref, gtgt, cost, Nk, Nk, gn, 1, min_d, keys, nullptr)));
+        LAUNCH(ctx, "blo1_norm", (k_blo1_agg2<WIN, true><<<grid, BLO2_THREADS, smem, ctx->stream>>>(gref, gtgt, cost, nullptr, Nk, gn, 1, min_d, keys, nullptr)));
     }
     dim3 grid(cdiv(g.W, SW), cdiv(g.H, TH), cdiv(g.di_hi - g.di_lo, dch));
     LAUNCH(ctx, "blo1_aggregate", (k_blo1_agg2<WIN, false><<<grid, BLO2_THREADS, smem, ctx->stream>>>(gref, gtgt, cost, Nk, nullptr, g, dch, min_d, keys, agg_dev)));
