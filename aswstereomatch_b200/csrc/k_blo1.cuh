@@ -269,6 +269,13 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
     const int sx = border_idx(x0 - h + cx, g.W, 1);                // boxFilter BORDER_REFLECT_101
     float* Ug = (grp ? U1 : U0) + cx;
     if (tid < PITCH) { U0[tid - PITCH] = 0.0f; U1[tid - PITCH] = 0.0f; }
+    // source rows of the two blocks (reflected once per CTA, not once per disparity and row)
+    __shared__ int srow[2][WIN];
+    if (tid < 2 * WIN) {
+        const int gq = tid / WIN, i = tid - gq * WIN;
+        srow[gq][i] = border_idx(y0 - h + (gq ? WIN + i : WIN - 1 - i), g.H, 1);   // block 0 runs upwards: its running sum is a suffix sum
+    }
+    __syncthreads();
     const float inv = 1.0f / (float)(WIN * WIN);
 
     for (int dd = 0; dd < dch; dd++) {
@@ -279,8 +286,7 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
         float a[WIN], b[WIN], c[WIN];
 #pragma unroll
         for (int i = 0; i < WIN; i++) {
-            int r = grp ? WIN + i : WIN - 1 - i;                   // block 0 runs upwards: its running sum is a suffix sum
-            int sy = border_idx(y0 - h + r, g.H, 1);
+            const int sy = srow[grp][i];
             int l = lg[(size_t)sy * g.W + sx], rr = rpad[(size_t)sy * g.Wp + xoff + sx];
             a[i] = (float)(l * rr);
             b[i] = (float)(l + rr);
