@@ -181,19 +181,35 @@ k_geo_aggregate_q(const float* __restrict__ dref, const float* __restrict__ dtgt
         float fn[GEO_Q], fd[GEO_Q];
 #pragma unroll
         for (int q = 0; q < GEO_Q; q++) { fn[q] = 0; fd[q] = 0; }
-#pragma unroll 5
-        for (int i = 0; i < win; i++) {
-            const int nx = clampi(x - h + i, 0, W - 1);
-            const size_t tap = (size_t)(j * win + i) * n;
-            const float dl = __ldg(dl_p + tap);
-            const uint32_t cr = __ldg(prow + nx);
+        // 7 taps per round: their loads (two distance planes are streamed from HBM) are issued before the first use
+        for (int i0 = 0; i0 < win; i0 += 7) {
+            float dl[7], dr[7][GEO_Q];
+            uint32_t cr[7], ct[7][GEO_Q];
 #pragma unroll
-            for (int q = 0; q < GEO_Q; q++) {
-                const int nxs = g.sign > 0 ? max(0, nx - dq[q]) : min(nx + dq[q], W - 1);
-                const float cd = (float)__vsadu4(cr, __ldg(trow + nxs));        // getColorDist (A.cpp:1321-1326)
-                const float t = __fmul_rn(dl, __ldg(dtgt + tap + pt[q]));       // float * float (A.cpp:1488-1489)
-                fn[q] = __fadd_rn(fn[q], __fmul_rn(t, cd));
-                fd[q] = __fadd_rn(fd[q], t);
+            for (int u = 0; u < 7; u++) {
+                const int i = min(i0 + u, win - 1);
+                const int nx = clampi(x - h + i, 0, W - 1);
+                const size_t tap = (size_t)(j * win + i) * n;
+                dl[u] = __ldg(dl_p + tap);
+                cr[u] = __ldg(prow + nx);
+#pragma unroll
+                for (int q = 0; q < GEO_Q; q++) {
+                    const int nxs = g.sign > 0 ? max(0, nx - dq[q]) : min(nx + dq[q], W - 1);
+                    ct[u][q] = __ldg(trow + nxs);
+                    dr[u][q] = __ldg(dtgt + tap + pt[q]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 7; u++) {
+                if (i0 + u < win) {
+#pragma unroll
+                    for (int q = 0; q < GEO_Q; q++) {
+                        const float cd = (float)__vsadu4(cr[u], ct[u][q]);          // getColorDist (A.cpp:1321-1326)
+                        const float t = __fmul_rn(dl[u], dr[u][q]);                 // float * float (A.cpp:1488-1489)
+                        fn[q] = __fadd_rn(fn[q], __fmul_rn(t, cd));
+                        fd[q] = __fadd_rn(fd[q], t);
+                    }
+                }
             }
         }
 #pragma unroll
