@@ -228,7 +228,10 @@ k_grid_build_wz(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, 
 }
 
 template <typename CT>
-__global__ void k_grid_slice(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, int H, int W, int d_first,
+// 64 registers (8 CTAs per SM): the 32 scattered loads per pixel are latency-bound, more resident warps hide more of it
+// (84 registers / 5 CTAs: 6.5 ms; 64 / 8: 5.1 ms; 48 / 10: 5.6 ms at config 3a)
+__global__ void __launch_bounds__(128, 8)
+k_grid_slice(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rg, int H, int W, int d_first,
                              int cand_first, GridDims g, GridTables tb, const double* __restrict__ S, const CT* __restrict__ C,
                              unsigned long long* __restrict__ keys, float* __restrict__ agg) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
