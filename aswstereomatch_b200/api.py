@@ -49,12 +49,12 @@ class MaskImage(C.Structure):
 # every symbol include/asw/asw.h declares (tests check the library exports all of them)
 EXPORTS = [
     "asw_device_count", "asw_create", "asw_destroy", "asw_last_error", "asw_version", "asw_sync", "asw_stream",
-    "asw_host_alloc", "asw_host_free", "asw_stereo_matching", "asw_adaptive_weight",
+    "asw_host_alloc", "asw_host_free", "asw_stereo_matching", "asw_method_candidates", "asw_adaptive_weight",
     "asw_adaptive_weight_geodesic", "asw_adaptive_weight_bilateral_grid", "asw_adaptive_weight_blo1",
     "asw_adaptive_weight_guidedf", "asw_adaptive_weight_guidedf_2", "asw_adaptive_weight_weighted_median",
     "asw_capture_aggregated", "asw_cost_tad_cg", "asw_cost_sad_box", "asw_wta", "asw_guided_filter",
     "asw_geodesic_dist", "asw_lr_check", "asw_fill_invalid", "asw_wmedian_refine", "asw_guidedf2_lr_refine",
-    "asw_batch_create", "asw_batch_destroy", "asw_batch_upload", "asw_batch_run_guidedf2_lr_refine",
+    "asw_batch_create", "asw_batch_destroy", "asw_batch_set_active", "asw_batch_upload", "asw_batch_run_guidedf2_lr_refine",
     "asw_batch_run_method", "asw_batch_download", "asw_split_local_keys", "asw_keys_alloc", "asw_keys_download",
     "asw_keys_upload", "asw_keys_min_merge", "asw_keys_to_disparity", "asw_timer_start", "asw_timer_stop",
     "asw_profile_enable", "asw_profile_reset", "asw_profile_count", "asw_profile_entry", "asw_launch_count",
@@ -86,6 +86,7 @@ def load_library():
         "asw_host_alloc": (vp, [C.c_size_t]),
         "asw_host_free": (None, [vp]),
         "asw_stereo_matching": (ci, [vp, pu8, pu8, pf32, ci, ci, ci, ci, ci]),
+        "asw_method_candidates": (ci, [ci, ci]),
         "asw_adaptive_weight": (ci, [vp, pu8, pu8, pf32, cd, cd, ci, ci, ci, ci]),
         "asw_adaptive_weight_geodesic": (ci, [vp, pu8, pu8, pf32, ci, ci, ci, ci]),
         "asw_adaptive_weight_bilateral_grid": (ci, [vp, pu8, pu8, pf32, ci, cd, cd, ci, ci]),
@@ -105,6 +106,7 @@ def load_library():
         "asw_guidedf2_lr_refine": (ci, [vp, pu8, pu8, pf32, cd, ci, ci, ci, cf, cd, cd, pf32, pf32, pmask]),
         "asw_batch_create": (ci, [vp, ci, ci, ci, C.POINTER(vp)]),
         "asw_batch_destroy": (None, [vp]),
+        "asw_batch_set_active": (ci, [vp, ci]),
         "asw_batch_upload": (ci, [vp, ci, pu8, pu8]),
         "asw_batch_run_guidedf2_lr_refine": (ci, [vp, cd, ci, ci, ci, cf, cd, cd]),
         "asw_batch_run_method": (ci, [vp, ci, ci, ci, ci, ci]),
@@ -130,6 +132,14 @@ def load_library():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def method_candidates(algorithm, num_disparity):
+    """candidates the dispatcher's method scans (numDisparity + 1 for traditional / geodesic / grid); needs no device"""
+    n = load_library().asw_method_candidates(int(algorithm), int(num_disparity))
+    if n < 0:
+        raise ValueError("algorithm outside the dense-matching hot path")
+    return n
 
 
 def _u8(a, channels=3):
@@ -451,12 +461,19 @@ class Batch:
         Ra, Rs = _u8(R)
         self.ctx._chk(self.ctx.lib.asw_batch_upload(self.h, i, C.byref(Ls), C.byref(Rs)))
 
-    def run_guidedf2_lr_refine(self, eps=1e-4, win=9, min_d=0, num_d=64, tol=0.0, rate_s=10.0, rate_r=10.0):
+    def set_active(self, n_pairs=None):
+        """the run calls process pairs [0, n_pairs) (None: the whole batch)"""
+        self.ctx._chk(self.ctx.lib.asw_batch_set_active(self.h, self.n if n_pairs is None else int(n_pairs)))
+
+    def run_guidedf2_lr_refine(self, eps=1e-4, win=9, min_d=0, num_d=64, tol=0.0, rate_s=10.0, rate_r=10.0,
+                               n_pairs=None):
+        self.set_active(n_pairs)
         self.ctx._chk(self.ctx.lib.asw_batch_run_guidedf2_lr_refine(self.h, float(eps), int(win), int(min_d),
                                                                     int(num_d), float(tol), float(rate_s),
                                                                     float(rate_r)))
 
-    def run_method(self, algorithm, disp_type=DISPARITY_LEFT, win=15, min_d=0, num_d=64):
+    def run_method(self, algorithm, disp_type=DISPARITY_LEFT, win=15, min_d=0, num_d=64, n_pairs=None):
+        self.set_active(n_pairs)
         self.ctx._chk(self.ctx.lib.asw_batch_run_method(self.h, int(algorithm), int(disp_type), int(win),
                                                         int(min_d), int(num_d)))
 
@@ -472,13 +489,15 @@ class Batch:
 
 
 def pinned_empty(shape, dtype):
-    """numpy array over cudaHostAlloc'ed (pinned) memory; keeps the allocation alive via .base."""
+    """numpy array over cudaHostAlloc'ed (pinned) memory; the allocation lives as long as any view of it
+    (the ctypes block is the views' base) and is released with asw_host_free when the last one dies."""
     lib = load_library()
     dtype = np.dtype(dtype)
     nbytes = int(np.prod(shape)) * dtype.itemsize
     p = lib.asw_host_alloc(max(nbytes, 1))
     if not p:
         raise MemoryError("asw_host_alloc failed")
-    buf = (C.c_uint8 * nbytes).from_address(p)
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p)
+    weakref.finalize(buf, lib.asw_host_free, p)     # the ctypes block is every view's base: freed with the last view
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
     return arr

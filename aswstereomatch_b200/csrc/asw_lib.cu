@@ -39,6 +39,15 @@ extern "C" asw_status asw_create(int device, asw_ctx** out) {
         cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_t0) != cudaSuccess || cudaEventCreate(&ctx->ev_t1) != cudaSuccess ||
         cudaEventCreate(&ctx->ev_p0) != cudaSuccess || cudaEventCreate(&ctx->ev_p1) != cudaSuccess) {
+        // release whatever was created before the failure (the handles start out null)
+        if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+        if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
+        if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
+        if (ctx->ev_p0) cudaEventDestroy(ctx->ev_p0);
+        if (ctx->ev_p1) cudaEventDestroy(ctx->ev_p1);
+        if (ctx->h2d_stream) cudaStreamDestroy(ctx->h2d_stream);
+        if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
         delete ctx;
         return ASW_ERR_CUDA;
     }

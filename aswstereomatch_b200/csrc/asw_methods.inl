@@ -293,6 +293,13 @@ static bool dispatcher_args(int algorithm, int disp_type, int win, int min_d, in
     default: return false;   // BM, SGBM, 8-direction, GuidedF_3, NCC: outside the hot path
     }
 }
+// candidates the dispatcher's method scans for a named numDisparity (D + 1 where the reference loop runs to
+// max_offset inclusive, A.cpp:1074, 1467, 2279); -1 for algorithms outside the hot path
+extern "C" int asw_method_candidates(int algorithm, int num_d) {
+    MethodArgs m;
+    if (num_d <= 0 || !dispatcher_args(algorithm, 0, 1, 0, num_d, &m)) return -1;
+    return method_n_eval(m);
+}
 extern "C" asw_status asw_stereo_matching(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, asw_f32_image* disp,
                                           int disp_type, int algorithm, int win, int min_d, int num_d) {
     if (!ctx) return ASW_ERR_BAD_ARG;
@@ -312,6 +319,7 @@ extern "C" asw_status asw_stereo_matching(asw_ctx* ctx, const asw_u8_image* L, c
 // pair i-1 therefore overlap the kernels of pair i.
 struct asw_batch {
     asw_ctx* ctx; int n, H, W;
+    int active;        // the run calls process pairs [0, active)
     uint8_t* imgs;     // [n][2][H][W][3]
     float* disp;       // [n][H][W]
     std::vector<cudaEvent_t> uploaded, computed, downloaded;
@@ -330,7 +338,7 @@ extern "C" asw_status asw_batch_create(asw_ctx* ctx, int n_pairs, int rows, int 
     if (!ctx || !out || n_pairs <= 0 || rows <= 0 || cols <= 0) return ASW_ERR_BAD_ARG;
     ASW_CUDA(ctx, cudaSetDevice(ctx->device));
     asw_batch* b = new asw_batch();
-    b->ctx = ctx; b->n = n_pairs; b->H = rows; b->W = cols; b->imgs = nullptr; b->disp = nullptr;
+    b->ctx = ctx; b->n = n_pairs; b->active = n_pairs; b->H = rows; b->W = cols; b->imgs = nullptr; b->disp = nullptr;
     size_t n = (size_t)rows * cols;
     if (cudaMalloc(&b->imgs, n * 6 * n_pairs) != cudaSuccess || cudaMalloc(&b->disp, n * 4 * n_pairs) != cudaSuccess) {
         if (b->imgs) cudaFree(b->imgs);
@@ -358,6 +366,11 @@ extern "C" void asw_batch_destroy(asw_batch* b) {
     cudaFree(b->imgs); cudaFree(b->disp);
     delete b;
 }
+extern "C" asw_status asw_batch_set_active(asw_batch* b, int n_active) {
+    if (!b || n_active < 0 || n_active > b->n) return ASW_ERR_BAD_ARG;
+    b->active = n_active;
+    return ASW_OK;
+}
 extern "C" asw_status asw_batch_upload(asw_batch* b, int i, const asw_u8_image* L, const asw_u8_image* R) {
     if (!b || i < 0 || i >= b->n) return ASW_ERR_BAD_ARG;
     asw_ctx* ctx = b->ctx;
@@ -379,7 +392,7 @@ extern "C" asw_status asw_batch_run_guidedf2_lr_refine(asw_batch* b, double eps,
     if (!valid_disp_args(0, min_d, num_d) || win <= 0 || win % 2 == 0) return asw_fail(ctx, ASW_ERR_BAD_ARG, "bad arguments%s%s");
     ASW_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t n = (size_t)b->H * b->W, n3 = n * 3;
-    for (int i = 0; i < b->n; i++) {
+    for (int i = 0; i < b->active; i++) {
         const uint8_t* dL = b->imgs + (size_t)i * 2 * n3;
         ASW_TRY(batch_pair_begin(b, i));
         ASW_TRY(dev_guidedf2_lr_refine(ctx, dL, dL + n3, b->H, b->W, eps, win, min_d, num_d, tol, rate_s, rate_r,
@@ -397,7 +410,7 @@ extern "C" asw_status asw_batch_run_method(asw_batch* b, int algorithm, int disp
     ASW_TRY(method_check(ctx, m));
     ASW_CUDA(ctx, cudaSetDevice(ctx->device));
     size_t n = (size_t)b->H * b->W, n3 = n * 3;
-    for (int i = 0; i < b->n; i++) {
+    for (int i = 0; i < b->active; i++) {
         const uint8_t* dL = b->imgs + (size_t)i * 2 * n3;
         ASW_TRY(batch_pair_begin(b, i));
         ASW_TRY(dev_run_method(ctx, m, dL, dL + n3, b->H, b->W, b->disp + (size_t)i * n, nullptr));

@@ -5,13 +5,20 @@
 #pragma once
 #include "k_cost.cuh"
 
-// valid = |dL(y,x) - dR(y, max(0, x - (int)dL))| <= tol
+// column of the right map a left-view disparity d points at: x - (int)d clamped to the row (the spec's max(0, .), plus
+// the upper clamp so that negative / non-finite user maps given to the stage-level entry never read out of bounds;
+// __float2int_rz saturates and maps NaN to 0)
+__device__ __forceinline__ int lr_target_col(int x, float d, int W) {
+    const long long t = (long long)x - (long long)__float2int_rz(d);
+    return (int)min(max(t, 0ll), (long long)(W - 1));
+}
+// valid = |dL(y,x) - dR(y, clamp(x - (int)dL, 0, W-1))| <= tol
 __global__ void k_lr_check(const float* __restrict__ dl, const float* __restrict__ dr, int H, int W, float tol,
                            uint8_t* __restrict__ valid) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     float d = dl[(size_t)y * W + x];
-    int xr = max(0, x - (int)d);
+    int xr = lr_target_col(x, d, W);
     valid[(size_t)y * W + x] = fabsf(d - dr[(size_t)y * W + xr]) <= tol ? 1 : 0;
 }
 
@@ -190,7 +197,7 @@ k_lr_fill_compact(const float* __restrict__ dl, const float* __restrict__ dr, in
     const float* rrow = dr + (size_t)y * W;
     for (int x = threadIdx.x; x < W; x += blockDim.x) {
         const float d = row[x];
-        const uint8_t v = fabsf(d - rrow[max(0, x - (int)d)]) <= tol ? 1 : 0;
+        const uint8_t v = fabsf(d - rrow[lr_target_col(x, d, W)]) <= tol ? 1 : 0;
         sm_valid[x] = v;
         valid[(size_t)y * W + x] = v;
     }

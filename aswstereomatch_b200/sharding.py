@@ -44,7 +44,9 @@ def allreduce_min_keys(keys_u64, device=None):
 
 def split_stereo_matching(ctx, L, R, algorithm, disp_type, win, min_d, num_d, rank, world, device=None):
     """disparity-split of one pair across the process group; every rank returns the full disparity map"""
-    lo, hi = split_range(num_d, rank, world)
+    from .api import method_candidates
+    # the candidates the method really scans: numDisparity + 1 for traditional / geodesic / grid (loop `<=`)
+    lo, hi = split_range(method_candidates(algorithm, num_d), rank, world)
     keys, _ = ctx.split_local_keys(L, R, algorithm, disp_type, win, min_d, num_d, lo, hi)
     merged = allreduce_min_keys(keys, device)
     return ctx.keys_to_disparity(merged)

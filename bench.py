@@ -12,8 +12,13 @@ One "step" = one pass of that pipeline over the rank's batch.
           copied host->device, processed, and its refined map copied device->host inside the timed region
   roofline / cpu_baseline : see DESIGN.md section "Measurement"
 
-`--impl reference` times the reference's CPU behaviour (the oracle port, all host threads) on a bounded
-sample of the same workload and prints the same line with "impl": "reference".
+Scaling: the named config is ONE batch of 64 pairs, so by default the 64 pairs are divided over the ranks
+("scaling": "strong", --pairs-total 64); `--pairs P` instead gives every rank P pairs ("weak").  At N > 1 the
+strong line also carries the weak figure ("weak": {...}) from one extra pass.
+
+`--impl reference` times the reference's CPU behaviour (oracle/_ref for the methods it covers; GuidedF_2 needs
+OpenCV's filters, so this path runs the oracle port, all host threads) on the SAME config: each step is one
+full-size pair of the batch (1920x1080, D = 256, both views + LR + refine), a bounded sample of the 64-pair step.
 """
 import argparse
 import json
@@ -103,12 +108,12 @@ def cpu_baseline(sample_hw=(1080, 1920), sample_d=256, threads=None):
     h, w = sample_hw
     L, R, _ = make_pair(h, w, sample_d, 1000)
     t0 = time.perf_counter()
-    orc.guidedf2_lr_refine(L, R, EPS, WIN, 0, sample_d)
+    out, _ = orc.guidedf2_lr_refine(L, R, EPS, WIN, 0, sample_d)
     dt = time.perf_counter() - t0
     mde = h * w * sample_d * VIEWS / 1e6
     return {"value": mde / dt, "unit": "MDE/s", "cores": orc.num_threads(), "kind": "port",
             "sample": f"1 pair {w}x{h}, D={sample_d}, r={WIN}, eps={EPS}, 2 views + LR + refine ({dt:.1f} s; "
-                      f"oracle/asw_oracle.c, OpenMP over slices/rows)"}, dt
+                      f"oracle/asw_oracle.c, OpenMP over slices/rows)"}, out
 
 
 def run_reference(args, rank, world):
@@ -120,7 +125,7 @@ def run_reference(args, rank, world):
     from oracle import orc
     orc.build()
     orc.set_num_threads(os.cpu_count() or 1)       # all host threads (torchrun presets OMP_NUM_THREADS=1)
-    h, w, d = 540, 960, 128
+    h, w, d = H, W, D                              # same config as the b200 arm: one full-size pair per step
     L, R, _ = make_pair(h, w, d, 1000)
     for _ in range(args.warmup):
         orc.guidedf2_lr_refine(L, R, EPS, WIN, 0, d)
@@ -130,11 +135,12 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     mde_step = h * w * d * VIEWS / 1e6
     val = mde_step * args.steps / dt
-    sample = f"per step: 1 pair {w}x{h}, D={d}, r={WIN}, eps={EPS}, 2 views + LR + refine (bounded sample of cfg5)"
+    sample = (f"per step: 1 pair {w}x{h}, D={d}, r={WIN}, eps={EPS}, 2 views + LR + refine (1 of the 64 pairs of a "
+              f"cfg5 step; same image size and disparity range as the b200 arm)")
     line = {"impl": "reference", "metric": "MDE/s", "value": val, "unit": "MDE/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": sample},
+            "config": {"workload": WORKLOAD, "sample": sample, "image": [W, H], "disparities": D, "views": VIEWS},
             "cpu_baseline": {"value": val, "unit": "MDE/s", "cores": orc.num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "MDE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -147,8 +153,11 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--pairs", type=int, default=64, help="pairs per GPU per step (cfg5: 64)")
+    ap.add_argument("--pairs-total", type=int, default=64, help="pairs per step over ALL ranks (cfg5: 64; strong scaling)")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs per GPU per step (weak scaling; overrides --pairs-total)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs 1-4 section")
+    ap.add_argument("--no-split", action="store_true", help="skip the disparity-split section")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -166,18 +175,25 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     import aswstereomatch_b200 as asw
+    from aswstereomatch_b200 import sharding
     from aswstereomatch_b200.synth import make_batch
     ctx = asw.Context(local_rank)          # raises without the CUDA library / a device: no CPU fallback
-    P = args.pairs
-    Ls, Rs = make_batch(P, H, W, D, seed0=1000 + 10000 * rank, distinct=min(P, 4))
+    weak = args.pairs > 0
+    PW = args.pairs if weak else 64                                           # pairs per GPU of the weak leg
+    mine = list(range(PW)) if weak else sharding.shard_pairs(args.pairs_total, rank, world)   # pair i -> rank i % N
+    P = len(mine)
+    total_pairs = PW * world if weak else args.pairs_total
+    n_buf = max(P, PW) if (world > 1 and not weak) else P                     # the extra weak pass needs PW pairs
+    # global pair i has seed 1000 + i (weak: rank r owns 1000 + 10000 r + i); pair 0 of rank 0 is always seed 1000
+    Ls, Rs = make_batch(n_buf, H, W, D, seed0=1000 + 10000 * rank, distinct=min(n_buf, 4))
     # pinned host buffers (inputs and results) for the end-to-end leg
-    hL = asw.pinned_empty((P, H, W, 3), np.uint8)
-    hR = asw.pinned_empty((P, H, W, 3), np.uint8)
-    hD = asw.pinned_empty((P, H, W), np.float32)
-    for i in range(P):
+    hL = asw.pinned_empty((n_buf, H, W, 3), np.uint8)
+    hR = asw.pinned_empty((n_buf, H, W, 3), np.uint8)
+    hD = asw.pinned_empty((n_buf, H, W), np.float32)
+    for i in range(n_buf):
         hL[i] = Ls[i]; hR[i] = Rs[i]
     del Ls, Rs
-    batch = asw.Batch(ctx, P, H, W)
+    batch = asw.Batch(ctx, n_buf, H, W)
 
     def barrier():
         ctx.sync()
@@ -186,14 +202,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def step_resident():
-        batch.run_guidedf2_lr_refine(EPS, WIN, 0, D)
+    def step_resident(n=P):
+        batch.run_guidedf2_lr_refine(EPS, WIN, 0, D, n_pairs=n)
 
-    def step_e2e():
-        for i in range(P):
+    def step_e2e(n=P):
+        for i in range(n):
             batch.upload(i, hL[i], hR[i])
-        batch.run_guidedf2_lr_refine(EPS, WIN, 0, D)
-        for i in range(P):
+        batch.run_guidedf2_lr_refine(EPS, WIN, 0, D, n_pairs=n)
+        for i in range(n):
             batch.download(i, hD[i], sync=False)
 
     def timed(fn, steps):
@@ -210,7 +226,7 @@ def main():
         return ms
 
     # inputs resident in HBM before the timed region of the `value` leg
-    for i in range(P):
+    for i in range(n_buf):
         batch.upload(i, hL[i], hR[i])
     for _ in range(args.warmup):
         step_resident()
@@ -232,18 +248,36 @@ def main():
     # end-to-end leg (host buffers; H2D + D2H inside the timed region)
     step_e2e(); ctx.sync()
     ms_e2e = timed(step_e2e, args.steps)
+    map0 = np.array(hD[0])                  # refined map of pair 0 (rank 0: seed 1000) from the last e2e step
+
+    weak_leg = None
+    if world > 1 and not weak:
+        # the same pipeline with 64 pairs on EVERY rank (weak scaling), one warm-up + the timed steps
+        step_resident(PW); ctx.sync()
+        ms_w = timed(lambda: step_resident(PW), args.steps)
+        weak_leg = {"pairs_per_gpu": PW, "ms_per_step": ms_w / args.steps,
+                    "value": H * W * D * VIEWS * PW * world / 1e6 / (ms_w / args.steps) * 1e3, "unit": "MDE/s"}
+
+    split = None
+    if not args.no_split:
+        split = bench_split(ctx, asw, dist, torch, rank, world, local_rank, args)
+    cfgs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs
+        cfgs = bench_configs.run_configs(ctx, reps=3, warmup=3, brief=True)
 
     # sanity: the last e2e result is a plausible disparity map (guards against timing a no-op)
-    ok = bool(np.isfinite(hD[0]).all() and hD[0].max() <= D - 1 and hD[0].std() > 0)
+    ok = bool(np.isfinite(map0).all() and map0.max() <= D - 1 and map0.std() > 0)
 
     if rank == 0:
-        mde_step = H * W * D * VIEWS * P * world / 1e6
+        mde_step = H * W * D * VIEWS * total_pairs / 1e6
         value = mde_step / (ms_res / args.steps) * 1e3
         e2e = mde_step / (ms_e2e / args.steps) * 1e3
         peak, peak_src = measured_peak()
         dom = max(prof.items(), key=lambda kv: kv[1][0])
         name, (tot_ms, n_l) = dom
-        de_per_launch = H * W * D * VIEWS * P / n_l            # each gf_ab / gf_q launch covers one slice chunk
+        de_per_launch = H * W * D * VIEWS * P / n_l            # one launch of the dominant kernel covers one view of one pair
         alg = ALG_BYTES.get(name)
         achieved = alg * de_per_launch / (tot_ms / n_l * 1e-3) / 1e9 if alg else None
         traffic = None
@@ -256,22 +290,29 @@ def main():
         line = {
             "metric": "MDE/s", "value": value, "unit": "MDE/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_res / args.steps, "ms_per_frame": ms_res / args.steps / P, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": P, "image": [W, H], "disparities": D, "views": VIEWS,
-                       "l2": "inputs larger than L2: every step streams 0.8 GB of images and, per view, a 2.1 GB "
-                             "filtered-cost volume (written by the filter kernel, read by the WTA pass) through the "
-                             "126 MB L2", "result_check": ok},
+            "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "pairs_total": total_pairs, "pairs_per_gpu": P, "image": [W, H],
+                       "disparities": D, "views": VIEWS,
+                       "l2": "inputs larger than L2: every step streams 12.4 MB of images and, per view, a 2.1 GB "
+                             "filtered-cost volume per pair through the 126 MB L2", "result_check": ok},
             "clocks": clk,
             "e2e": {"value": e2e, "unit": "MDE/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(hL.nbytes + hR.nbytes), "d2h_bytes_per_step": int(hD.nbytes)},
+                    "h2d_bytes_per_step": int(hL[:P].nbytes + hR[:P].nbytes), "d2h_bytes_per_step": int(hD[:P].nbytes)},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                          "avg_launch_ms": tot_ms / n_l, "share_of_step": tot_ms / total_prof,
-                         "alg_bytes_per_de": alg, "de_per_launch": de_per_launch},
+                         "alg_bytes_per_de": alg, "de_per_launch": de_per_launch,
+                         "frac_of_traffic": (traffic / (tot_ms / n_l * 1e-3) / 1e9 / peak) if traffic else None},
             "fp32_issue": None,
             "kernels_ms_per_step": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]},
         }
+        if weak_leg:
+            line["weak"] = weak_leg
+        if split:
+            line["split"] = split
+        if cfgs:
+            line["configs"] = cfgs
         if name in ALG_LANE_INSTR:
             # secondary view: the kernel moves far fewer HBM bytes than the 3-pass model, its own bound is the FP32
             # issue rate (148 SMs x 128 lanes x SM clock)
@@ -280,18 +321,33 @@ def main():
             ach_li = ALG_LANE_INSTR[name] * de_per_launch / (tot_ms / n_l * 1e-3)
             line["fp32_issue"] = {"alg_lane_instr_per_de": ALG_LANE_INSTR[name], "achieved": ach_li, "peak": peak_li,
                                   "unit": "lane-instr/s", "frac": ach_li / peak_li}
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:
+            # rank 0 at N = 1 only: the oracle on the pair the GPU holds at index 0 (seed 1000) -- timed as the CPU
+            # baseline AND compared with the GPU's refined map of that pair (parity of the headline run itself)
             try:
                 from oracle import orc
                 orc.build()
-                line["cpu_baseline"], _ = cpu_baseline()
+                line["cpu_baseline"], ref_map = cpu_baseline(threads=os.cpu_count() or 1)
+                n_diff = int((ref_map != map0).sum())
+                agree = 1.0 - n_diff / ref_map.size
+                line["parity"] = {"what": "refined map of pair 0 (e2e leg, through the C-ABI) vs the oracle on the same pair",
+                                  "agree": agree, "n_diff": n_diff, "pixels": int(ref_map.size)}
+                line["config"]["result_check"] = bool(ok and agree >= 0.995)
             except Exception as e:          # the baseline is reported, never required for the GPU numbers
                 line["cpu_baseline"] = {"value": None, "unit": "MDE/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
         print(json.dumps(line), flush=True)
+        if not line["config"]["result_check"]:
+            sys.exit("bench: result check failed (GPU map implausible or below 99.5 % agreement with the oracle)")
     batch.close()
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def bench_split(ctx, asw, dist, torch, rank, world, local_rank, args):
+    """disparity-range split of ONE 1080p x 256 GuidedF_2 pair over the ranks: filled in by the
+    device-resident split path"""
+    return None
 
 
 if __name__ == "__main__":

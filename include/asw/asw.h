@@ -73,6 +73,11 @@ asw_status asw_stereo_matching(asw_ctx* ctx, const asw_u8_image* left, const asw
                                asw_f32_image* disparity, int disparity_type, int algorithm_type,
                                int win_size, int min_disparity, int num_disparity);
 
+/* number of candidate disparities the dispatcher's method scans for a named numDisparity: num_disparity + 1 for
+ * traditional / geodesic / bilateral grid (their loops run to max_offset inclusive, A.cpp:1074, 1467, 2279),
+ * num_disparity for the others; -1 for algorithms outside the hot path.  Needs no device. */
+int asw_method_candidates(int algorithm_type, int num_disparity);
+
 /* ---- per-method entry points (same argument order and meaning as A.h) ---- */
 /* computeAdaptiveWeight (A.h:133-134, A.cpp:1016-1156) */
 asw_status asw_adaptive_weight(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
@@ -146,6 +151,8 @@ asw_status asw_guidedf2_lr_refine(asw_ctx* ctx, const asw_u8_image* left, const 
 typedef struct asw_batch asw_batch;
 asw_status asw_batch_create(asw_ctx* ctx, int n_pairs, int rows, int cols, asw_batch** out);
 void asw_batch_destroy(asw_batch* b);
+/* the run calls below process pairs [0, n_active) (default: all n_pairs) */
+asw_status asw_batch_set_active(asw_batch* b, int n_active);
 asw_status asw_batch_upload(asw_batch* b, int index, const asw_u8_image* left, const asw_u8_image* right);
 /* asynchronous on the ctx stream: every pair through asw_guidedf2_lr_refine's pipeline */
 asw_status asw_batch_run_guidedf2_lr_refine(asw_batch* b, double eps, int win_size, int min_disparity,

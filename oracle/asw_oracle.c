@@ -970,7 +970,10 @@ void orc_lr_check(const float* dl, const float* dr, int H, int W, float tol, uin
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++) {
             float d = dl[(size_t)y * W + x];
-            int xr = x - (int)d; if (xr < 0) xr = 0;
+            /* (int)d with saturation (NaN -> 0), target column clamped to the row */
+            long long di = d != d ? 0 : d >= 2147483648.0f ? 2147483647LL : d <= -2147483648.0f ? -2147483648LL : (long long)(int)d;
+            long long t = (long long)x - di;
+            int xr = t < 0 ? 0 : t > W - 1 ? W - 1 : (int)t;
             valid[(size_t)y * W + x] = fabsf(d - dr[(size_t)y * W + xr]) <= tol ? 1 : 0;
         }
 }

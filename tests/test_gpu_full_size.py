@@ -34,7 +34,7 @@ def split_agreement(ctx, L, R, alg, win, D, full, world=2):
     """fraction of pixels on which the MIN-merged keys of `world` disjoint candidate ranges give the unsplit map"""
     merged = None
     for r in range(world):
-        lo, hi = sharding.split_range(D + 1 if alg in (asw.ADAPTIVE_WEIGHT, asw.ADAPTIVE_WEIGHT_GEODESIC, asw.ADAPTIVE_WEIGHT_BILATERAL_GRID) else D, r, world)
+        lo, hi = sharding.split_range(asw.method_candidates(alg, D), r, world)
         keys, _ = ctx.split_local_keys(L, R, alg, 0, win, 0, D, lo, hi)
         merged = keys if merged is None else np.minimum(merged, keys)
     return float((ctx.keys_to_disparity(merged) == full).mean())
@@ -97,3 +97,37 @@ def test_config4_geodesic_full_size_band(ctx):
     # the candidate remainder (d = 128) is summed by another kernel in the unsplit run than in rank 1's: equal costs up to
     # rounding, so a pixel whose two best candidates are within 1e-6 of each other may flip
     assert split_agreement(ctx, L, R, asw.ADAPTIVE_WEIGHT_GEODESIC, win, D, d) >= 0.9999
+
+
+def test_config5_guidedf2_lr_refine_full_size():
+    """config 5's own size: one 1920x1080 pair, 256 disparities, r = 9, eps = 1e-4, both views + LR check + refine
+    against the whole oracle (A.cpp:2976-3050 per view; stage 4 = the a-14 specification).  Raw left / right maps
+    >= 99.9 %, stage 4 integer-exact given the GPU's own maps, refined map >= 99.9 %, aggregated costs within 1e-4 of
+    the slice maximum on slices spread over the range (first and last included)."""
+    import os
+    import __graft_entry__ as g
+    g.build()
+    H, W, D = 1080, 1920, 256
+    orc.set_num_threads(os.cpu_count() or 1)
+    L, R, gt = make_pair(H, W, D, 1000)          # the pair bench.py's rank 0 holds at index 0
+    ctx = asw.Context(0)
+    try:
+        out, parts = ctx.guidedf2_lr_refine(L, R, 1e-4, 9, 0, D, parts=True)
+        ref, rparts = orc.guidedf2_lr_refine(L, R, 1e-4, 9, 0, D)
+        assert (parts["dl"] == rparts["dl"]).mean() >= AGREE
+        assert (parts["dr"] == rparts["dr"]).mean() >= AGREE
+        # stage 4 on the GPU's own raw maps: mask, fill and median selection are integer-exact
+        v = orc.lr_check(parts["dl"], parts["dr"], 0.0)
+        assert np.array_equal(parts["valid"], v)
+        assert np.array_equal(out, orc.wmedian_refine(L, orc.fill_invalid(parts["dl"], v), v, 9, 10, 10))
+        assert (out == ref).mean() >= AGREE
+        assert np.mean(np.abs(parts["dl"] - gt) <= 1) > 0.85
+        # aggregated costs (left view), slice by slice to bound host memory
+        d, q = ctx.computeAdaptiveWeight_GuidedF_2(L, R, 0, 1e-4, 9, 0, D, agg=True, strict=True)
+        assert np.array_equal(d, parts["dl"])
+        assert np.array_equal(d, orc.wta(q, 0))                      # WTA index bit-exact given the GPU volume
+        d_ref, q_ref = orc.asw_guidedf2(L, R, 0, 1e-4, 9, 0, D, agg=True)
+        for s in (0, 1, 31, 64, 127, 128, 200, 254, 255):
+            assert slice_err(q[s:s + 1], q_ref[s:s + 1]) <= REL_TOL, s
+    finally:
+        ctx.close()

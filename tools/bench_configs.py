@@ -38,18 +38,12 @@ CONFIGS = [
 ]
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--only", default="")
-    ap.add_argument("--out", default="")
-    a = ap.parse_args()
-    ctx = asw.Context(0)
+def run_configs(ctx, reps=3, warmup=3, only="", brief=False):
+    """measure configs 1-4 on `ctx`; returns one dict per config (brief: the bench.py `configs` entries)"""
     hbm = peaks()
     lines = []
     for idx, (name, (W, H), D, Dev, run, (kind, work)) in enumerate(CONFIGS):
-        if a.only and a.only not in name:
+        if only and only not in name:
             continue
         L, R, _ = make_pair(H, W, D, idx + 1)
         b = asw.Batch(ctx, 1, H, W)
@@ -62,11 +56,11 @@ def main():
             else:
                 b.run_method(run[1], 0, run[2], 0, D)
 
-        for _ in range(a.warmup):
+        for _ in range(warmup):
             step()
         ctx.sync()
         times = []
-        for _ in range(a.reps):
+        for _ in range(reps):
             ctx.flush_l2()
             ctx.timer_start()
             step()
@@ -80,19 +74,35 @@ def main():
         de_eval = W * H * Dev * views
         if kind == "fp32":
             peak = SM * LANES * 1.965e9
-            achieved = work * de_eval / (ms * 1e-3)
             unit = "lane-instr/s"
         else:
             peak = hbm * 1e9
-            achieved = work * de_eval / (ms * 1e-3)
             unit = "B/s"
-        line = {"config": name, "ms": ms, "mde_per_s": de_named / ms / 1e3, "roofline": {
-            "bound": kind, "work_per_de": work, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak},
-            "kernels_ms": {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]},
-            "l2": "flushed before every repetition", "reps": a.reps, "warmup": a.warmup}
-        print(json.dumps(line), flush=True)
+        achieved = work * de_eval / (ms * 1e-3)
+        kern = {k: round(v[0], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])[:6]}
+        if brief:
+            line = {"cfg": name.split()[0], "config": name, "ms": round(ms, 4), "mde_s": round(de_named / ms / 1e3, 1),
+                    "frac": round(achieved / peak, 4), "bound": kind, "work_per_de": work, "kernels_ms": kern}
+        else:
+            line = {"config": name, "ms": ms, "mde_per_s": de_named / ms / 1e3, "roofline": {
+                "bound": kind, "work_per_de": work, "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak},
+                "kernels_ms": kern, "l2": "flushed before every repetition", "reps": reps, "warmup": warmup}
         lines.append(line)
         b.close()
+    return lines
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    ctx = asw.Context(0)
+    lines = run_configs(ctx, a.reps, a.warmup, a.only)
+    for ln in lines:
+        print(json.dumps(ln), flush=True)
     if a.out:
         with open(a.out, "w") as f:
             for ln in lines:
