@@ -202,10 +202,11 @@ static asw_status method_check(asw_ctx* ctx, const MethodArgs& m) {
     bool needs_odd = m.id != M_GRID;
     if (needs_odd && (m.win <= 0 || m.win % 2 == 0))
         return asw_fail(ctx, ASW_ERR_BAD_ARG, "window size must be odd%s%s");           // A.cpp:1440, 2458, 3238
-    // DISPARITY_RIGHT: the TAD-cost methods throw in the reference (Appendix A-3), the grid reads out of
-    // bounds (A-7), the weighted median is UB (A-10).  GuidedF_2 RIGHT is offered only through the
-    // explicit LR pipeline (asw_guidedf2_lr_refine), with the mirrored-LEFT cost.
-    if (m.disp_type == 1 && (m.id == M_GRID || m.id == M_WMED || m.id == M_BLO1))
+    // DISPARITY_RIGHT: the TAD-cost methods throw in the reference (Appendix A-3; observed on the reference's own code,
+    // tests/test_cpu_ref.py), the grid reads out of bounds (A-7).  GuidedF_2 RIGHT is offered only through the explicit
+    // LR pipeline (asw_guidedf2_lr_refine), with the mirrored-LEFT cost.  BLO(1), traditional, geodesic and GuidedF
+    // define RIGHT (A.cpp:2538-2546, 2600-2631, 2685-2722 for BLO(1)).
+    if (m.disp_type == 1 && (m.id == M_GRID || m.id == M_WMED))
         return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "DISPARITY_RIGHT is undefined for this method in the reference%s%s");
     if (m.id == M_BLO1 && m.min_d != 0)
         return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "BLO1 indexes planes by offset (A.cpp:2666): minDisparity must be 0%s%s");
@@ -219,7 +220,7 @@ static asw_status dev_run_method(asw_ctx* ctx, const MethodArgs& m, const uint8_
     case M_TRAD: return dev_traditional(ctx, dL, dR, H, W, m.p0, m.p1, m.disp_type, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
     case M_GEO: return dev_geodesic(ctx, dL, dR, H, W, m.disp_type, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
     case M_GRID: return dev_bilateral_grid(ctx, dL, dR, H, W, m.p0, m.p1, m.min_d, m.num_d, disp_dev, agg_dev);
-    case M_BLO1: return dev_blo1(ctx, dL, dR, H, W, m.p0, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
+    case M_BLO1: return dev_blo1(ctx, dL, dR, H, W, m.disp_type, m.p0, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
     case M_WMED: return dev_weighted_median(ctx, dL, dR, H, W, m.win, m.p0, m.p1, m.min_d, m.num_d, disp_dev, agg_dev);
     }
     return ASW_ERR_UNSUPPORTED;
@@ -468,7 +469,7 @@ extern "C" asw_status asw_split_local_keys(asw_ctx* ctx, const asw_u8_image* L, 
             if (m.id == M_TRAD) ASW_TRY(dev_traditional(ctx, dL, dR, H, W, m.p0, m.p1, disp_type, win, min_d + d_begin, cnt - 1, tmp, nullptr));
             else if (m.id == M_GEO) ASW_TRY(dev_geodesic(ctx, dL, dR, H, W, disp_type, win, min_d + d_begin, cnt - 1, tmp, nullptr));
             else if (m.id == M_GRID) ASW_TRY(dev_bilateral_grid(ctx, dL, dR, H, W, m.p0, m.p1, min_d + d_begin, cnt - 1, tmp, nullptr));
-            else ASW_TRY(dev_blo1_range(ctx, dL, dR, H, W, m.p0, win, min_d, num_d, d_begin, d_end, tmp, nullptr));
+            else ASW_TRY(dev_blo1_range(ctx, dL, dR, H, W, disp_type, m.p0, win, min_d, num_d, d_begin, d_end, tmp, nullptr));
         }
     }
     ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

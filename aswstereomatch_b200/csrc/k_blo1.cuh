@@ -1,4 +1,6 @@
-// k_blo1.cuh -- O(1)-bilateral ASW, computeAdaptiveWeight_BLO1 (A.cpp:2505-2725), LEFT, minDisparity = 0.
+// k_blo1.cuh -- O(1)-bilateral ASW, computeAdaptiveWeight_BLO1 (A.cpp:2505-2725), minDisparity = 0.  Written for the LEFT
+// view; DISPARITY_RIGHT (A.cpp:2538-2546, 2600-2631, 2685-2722) is the same computation with the right gray image as the
+// reference side `lg` and the left one, padded on its right, as the target `rpad` (crop column +d): only the geometry differs.
 //
 // Reference: for every intensity level k (0, step, 2 step, ..., 255; step = int(256*sampleRateR)) and every d:
 //   M_d = |L-k| * |R_d-k| ; J_{k,d} = box(M_d * c_d) ; N_k = box(M_{D-1})  (LAST d only, A.cpp:2588) ;
@@ -404,8 +406,8 @@ static asw_status launch_blo1_agg2(asw_ctx* ctx, const uint8_t* gref, const uint
 
 // slices [di_lo, di_hi) of the num_d-slice problem (the whole range: dev_blo1).  agg_dev, if given, is the full
 // [num_d][H][W] volume.
-static asw_status dev_blo1_range(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_r, int win,
-                                 int min_d, int num_d, int di_lo, int di_hi, float* disp_dev, float* agg_dev) {
+static asw_status dev_blo1_range(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type, double rate_r,
+                                 int win, int min_d, int num_d, int di_lo, int di_hi, float* disp_dev, float* agg_dev) {
     size_t n = (size_t)H * W;
     BloGeom g;
     g.step = (int)(256 * rate_r);                                  // A.cpp:2549
@@ -418,8 +420,8 @@ static asw_status dev_blo1_range(asw_ctx* ctx, const uint8_t* dL, const uint8_t*
     uint8_t *gref, *gtgt;
     ASW_TRY(ws_get(ctx, WS_VOL0, n * num_d, &cost));
     if (agg_dev == cost) return asw_fail(ctx, ASW_ERR_BAD_ARG, "internal: capture buffer aliases the cost volume%s%s");
-    ASW_TRY(dev_cost_sad_box(ctx, dL, dR, H, W, ASW_DISPARITY_LEFT, win, min_d, num_d, cost, &gref, &gtgt));   // A.cpp:2531-2536
-    ViewGeom v = make_view(dL, dR, H, W, ASW_DISPARITY_LEFT, min_d, num_d);
+    ASW_TRY(dev_cost_sad_box(ctx, dL, dR, H, W, disp_type, win, min_d, num_d, cost, &gref, &gtgt));   // A.cpp:2531-2546
+    ViewGeom v = make_view(dL, dR, H, W, disp_type, min_d, num_d);
     g.H = H; g.W = W; g.Wp = v.Wp; g.win = win; g.h = win / 2; g.D = num_d;
     g.x0_base = v.x0_base; g.x0_step = v.x0_step;
     g.di_lo = di_lo; g.di_hi = di_hi;
@@ -453,7 +455,7 @@ static asw_status dev_blo1_range(asw_ctx* ctx, const uint8_t* dL, const uint8_t*
     }
     return keys_to_disp(ctx, keys, n, disp_dev);
 }
-static asw_status dev_blo1(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double rate_r, int win,
+static asw_status dev_blo1(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type, double rate_r, int win,
                            int min_d, int num_d, float* disp_dev, float* agg_dev) {
-    return dev_blo1_range(ctx, dL, dR, H, W, rate_r, win, min_d, num_d, 0, num_d, disp_dev, agg_dev);
+    return dev_blo1_range(ctx, dL, dR, H, W, disp_type, rate_r, win, min_d, num_d, 0, num_d, disp_dev, agg_dev);
 }

@@ -782,21 +782,25 @@ int orc_asw_bilateral_grid(const uint8_t* L, const uint8_t* R, int H, int W, int
 int orc_asw_blo1(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, double rate_r,
                  int win, int min_d, int num_d, float* disp, float* agg) {
     if (!L || !R || !disp || H <= 0 || W <= 0 || num_d <= 0 || win <= 0) return ORC_BAD_ARG;
-    if (disp_type != 0) return ORC_UNSUPPORTED;
+    if (disp_type != 0 && disp_type != 1) return ORC_BAD_ARG;
     if (min_d != 0) return ORC_UNSUPPORTED;        /* plane index uses 'offset' not offset-min (A.cpp:2666) */
     size_t n = (size_t)H * W;
     int max_off = min_d + num_d - 1;
     int step = (int)(256 * rate_r);                /* A.cpp:2549 */
     if (step <= 0) return ORC_BAD_ARG;             /* the reference would loop forever */
     float* cost = (float*)malloc(n * num_d * sizeof(float));
-    int rc = orc_cost_sad_box(L, R, H, W, min_d, num_d, 0, win, cost);   /* A.cpp:2531-2536 */
+    int rc = orc_cost_sad_box(L, R, H, W, min_d, num_d, disp_type, win, cost);   /* A.cpp:2531-2546 */
     if (rc != ORC_OK) { free(cost); return rc; }
     uint8_t* lg = (uint8_t*)malloc(n);
     uint8_t* rg = (uint8_t*)malloc(n);
     orc_bgr2gray(L, (int)n, lg);
     orc_bgr2gray(R, (int)n, rg);
-    uint8_t* rb = pad_cols_reflect_u8(rg, H, W, 1, max_off, 0);          /* A.cpp:2525 */
+    /* LEFT: reference side = left gray, target = right gray padded on the left, crop at max_off - d (A.cpp:2525, 2578);
+     * RIGHT: reference side = right gray, target = left gray padded on the right, crop at d (A.cpp:2524, 2612) */
+    uint8_t* rb = disp_type == 0 ? pad_cols_reflect_u8(rg, H, W, 1, max_off, 0) : pad_cols_reflect_u8(lg, H, W, 1, 0, max_off);
+    if (disp_type == 1) { uint8_t* t = lg; lg = rg; rg = t; }           /* lg = the reference-side image from here on */
     int Wp = W + max_off;
+#define BLO1_X0(d) (disp_type == 0 ? max_off - (d) : (d))
     int levels[257], nl = 0, is_level[256];
     memset(is_level, 0, sizeof(is_level));
     for (int i = 0; i < 256; i += step) levels[nl++] = i;                /* A.cpp:2550-2555 */
@@ -818,14 +822,14 @@ int orc_asw_blo1(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type
         /* normaliser from the LAST disparity only (A.cpp:2588) */
         for (int y = 0; y < H; y++)
             for (int x = 0; x < W; x++) {
-                float mr = (float)abs((int)rb[(size_t)y * Wp + (max_off - (num_d - 1)) + x] - k);
+                float mr = (float)abs((int)rb[(size_t)y * Wp + BLO1_X0(num_d - 1) + x] - k);
                 m[(size_t)y * W + x] = mr * ml[(size_t)y * W + x];
             }
         orc_box_filter_f32(m, H, W, win, nk);
         for (int d = 0; d < num_d; d++) {
             for (int y = 0; y < H; y++)
                 for (int x = 0; x < W; x++) {
-                    float mr = (float)abs((int)rb[(size_t)y * Wp + (max_off - d) + x] - k);  /* A.cpp:2578 */
+                    float mr = (float)abs((int)rb[(size_t)y * Wp + BLO1_X0(d) + x] - k);     /* A.cpp:2578 / 2612 */
                     float mm = mr * ml[(size_t)y * W + x];                                   /* A.cpp:2580 */
                     m[(size_t)y * W + x] = mm * cost[(size_t)d * n + (size_t)y * W + x];     /* A.cpp:2583 */
                 }
@@ -848,7 +852,8 @@ int orc_asw_blo1(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type
     for (int d = 0; d < num_d; d++)
         for (size_t i = 0; i < n; i++)
             if (!is_level[lg[i]]) q[(size_t)d * n + i] = part_lo[(size_t)d * n + i] + part_hi[(size_t)d * n + i];
-    orc_wta(q, num_d, H, W, min_d, disp);                                            /* A.cpp:2675-2680 */
+#undef BLO1_X0
+    orc_wta(q, num_d, H, W, min_d, disp);                                            /* A.cpp:2675-2680, 2711-2716 */
     if (!agg) free(q);
     free(part_lo); free(part_hi); free(cost); free(lg); free(rg); free(rb);
     return ORC_OK;

@@ -8,13 +8,15 @@
  * --impl reference legs may load it.  The product (aswstereomatch_b200/) never
  * links, imports or calls anything in this directory.
  *
- * Parity pin: the reference ships no tests / golden vectors and cannot be
- * compiled here (needs OpenCV 4.1.0 C++ + MSVC).  The OpenCV-primitive stages
- * of this oracle are pinned bit-exactly against Python cv2 4.13 by
- * oracle/cv2_restatement.py (fixtures in tests/golden/).  The loop-only methods
- * (traditional, geodesic, bilateral grid, weighted median) are "parity
- * unpinned": they follow the reference source line by line but there is no
- * reference-produced output to compare with.
+ * Parity pin: the reference ships no tests / golden vectors.  Every function of
+ * this file is pinned bit-exactly against the reference's OWN code: oracle/_ref/
+ * libasw_ref.so is /root/reference's aswMethods.cpp compiled UNMODIFIED against an
+ * OpenCV stand-in (oracle/refshim/, itself pinned against the real cv2 4.13), see
+ * tests/test_cpu_ref.py and the fixture tests/golden/ref_methods_44x60_d6.npz made
+ * by that library (tools/make_ref_golden.py).  The OpenCV-primitive stages are in
+ * addition pinned against Python cv2 4.13 by oracle/cv2_restatement.py.  Only
+ * stage 4 (LR check / fill / refine) has no reference counterpart: it is our own
+ * specification (its median selection rule and weights are the reference's).
  *
  * Conventions: images are tightly packed, row-major; colour = BGR interleaved
  * u8 (CV_8UC3).  Volumes are [Deval][H][W] float.  disp_type: 0 = DISPARITY_LEFT,

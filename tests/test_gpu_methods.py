@@ -131,6 +131,17 @@ def test_blo1(ctx, H, W, D, win, seed):
     assert (d == d_ref).mean() >= AGREE
 
 
+@pytest.mark.parametrize("H,W,D,win,seed", [(40, 56, 8, 7, 17), (70, 100, 8, 35, 13), (50, 300, 20, 15, 14), (48, 64, 8, 11, 16)])
+def test_blo1_right(ctx, H, W, D, win, seed):
+    """DISPARITY_RIGHT (A.cpp:2538-2546, 2600-2631, 2685-2722): the reference defines it; templated and tiled kernels"""
+    L, R, _ = make_pair(H, W, D, seed)
+    d, q = ctx.computeAdaptiveWeight_BLO1(L, R, 1, 0.015, win, 0, D, agg=True, strict=True)
+    d_ref, q_ref = orc.asw_blo1(L, R, 1, 0.015, win, 0, D, agg=True)
+    assert rel_err(q, q_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+    assert np.array_equal(ctx.stereoMatching(L, R, 1, asw.ADAPTIVE_WEIGHT_BLO1, win, 0, D, strict=True), d)
+
+
 def test_blo1_golden(ctx):
     g = np.load("tests/golden/cv2_stages_40x56_d8.npz")
     d, q = ctx.computeAdaptiveWeight_BLO1(g["L"], g["R"], 0, 0.015, 7, 0, 8, agg=True, strict=True)
