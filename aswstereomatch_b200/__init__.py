@@ -6,4 +6,4 @@ libasw_b200.so); this package is its host-side mirror of the reference's method 
 from .api import (ADAPTIVE_WEIGHT, ADAPTIVE_WEIGHT_8DIRECT, ADAPTIVE_WEIGHT_BILATERAL_GRID, ADAPTIVE_WEIGHT_BLO1,  # noqa: F401
                   ADAPTIVE_WEIGHT_GEODESIC, ADAPTIVE_WEIGHT_GUIDED_FILTER, ADAPTIVE_WEIGHT_GUIDED_FILTER_2,
                   ADAPTIVE_WEIGHT_GUIDED_FILTER_3, ADAPTIVE_WEIGHT_MEDIAN, BM, DISPARITY_LEFT, DISPARITY_RIGHT, NCC, SGBM,
-                  AswError, Batch, Context, EXPORTS, LIB_PATH, load_library, method_candidates, pinned_empty)
+                  AswError, Batch, Context, EXPORTS, Pool, LIB_PATH, load_library, method_candidates, pinned_empty)

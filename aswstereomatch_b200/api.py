@@ -56,7 +56,9 @@ EXPORTS = [
     "asw_geodesic_dist", "asw_lr_check", "asw_fill_invalid", "asw_wmedian_refine", "asw_guidedf2_lr_refine",
     "asw_batch_create", "asw_batch_destroy", "asw_batch_set_active", "asw_batch_upload", "asw_batch_run_guidedf2_lr_refine",
     "asw_batch_run_method", "asw_batch_download", "asw_split_local_keys", "asw_keys_alloc", "asw_keys_download",
-    "asw_keys_upload", "asw_keys_min_merge", "asw_keys_to_disparity", "asw_timer_start", "asw_timer_stop",
+    "asw_keys_upload", "asw_keys_min_merge", "asw_keys_to_disparity", "asw_keys_flip_sign", "asw_pool_create",
+    "asw_pool_destroy", "asw_pool_size", "asw_pool_last_error", "asw_pool_ctx", "asw_stereo_matching_batch",
+    "asw_guidedf2_lr_refine_batch", "asw_stereo_matching_split", "asw_pool_last_allreduce_ms", "asw_timer_start", "asw_timer_stop",
     "asw_profile_enable", "asw_profile_reset", "asw_profile_count", "asw_profile_entry", "asw_launch_count",
     "asw_flush_l2",
 ]
@@ -117,6 +119,16 @@ def load_library():
         "asw_keys_upload": (ci, [vp, vp, ci, ci, vp]),
         "asw_keys_min_merge": (ci, [vp, vp, vp, ci, ci]),
         "asw_keys_to_disparity": (ci, [vp, vp, pf32]),
+        "asw_keys_flip_sign": (ci, [vp, vp, ci, ci]),
+        "asw_pool_create": (ci, [ci, C.POINTER(vp)]),
+        "asw_pool_destroy": (None, [vp]),
+        "asw_pool_size": (ci, [vp]),
+        "asw_pool_last_error": (C.c_char_p, [vp]),
+        "asw_pool_ctx": (vp, [vp, ci]),
+        "asw_stereo_matching_batch": (ci, [vp, ci, pu8, pu8, pf32, ci, ci, ci, ci, ci]),
+        "asw_guidedf2_lr_refine_batch": (ci, [vp, ci, pu8, pu8, pf32, cd, ci, ci, ci, cf, cd, cd]),
+        "asw_stereo_matching_split": (ci, [vp, pu8, pu8, pf32, ci, ci, ci, ci, ci]),
+        "asw_pool_last_allreduce_ms": (cf, [vp]),
         "asw_timer_start": (ci, [vp]),
         "asw_timer_stop": (ci, [vp, C.POINTER(cf)]),
         "asw_profile_enable": (ci, [vp, ci]),
@@ -374,6 +386,25 @@ class Context:
         self._chk(self.lib.asw_keys_download(self.h, dk, H, W, keys.ctypes.data))
         return keys, dk
 
+    def split_local_keys_device(self, L, R, algorithm, disp_type, win, min_d, num_d, d_begin, d_end):
+        """as split_local_keys, but the keys stay in device memory: returns the device pointer (valid until the next call
+        that touches the ctx's key workspace)"""
+        La, Ls = _u8(L)
+        Ra, Rs = _u8(R)
+        dk = C.c_void_p()
+        self._chk(self.lib.asw_split_local_keys(self.h, C.byref(Ls), C.byref(Rs), int(algorithm), int(disp_type),
+                                                int(win), int(min_d), int(num_d), int(d_begin), int(d_end),
+                                                C.byref(dk)))
+        return dk, La.shape[:2]
+
+    def keys_flip_sign(self, dk, H, W):
+        self._chk(self.lib.asw_keys_flip_sign(self.h, dk, int(H), int(W)))
+
+    def device_keys_to_disparity(self, dk, H, W):
+        out, outs = _f32_out(H, W)
+        self._chk(self.lib.asw_keys_to_disparity(self.h, dk, C.byref(outs)))
+        return out
+
     def keys_to_disparity(self, keys):
         keys = np.ascontiguousarray(keys, dtype=np.uint64)
         H, W = keys.shape
@@ -486,6 +517,77 @@ class Batch:
         if sync:
             self.ctx.sync()
         return out
+
+
+class Pool:
+    """Every device of the box behind one handle (asw_pool): pair-sharded batches and the disparity-range split of one
+    pair with an NCCL MIN all-reduce of the device-resident keys.  Single process, one host thread per device inside
+    the library (the torchrun path of bench.py uses one Context per process instead)."""
+
+    def __init__(self, n_devices=0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.asw_pool_create(int(n_devices), C.byref(h))
+        if st != ASW_OK:
+            raise AswError(st, "asw_pool_create failed: not enough usable CUDA devices (there is no CPU fallback)")
+        self.h = h
+        self.size = int(self.lib.asw_pool_size(h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.asw_pool_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, st):
+        if st != ASW_OK:
+            raise AswError(st, self.lib.asw_pool_last_error(self.h).decode())
+
+    @staticmethod
+    def _arrays(Ls, Rs):
+        n = len(Ls)
+        keep, la, ra = [], (U8Image * n)(), (U8Image * n)()
+        for i in range(n):
+            a, la[i] = _u8(Ls[i])
+            b, ra[i] = _u8(Rs[i])
+            keep += [a, b]
+        H, W = keep[0].shape[:2]
+        outs = [np.empty((H, W), np.float32) for _ in range(n)]
+        da = (F32Image * n)()
+        for i in range(n):
+            da[i] = F32Image(outs[i].ctypes.data, H, W, outs[i].strides[0])
+        return n, keep, la, ra, outs, da
+
+    def stereoMatchingBatch(self, Ls, Rs, disparityType, algorithmType, winSize=15, minDisparity=0, numDisparity=64):
+        """stereoMatching (A.h:91-92) for a list of pairs, pair i on device i % n"""
+        n, keep, la, ra, outs, da = self._arrays(Ls, Rs)
+        self._chk(self.lib.asw_stereo_matching_batch(self.h, n, la, ra, da, int(disparityType), int(algorithmType),
+                                                     int(winSize), int(minDisparity), int(numDisparity)))
+        return outs
+
+    def guidedf2_lr_refine_batch(self, Ls, Rs, eps=1e-4, win=9, min_d=0, num_d=64, tol=0.0, rate_s=10.0, rate_r=10.0):
+        n, keep, la, ra, outs, da = self._arrays(Ls, Rs)
+        self._chk(self.lib.asw_guidedf2_lr_refine_batch(self.h, n, la, ra, da, float(eps), int(win), int(min_d),
+                                                        int(num_d), float(tol), float(rate_s), float(rate_r)))
+        return outs
+
+    def stereoMatchingSplit(self, L, R, disparityType, algorithmType, winSize=15, minDisparity=0, numDisparity=64):
+        """one pair, its candidate range split over the devices, NCCL MIN all-reduce of the keys"""
+        La, Ls = _u8(L)
+        Ra, Rs = _u8(R)
+        out, outs = _f32_out(*La.shape[:2])
+        self._chk(self.lib.asw_stereo_matching_split(self.h, C.byref(Ls), C.byref(Rs), C.byref(outs), int(disparityType),
+                                                     int(algorithmType), int(winSize), int(minDisparity),
+                                                     int(numDisparity)))
+        return out
+
+    def last_allreduce_ms(self):
+        return float(self.lib.asw_pool_last_allreduce_ms(self.h))
 
 
 def pinned_empty(shape, dtype):

@@ -595,3 +595,4 @@ static asw_status dev_guidedf2_lr_refine(asw_ctx* ctx, const uint8_t* dL, const 
 #include "k_blo1.cuh"
 #include "k_wmedian.cuh"
 #include "asw_methods.inl"
+#include "asw_pool.inl"

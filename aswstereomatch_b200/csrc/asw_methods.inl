@@ -435,9 +435,10 @@ extern "C" asw_status asw_batch_download(asw_batch* b, int i, asw_f32_image* dis
 // -------------------------------------------------------------------------------------------------
 // disparity-range split (multi-GPU): local keys for [d_begin, d_end), merge, finalise
 // -------------------------------------------------------------------------------------------------
-extern "C" asw_status asw_split_local_keys(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, int algorithm,
-                                           int disp_type, int win, int min_d, int num_d, int d_begin, int d_end,
-                                           void** device_keys) {
+// device part of the split: keys of candidates [d_begin, d_end) left in WS_KEYS (asynchronous on the ctx stream)
+static asw_status split_local_keys_dev(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, int algorithm,
+                                       int disp_type, int win, int min_d, int num_d, int d_begin, int d_end,
+                                       void** device_keys) {
     ASW_TRY(check_pair(ctx, L, R, nullptr));
     if (!device_keys) return ASW_ERR_BAD_ARG;
     MethodArgs m;
@@ -448,6 +449,7 @@ extern "C" asw_status asw_split_local_keys(asw_ctx* ctx, const asw_u8_image* L, 
     // reference loop runs to max_offset inclusive (traditional, geodesic, grid)
     if (m.id != M_GF2 && m.id != M_TRAD && m.id != M_GEO && m.id != M_GRID && m.id != M_BLO1)
         return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "disparity split is not implemented for this method%s%s");
+    if (m.id == M_GF2 && disp_type == 1) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "GuidedF_2 DISPARITY_RIGHT throws in the reference%s%s");
     if (d_begin < 0 || d_end > method_n_eval(m) || d_begin > d_end) return asw_fail(ctx, ASW_ERR_BAD_ARG, "bad disparity range%s%s");
     ASW_CUDA(ctx, cudaSetDevice(ctx->device));
     int H = L->rows, W = L->cols; size_t n = (size_t)H * W;
@@ -472,8 +474,27 @@ extern "C" asw_status asw_split_local_keys(asw_ctx* ctx, const asw_u8_image* L, 
             else ASW_TRY(dev_blo1_range(ctx, dL, dR, H, W, disp_type, m.p0, win, min_d, num_d, d_begin, d_end, tmp, nullptr));
         }
     }
-    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     *device_keys = keys;
+    return ASW_OK;
+}
+extern "C" asw_status asw_split_local_keys(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, int algorithm,
+                                           int disp_type, int win, int min_d, int num_d, int d_begin, int d_end,
+                                           void** device_keys) {
+    ASW_TRY(split_local_keys_dev(ctx, L, R, algorithm, disp_type, win, min_d, num_d, d_begin, d_end, device_keys));
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ASW_OK;
+}
+// in-place x ^= 1 << 63 on a device key buffer: the order-preserving map u64 <-> i64 for collectives that only know signed
+// 64-bit MIN (torch.distributed); asynchronous on the ctx stream
+__global__ void k_keys_flip_sign(unsigned long long* k, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) k[i] ^= 0x8000000000000000ull;
+}
+extern "C" asw_status asw_keys_flip_sign(asw_ctx* ctx, void* device_keys, int rows, int cols) {
+    if (!ctx || !device_keys || rows <= 0 || cols <= 0) return ASW_ERR_BAD_ARG;
+    ASW_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t n = (size_t)rows * cols;
+    LAUNCH(ctx, "keys_flip_sign", (k_keys_flip_sign<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((unsigned long long*)device_keys, n)));
     return ASW_OK;
 }
 extern "C" asw_status asw_keys_alloc(asw_ctx* ctx, int rows, int cols, void** device_keys) {

@@ -42,11 +42,45 @@ def allreduce_min_keys(keys_u64, device=None):
     return keys_from_i64(t.cpu().numpy())
 
 
+class _DevKeys:
+    """a device key buffer as a torch-readable CUDA array (int64 view of the u64 keys)"""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
+def allreduce_min_keys_device(ctx, dk, H, W, device):
+    """MIN all-reduce of the ctx's device-resident u64 keys over the default process group (NCCL), IN PLACE: the keys never
+    leave device memory.  torch.distributed has no unsigned 64-bit MIN, so the sign bit is flipped on the device before
+    and after (asw_keys_flip_sign: order-preserving u64 <-> i64) and NCCL reduces the buffer through an int64 alias."""
+    import torch
+    import torch.distributed as dist
+    ctx.keys_flip_sign(dk, H, W)
+    ctx.sync()                                   # the library's stream -> torch's stream
+    t = torch.as_tensor(_DevKeys(dk.value, H * W), device=device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    e1.record()
+    torch.cuda.synchronize(device)
+    ctx.keys_flip_sign(dk, H, W)
+    return e0.elapsed_time(e1)               # device time of the collective on this rank, ms
+
+
 def split_stereo_matching(ctx, L, R, algorithm, disp_type, win, min_d, num_d, rank, world, device=None):
-    """disparity-split of one pair across the process group; every rank returns the full disparity map"""
+    """disparity-split of one pair across the process group; every rank returns the full disparity map.
+    With a CUDA `device` the keys are reduced in device memory (NCCL, no host bounce); without one (gloo, CPU tests)
+    they travel through the host."""
     from .api import method_candidates
     # the candidates the method really scans: numDisparity + 1 for traditional / geodesic / grid (loop `<=`)
     lo, hi = split_range(method_candidates(algorithm, num_d), rank, world)
+    if device is not None:
+        dk, (H, W) = ctx.split_local_keys_device(L, R, algorithm, disp_type, win, min_d, num_d, lo, hi)
+        split_stereo_matching.last_allreduce_ms = allreduce_min_keys_device(ctx, dk, H, W, device)
+        return ctx.device_keys_to_disparity(dk, H, W)
     keys, _ = ctx.split_local_keys(L, R, algorithm, disp_type, win, min_d, num_d, lo, hi)
-    merged = allreduce_min_keys(keys, device)
+    merged = allreduce_min_keys(keys, None)
     return ctx.keys_to_disparity(merged)
+
+
+split_stereo_matching.last_allreduce_ms = None

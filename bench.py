@@ -345,9 +345,54 @@ def main():
 
 
 def bench_split(ctx, asw, dist, torch, rank, world, local_rank, args):
-    """disparity-range split of ONE 1080p x 256 GuidedF_2 pair over the ranks: filled in by the
-    device-resident split path"""
-    return None
+    """disparity-range split of ONE 1080p x 256 GuidedF_2 pair (the dispatcher call, left view) over the ranks
+    (SURVEY 8e-2): every rank evaluates D / N slices, the u64 keys are MIN-all-reduced in device memory over NCCL, every
+    rank converts them to the map.  Timed through the C ABI with host buffers (upload of the pair, kernels, collective,
+    download of the map), max over ranks; at N = 1 the same call unsplit."""
+    from aswstereomatch_b200 import sharding
+    from aswstereomatch_b200.synth import make_pair
+    L, R, _ = make_pair(H, W, D, 1000)
+    alg = asw.ADAPTIVE_WEIGHT_GUIDED_FILTER_2
+    dev = torch.device("cuda", local_rank) if world > 1 else None
+
+    def one():
+        if world == 1:
+            return ctx.stereoMatching(L, R, 0, alg, WIN, 0, D, strict=True)
+        return sharding.split_stereo_matching(ctx, L, R, alg, 0, WIN, 0, D, rank, world, device=dev)
+
+    def sync_all():
+        ctx.sync()
+        if dist is not None:
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    out = None
+    for _ in range(max(args.warmup, 2)):
+        out = one()
+    times, ar = [], []
+    for _ in range(max(args.steps, 3)):
+        sync_all()
+        t0 = time.perf_counter()
+        out = one()
+        ctx.sync()
+        dt = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            t = torch.tensor([dt, sharding.split_stereo_matching.last_allreduce_ms or 0.0], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt, a = float(t[0].item()), float(t[1].item())
+            ar.append(a)
+        times.append(dt)
+    res = {"what": f"one {W}x{H} pair, D={D}, GuidedF_2 (dispatcher, left view) disparity-split over {world} rank(s), "
+                   "host buffers in and out, max over ranks", "ms": float(np.median(times)),
+           "allreduce_ms": float(np.median(ar)) if ar else 0.0, "slices_per_rank": -(-D // world),
+           "mde_s": H * W * D / 1e6 / (float(np.median(times)) * 1e-3)}
+    if world > 1:
+        # every rank holds the same merged map; rank 0 also checks it against its own unsplit run
+        if rank == 0:
+            res["bit_identical_to_unsplit"] = bool(np.array_equal(out, ctx.stereoMatching(L, R, 0, alg, WIN, 0, D, strict=True)))
+        sync_all()
+    return res
 
 
 if __name__ == "__main__":

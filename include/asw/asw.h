@@ -180,6 +180,35 @@ asw_status asw_keys_upload(asw_ctx* ctx, const uint64_t* host_keys, int rows, in
 asw_status asw_keys_min_merge(asw_ctx* ctx, void* device_keys_inout, const void* device_keys_other,
                               int rows, int cols);
 asw_status asw_keys_to_disparity(asw_ctx* ctx, const void* device_keys, asw_f32_image* disparity);
+/* in-place key ^= 1 << 63 on the device (asynchronous on the ctx stream): the order-preserving map u64 <-> i64, for
+ * hosts whose collective only offers a signed 64-bit MIN (torch.distributed); apply before and after the all-reduce */
+asw_status asw_keys_flip_sign(asw_ctx* ctx, void* device_keys, int rows, int cols);
+
+/* ---- device pool: the multi-GPU face of stereoMatching (A.h:91-92) for C / C++ hosts ----
+ * One asw_ctx per device, one host thread per device inside every call.  n_devices = 0 takes every device of the box. */
+typedef struct asw_pool asw_pool;
+asw_status asw_pool_create(int n_devices, asw_pool** out);
+void asw_pool_destroy(asw_pool* pool);
+int asw_pool_size(const asw_pool* pool);
+const char* asw_pool_last_error(const asw_pool* pool);
+asw_ctx* asw_pool_ctx(asw_pool* pool, int device);              /* the pool's ctx of a device (owned by the pool) */
+/* pair sharding (config 5): pair i runs on device i % n through the dispatcher (A.cpp:46-88), no collective.  All pairs
+ * of one call have the same size.  Arrays of n_pairs images; host pointers, caller-owned. */
+asw_status asw_stereo_matching_batch(asw_pool* pool, int n_pairs, const asw_u8_image* left, const asw_u8_image* right,
+                                     asw_f32_image* disparity, int disparity_type, int algorithm_type, int win_size,
+                                     int min_disparity, int num_disparity);
+/* the same sharding for the full frame of configs 2 / 5 (asw_guidedf2_lr_refine per pair) */
+asw_status asw_guidedf2_lr_refine_batch(asw_pool* pool, int n_pairs, const asw_u8_image* left, const asw_u8_image* right,
+                                        asw_f32_image* refined, double eps, int win_size, int min_disparity,
+                                        int num_disparity, float lr_tol, double rate_s, double rate_r);
+/* disparity-range split of ONE pair over the pool's devices: device g evaluates its share of the method's candidates
+ * (asw_method_candidates), the u64 keys are MIN-all-reduced in device memory with ncclAllReduce(ncclMin, ncclUint64)
+ * over NVLink (libnccl.so.2 is bound at run time; ASW_ERR_UNSUPPORTED without it), device 0 returns the map.
+ * Bit-identical to the single-device call for every method that supports the split (see asw_split_local_keys). */
+asw_status asw_stereo_matching_split(asw_pool* pool, const asw_u8_image* left, const asw_u8_image* right,
+                                     asw_f32_image* disparity, int disparity_type, int algorithm_type, int win_size,
+                                     int min_disparity, int num_disparity);
+float asw_pool_last_allreduce_ms(const asw_pool* pool);        /* device time of the last split's all-reduce (device 0) */
 
 /* ---- measurement hooks (CUDA events on the ctx stream) ---- */
 asw_status asw_timer_start(asw_ctx* ctx);
