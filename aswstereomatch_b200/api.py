@@ -49,8 +49,8 @@ class MaskImage(C.Structure):
 # every symbol include/asw/asw.h declares (tests check the library exports all of them)
 EXPORTS = [
     "asw_device_count", "asw_create", "asw_destroy", "asw_last_error", "asw_version", "asw_sync", "asw_stream",
-    "asw_host_alloc", "asw_host_free", "asw_stereo_matching", "asw_method_candidates", "asw_adaptive_weight",
-    "asw_adaptive_weight_geodesic", "asw_adaptive_weight_bilateral_grid", "asw_adaptive_weight_blo1",
+    "asw_set_tuning", "asw_host_alloc", "asw_host_free", "asw_stereo_matching", "asw_method_candidates", "asw_adaptive_weight",
+    "asw_adaptive_weight_direct8", "asw_adaptive_weight_geodesic", "asw_adaptive_weight_bilateral_grid", "asw_adaptive_weight_blo1",
     "asw_adaptive_weight_guidedf", "asw_adaptive_weight_guidedf_2", "asw_adaptive_weight_weighted_median",
     "asw_capture_aggregated", "asw_cost_tad_cg", "asw_cost_sad_box", "asw_wta", "asw_guided_filter",
     "asw_geodesic_dist", "asw_lr_check", "asw_fill_invalid", "asw_wmedian_refine", "asw_guidedf2_lr_refine",
@@ -85,11 +85,13 @@ def load_library():
         "asw_version": (C.c_char_p, []),
         "asw_sync": (ci, [vp]),
         "asw_stream": (vp, [vp]),
+        "asw_set_tuning": (ci, [vp, ci, ci]),
         "asw_host_alloc": (vp, [C.c_size_t]),
         "asw_host_free": (None, [vp]),
         "asw_stereo_matching": (ci, [vp, pu8, pu8, pf32, ci, ci, ci, ci, ci]),
         "asw_method_candidates": (ci, [ci, ci]),
         "asw_adaptive_weight": (ci, [vp, pu8, pu8, pf32, cd, cd, ci, ci, ci, ci]),
+        "asw_adaptive_weight_direct8": (ci, [vp, pu8, pu8, pf32, ci, ci, ci, ci]),
         "asw_adaptive_weight_geodesic": (ci, [vp, pu8, pu8, pf32, ci, ci, ci, ci]),
         "asw_adaptive_weight_bilateral_grid": (ci, [vp, pu8, pu8, pf32, ci, cd, cd, ci, ci]),
         "asw_adaptive_weight_blo1": (ci, [vp, pu8, pu8, pf32, ci, cd, ci, ci, ci]),
@@ -248,6 +250,12 @@ class Context:
         return self._method(self.lib.asw_adaptive_weight, leftImg, rightImg,
                             (float(gamma_c), float(gamma_g), int(dispType), int(winSize), int(minDisparity),
                              int(numDisparity)), numDisparity + 1, agg, strict)
+
+    def computeAdaptiveWeight_direct8(self, leftImg, rightImg, dispType=DISPARITY_LEFT, winSize=7, minDisparity=186,
+                                      numDisparity=144, agg=False, strict=False):
+        return self._method(self.lib.asw_adaptive_weight_direct8, leftImg, rightImg,
+                            (int(dispType), int(winSize), int(minDisparity), int(numDisparity)),
+                            numDisparity + 1, agg, strict)
 
     def computeAdaptiveWeight_geodesic(self, leftImg, rightImg, dispType=DISPARITY_LEFT, winSize=7,
                                        minDisparity=186, numDisparity=144, agg=False, strict=False):
@@ -427,6 +435,16 @@ class Context:
         out, outs = _f32_out(H, W)
         self._chk(self.lib.asw_keys_to_disparity(self.h, dk, C.byref(outs)))
         return out
+
+    # ---- tuning knobs (asw_set_tuning): 0 restores the built-in choice ----
+    TUNE_GFS_BANDS, TUNE_BLO_DCH, TUNE_GF_CHUNK_MB = 0, 1, 2
+
+    def set_tuning(self, key, value):
+        self._chk(self.lib.asw_set_tuning(self.h, int(key), int(value)))
+
+    def has_dev_kernels(self):
+        """True when the library was built with -DASW_DEV_KERNELS (superseded kernels selectable through ASW_* variables)"""
+        return b"+dev-kernels" in self.lib.asw_version()
 
     # ---- measurement ----
     def sync(self):

@@ -13,9 +13,20 @@
 
 #define ASW_MAX_PROFILE 48
 
+// Superseded kernels (kept for A/B measurements) are compiled, and selectable through ASW_* environment variables, only
+// with -DASW_DEV_KERNELS.  The product build contains one path per method plus the size-generic fallbacks and never
+// reads the environment.
+#ifdef ASW_DEV_KERNELS
+#include <stdlib.h>
+static inline bool asw_dev(const char* name) { return getenv(name) != nullptr; }
+#else
+#define asw_dev(name) false
+#endif
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    unsigned gen = 0;          // bumped on every (re)allocation: cached contents are keyed on it
 };
 
 struct ProfEntry {
@@ -48,6 +59,10 @@ struct asw_ctx {
     // pinned staging for small D2H results
     void* pinned = nullptr;
     size_t pinned_cap = 0;
+    // tuning knobs (asw_set_tuning; 0 = the built-in choice)
+    int tune[ASW_TUNE_COUNT] = {0};
+    // host-built tables are cached per parameter set: nothing is uploaded (and nothing synchronises) on a repeated call
+    std::string table_key[4];
 };
 
 // workspace slots
@@ -56,7 +71,8 @@ enum {
     WS_TMP0, WS_TMP1, WS_TMP2, WS_TMP3, WS_VOL0, WS_VOL1, WS_AB, WS_KEYS, WS_KEYS2, WS_DISP_L, WS_DISP_R,
     WS_MASK, WS_FILLED, WS_OUT, WS_SLICE_MM, WS_GRAY_L, WS_GRAY_R, WS_GEO_L, WS_GEO_R, WS_GRID_S, WS_GRID_C,
     WS_TABLE0, WS_TABLE1, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3, WS_CAPTURE, WS_GUIDE_RDEN,
-    WS_FEATF_REF, WS_FEATF_TGT, WS_GUIDE_NM, WS_GUIDE_RD2, WS_AFF, WS_REFINE_LIST, WS_COUNT
+    WS_FEATF_REF, WS_FEATF_TGT, WS_GUIDE_NM, WS_GUIDE_RD2, WS_AFF, WS_REFINE_LIST,
+    WS_TRAD_C2, WS_TRAD_TABLE, WS_GRID_TI, WS_GRID_TD, WS_COUNT
 };
 
 static inline asw_status asw_fail(asw_ctx* ctx, asw_status st, const char* fmt, const char* a = "", const char* b = "") {
@@ -78,6 +94,15 @@ static inline asw_status asw_fail(asw_ctx* ctx, asw_status st, const char* fmt, 
         if (s__ != ASW_OK) return s__;       \
     } while (0)
 
+// cached host-built table: true when slot `ks` already holds the table described by `what` (same buffer generation)
+static inline bool table_cached(asw_ctx* ctx, int ks, int ws_slot, const char* what) {
+    char key[160];
+    snprintf(key, sizeof(key), "%u|%s", ctx->bufs[ws_slot].gen, what);
+    if (ctx->table_key[ks] == key) return true;
+    ctx->table_key[ks] = key;
+    return false;
+}
+
 // reserve a workspace slot (grow-only; contents undefined after growth)
 static inline asw_status ws_reserve(asw_ctx* ctx, int slot, size_t bytes, void** out) {
     if ((int)ctx->bufs.size() < WS_COUNT) ctx->bufs.resize(WS_COUNT);
@@ -95,6 +120,7 @@ static inline asw_status ws_reserve(asw_ctx* ctx, int slot, size_t bytes, void**
             return asw_fail(ctx, ASW_ERR_NOMEM, "cudaMalloc failed: %s", cudaGetErrorString(e));
         }
         b.cap = cap;
+        b.gen++;
     }
     *out = b.p;
     return ASW_OK;

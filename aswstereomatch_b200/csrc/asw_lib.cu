@@ -20,7 +20,16 @@ extern "C" int asw_device_count(void) {
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
     return n;
 }
-extern "C" const char* asw_version(void) { return "aswstereomatch_b200 0.1 (sm_100a)"; }
+#ifdef ASW_DEV_KERNELS
+extern "C" const char* asw_version(void) { return "aswstereomatch_b200 0.2 (sm_100a) +dev-kernels"; }
+#else
+extern "C" const char* asw_version(void) { return "aswstereomatch_b200 0.2 (sm_100a)"; }
+#endif
+extern "C" asw_status asw_set_tuning(asw_ctx* ctx, int key, int value) {
+    if (!ctx || key < 0 || key >= ASW_TUNE_COUNT || value < 0) return ASW_ERR_BAD_ARG;
+    ctx->tune[key] = value;
+    return ASW_OK;
+}
 
 extern "C" asw_status asw_create(int device, asw_ctx** out) {
     if (!out) return ASW_ERR_BAD_ARG;
@@ -293,11 +302,10 @@ static size_t gf_smem_bytes(int k) {
     int IW = GF_TW + k - 1, IH = GF_TH + k - 1;
     return ((size_t)IH * (IW | 1) + (size_t)IH * GF_HP) * sizeof(float4);
 }
-static int gf_chunk_slices(size_t n) {
+static int gf_chunk_slices(asw_ctx* ctx, size_t n) {
     // keep one chunk's a/b planes (16 B per DE) inside the 126 MB L2 so pass 2 reads them from L2
     size_t budget = (size_t)64 << 20;
-    const char* e = getenv("ASW_GF_CHUNK_MB");
-    if (e && atoi(e) > 0) budget = (size_t)atoi(e) << 20;
+    if (ctx->tune[ASW_TUNE_GF_CHUNK_MB] > 0) budget = (size_t)ctx->tune[ASW_TUNE_GF_CHUNK_MB] << 20;
     size_t s = budget / (n * 16);
     if (s < 1) s = 1;
     return (int)s;
@@ -313,7 +321,7 @@ static int gfs_chunk_slices(int H, int W, int win, int span) {
     return (int)std::min<size_t>((size_t)span, std::max<size_t>(GFS_NS, GFS_Q_BUDGET / (per_slice * 4) / GFS_NS * GFS_NS));
 }
 static bool gfs_streaming(int H, int W, int win) {
-    return gfs_supported(H, W, win) && !getenv("ASW_GF_TILED") && !getenv("ASW_GF_GENERIC");
+    return gfs_supported(H, W, win) && !asw_dev("ASW_GF_TILED") && !asw_dev("ASW_GF_GENERIC");
 }
 // disp_direct (optional): when the range is the method's whole range and one chunk holds it, the streaming path's WTA
 // pass writes the disparity map itself; *direct_done tells the caller (who then needs neither keys nor keys_to_disp).
@@ -379,15 +387,15 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
         }
         return ASW_OK;
     }
-    if ((win == 5 || win == 7 || win == 9) && !getenv("ASW_GF_GENERIC")) {
+#ifdef ASW_DEV_KERNELS   // the tiled pair of k_guided_fast.cuh: superseded by the streaming kernel
+    if ((win == 5 || win == 7 || win == 9) && !asw_dev("ASW_GF_GENERIC")) {
         // tuned kernels (k_guided_fast.cuh): fixed 32x64 input tile, register-resident reference-side data
         const int DC1 = 8;
         float4* grd;
         ASW_TRY(ws_get(ctx, WS_GUIDE_RDEN, n, &grd));
         LAUNCH(ctx, "reciprocal4", (k_reciprocal4<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(gp.Gd, n, grd)));
         size_t budget = (size_t)16 << 30;                 // a/b workspace budget (16 B per disparity evaluation)
-        const char* e = getenv("ASW_GF_CHUNK_MB");
-        if (e && atoi(e) > 0) budget = (size_t)atoi(e) << 20;
+        if (ctx->tune[ASW_TUNE_GF_CHUNK_MB] > 0) budget = (size_t)ctx->tune[ASW_TUNE_GF_CHUNK_MB] << 20;
         int span = d_hi - d_lo;
         int chunk = (int)(budget / (n * 16));
         if (chunk < DC1) chunk = DC1;
@@ -407,8 +415,9 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
         }
         return ASW_OK;
     }
+#endif
     const int DC = 4;
-    int chunk = gf_chunk_slices(n);
+    int chunk = gf_chunk_slices(ctx, n);
     chunk = ((chunk + DC - 1) / DC) * DC;
     int span = d_hi - d_lo;
     if (chunk > span) chunk = ((span + DC - 1) / DC) * DC;
@@ -538,7 +547,7 @@ static asw_status dev_lr_refine(asw_ctx* ctx, const uint8_t* dL, const float* dl
     float alpha_s = (float)((1.0 / rate_s) * (-1));
     const size_t ne = (size_t)win * win, n = (size_t)H * W;
     const int bt = (ne * (2 * 64 + 1)) * sizeof(float) <= 96 * 1024 ? 64 : (ne * (2 * 32 + 1)) * sizeof(float) <= 96 * 1024 ? 32 : 0;
-    const bool listed = bt && n < ((size_t)1 << 31) && !getenv("ASW_REFINE_DENSE");
+    const bool listed = bt && n < ((size_t)1 << 31) && !asw_dev("ASW_REFINE_DENSE");
     if (listed && W <= 48 * 1024) {
         int* list;
         ASW_TRY(ws_get(ctx, WS_REFINE_LIST, n + 1, &list));               // list[0] = count

@@ -187,13 +187,13 @@ extern "C" asw_status asw_guidedf2_lr_refine(asw_ctx* ctx, const asw_u8_image* L
 // -------------------------------------------------------------------------------------------------
 // per-method entry points
 // -------------------------------------------------------------------------------------------------
-enum MethodId { M_TRAD, M_GEO, M_GRID, M_BLO1, M_GF1, M_GF2, M_WMED };
+enum MethodId { M_TRAD, M_GEO, M_GRID, M_BLO1, M_GF1, M_GF2, M_WMED, M_D8 };
 struct MethodArgs {
     int id, disp_type, win, min_d, num_d;
     double p0, p1;   // method-specific: (gamma_c, gamma_g) | (rate_s, rate_r) | (rate_r) | (eps)
 };
 static int method_n_eval(const MethodArgs& m) {
-    return (m.id == M_TRAD || m.id == M_GEO || m.id == M_GRID) ? m.num_d + 1 : m.num_d;
+    return (m.id == M_TRAD || m.id == M_GEO || m.id == M_GRID || m.id == M_D8) ? m.num_d + 1 : m.num_d;
 }
 // argument checks mirroring the reference's early-outs (SURVEY 8b "errors")
 static asw_status method_check(asw_ctx* ctx, const MethodArgs& m) {
@@ -206,7 +206,8 @@ static asw_status method_check(asw_ctx* ctx, const MethodArgs& m) {
     // tests/test_cpu_ref.py), the grid reads out of bounds (A-7).  GuidedF_2 RIGHT is offered only through the explicit
     // LR pipeline (asw_guidedf2_lr_refine), with the mirrored-LEFT cost.  BLO(1), traditional, geodesic and GuidedF
     // define RIGHT (A.cpp:2538-2546, 2600-2631, 2685-2722 for BLO(1)).
-    if (m.disp_type == 1 && (m.id == M_GRID || m.id == M_WMED))
+    // The 8-direction method's RIGHT branch indexes its weight lists out of bounds (A.cpp:1291: [i] for [count]).
+    if (m.disp_type == 1 && (m.id == M_GRID || m.id == M_WMED || m.id == M_D8))
         return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "DISPARITY_RIGHT is undefined for this method in the reference%s%s");
     if (m.id == M_BLO1 && m.min_d != 0)
         return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "BLO1 indexes planes by offset (A.cpp:2666): minDisparity must be 0%s%s");
@@ -218,6 +219,9 @@ static asw_status dev_run_method(asw_ctx* ctx, const MethodArgs& m, const uint8_
     case M_GF2: return dev_guidedf2(ctx, dL, dR, H, W, m.disp_type, m.p0, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
     case M_GF1: return dev_guidedf(ctx, dL, dR, H, W, m.disp_type, m.p0, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
     case M_TRAD: return dev_traditional(ctx, dL, dR, H, W, m.p0, m.p1, m.disp_type, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
+    case M_D8:    // gamma_c = 30, gamma_g = win * 2 / 3 in integer arithmetic (A.cpp:1175)
+        if (m.win * 2 / 3 == 0) return asw_fail(ctx, ASW_ERR_BAD_ARG, "8-direction ASW: window too small (gamma_g = 0)%s%s");
+        return dev_traditional(ctx, dL, dR, H, W, 30.0, (double)(m.win * 2 / 3), m.disp_type, m.win, m.min_d, m.num_d, disp_dev, agg_dev, 1);
     case M_GEO: return dev_geodesic(ctx, dL, dR, H, W, m.disp_type, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
     case M_GRID: return dev_bilateral_grid(ctx, dL, dR, H, W, m.p0, m.p1, m.min_d, m.num_d, disp_dev, agg_dev);
     case M_BLO1: return dev_blo1(ctx, dL, dR, H, W, m.disp_type, m.p0, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
@@ -246,6 +250,11 @@ static asw_status run_method_host(asw_ctx* ctx, const MethodArgs& m, const asw_u
 extern "C" asw_status asw_adaptive_weight(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, asw_f32_image* disp,
                                           double gamma_c, double gamma_g, int disp_type, int win, int min_d, int num_d) {
     MethodArgs m = {M_TRAD, disp_type, win, min_d, num_d, gamma_c, gamma_g};
+    return run_method_host(ctx, m, L, R, disp);
+}
+extern "C" asw_status asw_adaptive_weight_direct8(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, asw_f32_image* disp,
+                                                  int disp_type, int win, int min_d, int num_d) {
+    MethodArgs m = {M_D8, disp_type, win, min_d, num_d, 0, 0};
     return run_method_host(ctx, m, L, R, disp);
 }
 extern "C" asw_status asw_adaptive_weight_geodesic(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, asw_f32_image* disp,
@@ -285,13 +294,14 @@ extern "C" asw_status asw_adaptive_weight_weighted_median(asw_ctx* ctx, const as
 static bool dispatcher_args(int algorithm, int disp_type, int win, int min_d, int num_d, MethodArgs* m) {
     switch (algorithm) {
     case ASW_ALG_ADAPTIVE_WEIGHT: *m = {M_TRAD, disp_type, win, min_d, num_d, 30, 20}; return true;              // A.cpp:58
+    case ASW_ALG_ADAPTIVE_WEIGHT_8DIRECT: *m = {M_D8, disp_type, win, min_d, num_d, 0, 0}; return true;           // A.cpp:61
     case ASW_ALG_ADAPTIVE_WEIGHT_GEODESIC: *m = {M_GEO, disp_type, win, min_d, num_d, 0, 0}; return true;         // A.cpp:64
     case ASW_ALG_ADAPTIVE_WEIGHT_BILATERAL_GRID: *m = {M_GRID, disp_type, 1, min_d, num_d, 10, 10}; return true;  // A.cpp:67
     case ASW_ALG_ADAPTIVE_WEIGHT_BLO1: *m = {M_BLO1, disp_type, win, min_d, num_d, 0.015, 0}; return true;        // A.cpp:70
     case ASW_ALG_ADAPTIVE_WEIGHT_GUIDED_FILTER: *m = {M_GF1, disp_type, win, min_d, num_d, 1e-6, 0}; return true; // A.cpp:73
     case ASW_ALG_ADAPTIVE_WEIGHT_GUIDED_FILTER_2: *m = {M_GF2, disp_type, win, min_d, num_d, 1e-6, 0}; return true; // A.cpp:76
     case ASW_ALG_ADAPTIVE_WEIGHT_MEDIAN: *m = {M_WMED, disp_type, win, min_d, num_d, 10, 10}; return true;        // A.cpp:82
-    default: return false;   // BM, SGBM, 8-direction, GuidedF_3, NCC: outside the hot path
+    default: return false;   // BM, SGBM, GuidedF_3, NCC: outside the hot path
     }
 }
 // candidates the dispatcher's method scans for a named numDisparity (D + 1 where the reference loop runs to
@@ -447,7 +457,7 @@ static asw_status split_local_keys_dev(asw_ctx* ctx, const asw_u8_image* L, cons
     ASW_TRY(method_check(ctx, m));
     // [d_begin, d_end) indexes the candidates the method scans: num_d of them, or num_d + 1 for the methods whose
     // reference loop runs to max_offset inclusive (traditional, geodesic, grid)
-    if (m.id != M_GF2 && m.id != M_TRAD && m.id != M_GEO && m.id != M_GRID && m.id != M_BLO1)
+    if (m.id != M_GF2 && m.id != M_TRAD && m.id != M_GEO && m.id != M_GRID && m.id != M_BLO1 && m.id != M_D8)
         return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "disparity split is not implemented for this method%s%s");
     if (m.id == M_GF2 && disp_type == 1) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "GuidedF_2 DISPARITY_RIGHT throws in the reference%s%s");
     if (d_begin < 0 || d_end > method_n_eval(m) || d_begin > d_end) return asw_fail(ctx, ASW_ERR_BAD_ARG, "bad disparity range%s%s");
@@ -469,6 +479,7 @@ static asw_status split_local_keys_dev(asw_ctx* ctx, const asw_u8_image* L, cons
             ASW_TRY(ws_get(ctx, WS_OUT, n, &tmp));
             const int cnt = d_end - d_begin;
             if (m.id == M_TRAD) ASW_TRY(dev_traditional(ctx, dL, dR, H, W, m.p0, m.p1, disp_type, win, min_d + d_begin, cnt - 1, tmp, nullptr));
+            else if (m.id == M_D8) ASW_TRY(dev_traditional(ctx, dL, dR, H, W, 30.0, (double)(win * 2 / 3), disp_type, win, min_d + d_begin, cnt - 1, tmp, nullptr, 1));
             else if (m.id == M_GEO) ASW_TRY(dev_geodesic(ctx, dL, dR, H, W, disp_type, win, min_d + d_begin, cnt - 1, tmp, nullptr));
             else if (m.id == M_GRID) ASW_TRY(dev_bilateral_grid(ctx, dL, dR, H, W, m.p0, m.p1, min_d + d_begin, cnt - 1, tmp, nullptr));
             else ASW_TRY(dev_blo1_range(ctx, dL, dR, H, W, disp_type, m.p0, win, min_d, num_d, d_begin, d_end, tmp, nullptr));

@@ -390,9 +390,7 @@ static asw_status launch_blo1_agg2(asw_ctx* ctx, const uint8_t* gref, const uint
                   (size_t)NPIX * sizeof(uint32_t) + (size_t)NPIX * sizeof(unsigned long long);
     cudaFuncSetAttribute(k_blo1_agg2<WIN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(k_blo1_agg2<WIN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int dch = 8;
-    const char* e = getenv("ASW_BLO_DCH");
-    if (e && atoi(e) > 0) dch = atoi(e);
+    const int dch = ctx->tune[ASW_TUNE_BLO_DCH] > 0 ? ctx->tune[ASW_TUNE_BLO_DCH] : 8;
     {   // normalisers: the same kernel on the last disparity with unit costs
         BloGeom gn = g;
         gn.di_lo = g.D - 1; gn.di_hi = g.D;
@@ -437,8 +435,7 @@ static asw_status dev_blo1_range(asw_ctx* ctx, const uint8_t* dL, const uint8_t*
     unsigned long long* keys;
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
     ASW_TRY(init_keys(ctx, keys, n));
-    const char* tiled = getenv("ASW_BLO_TILED");
-    const bool generic = tiled && atoi(tiled) == 1;
+    const bool generic = asw_dev("ASW_BLO_TILED");
     const bool templated = !generic && (win == 5 || win == 7 || win == 9 || win == 15 || win == 25 || win == 35);
     if (!templated)   // exact integer normalisers for the tiled fallback (the register-resident kernel computes its own)
         LAUNCH(ctx, "blo1_norm", (k_blo1_norm<<<dim3(tiles.x, tiles.y, g.nl), BLO_THREADS, smem_n, ctx->stream>>>(gref, gtgt, g, Nk)));

@@ -660,7 +660,9 @@ template <bool BORDER>
 static asw_status geo_segments(asw_ctx* ctx, const float* dref, const float* dtgt, const uint32_t* cref,
                                const uint32_t* ctgt, GeoGeom g, int seg_first, int seg_count,
                                unsigned long long* keys, float* agg) {
-    if (getenv("ASW_GEO_TILE")) return geo_tile_segments<BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, keys, agg);
+#ifdef ASW_DEV_KERNELS
+    if (asw_dev("ASW_GEO_TILE")) return geo_tile_segments<BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, keys, agg);
+#endif
     if (g.sign > 0) return geo_segments_signed<1, BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, keys, agg);
     return geo_segments_signed<-1, BORDER>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, keys, agg);
 }
@@ -688,7 +690,7 @@ static asw_status dev_geodesic_dist(asw_ctx* ctx, const uint8_t* img, int H, int
     ASW_TRY(ws_get(ctx, ws_slot, n * win * win, &dist));
     LAUNCH(ctx, "pack_bgrx_pad", (k_pack_bgrx_pad<<<dim3(cdiv(Wp, 128), Hp), 128, 0, ctx->stream>>>(img, H, W, pad, ext)));   // A.cpp:1404
     dim3 dgrid(cdiv(W, 128), H);
-    if (getenv("ASW_GEO_DIST_GENERIC")) LAUNCH(ctx, "geo_dist", (k_geo_dist<<<dgrid, 128, 0, ctx->stream>>>(ext, H, W, win, dist)));
+    if (asw_dev("ASW_GEO_DIST_GENERIC")) LAUNCH(ctx, "geo_dist", (k_geo_dist<<<dgrid, 128, 0, ctx->stream>>>(ext, H, W, win, dist)));
     else if (win == 35) LAUNCH(ctx, "geo_dist", (k_geo_dist_t<35><<<dgrid, 128, 0, ctx->stream>>>(ext, H, W, dist)));
     else if (win == 9) LAUNCH(ctx, "geo_dist", (k_geo_dist_t<9><<<dgrid, 128, 0, ctx->stream>>>(ext, H, W, dist)));
     else if (win == 7) LAUNCH(ctx, "geo_dist", (k_geo_dist_t<7><<<dgrid, 128, 0, ctx->stream>>>(ext, H, W, dist)));
@@ -730,7 +732,7 @@ static asw_status dev_geodesic(asw_ctx* ctx, const uint8_t* dL, const uint8_t* d
     bool left = disp_type == ASW_DISPARITY_LEFT;
     const float* dref = left ? distL : distR; const float* dtgt = left ? distR : distL;
     const uint32_t* cref = left ? pl : pr; const uint32_t* ctgt = left ? pr : pl;
-    if (getenv("ASW_GEO_GENERIC")) {
+    if (asw_dev("ASW_GEO_GENERIC")) {
         dim3 grid(cdiv(W, 128), H, cdiv(g.n_cand, 4));
         LAUNCH(ctx, "geo_aggregate", (k_geo_aggregate_q<4><<<grid, 128, 0, ctx->stream>>>(dref, dtgt, cref, ctgt, g, 0, keys, agg_dev)));
         return keys_to_disp(ctx, keys, n, disp_dev);
@@ -739,7 +741,7 @@ static asw_status dev_geodesic(asw_ctx* ctx, const uint8_t* dL, const uint8_t* d
     // would run the diagonal kernel with one warp per CTA (all the staging, 1/8 of the work).  The thread-per-pixel
     // kernel evaluates exactly those candidates over the whole image instead.
     const int rem = g.n_cand % 32;
-    if (rem >= 1 && rem <= 4 && g.n_cand > 32 && !getenv("ASW_GEO_DIAG_REM")) {
+    if (rem >= 1 && rem <= 4 && g.n_cand > 32 && !asw_dev("ASW_GEO_DIAG_REM")) {
         GeoGeom gr = g;
         const int c1 = g.n_cand - rem;
         gr.d_first = g.d_first + c1; gr.n_cand = rem;

@@ -297,7 +297,7 @@ static asw_status grid_batches(asw_ctx* ctx, const uint8_t* gl, const uint8_t* g
         // holds a CTA iteration's cells in GRID_CONV_MAX registers per thread
         const int PL_max = std::min(std::min(128 / std::max(Zd, Wdd), (int)((96 * 1024) / plane_bytes)),
                                     (int)((size_t)GRID_CONV_MAX * 128 / ((size_t)Zd * (Wdd | 1))));
-        if (PL_max >= 1 && !getenv("ASW_GRID_UNFUSED")) {
+        if (PL_max >= 1 && !asw_dev("ASW_GRID_UNFUSED")) {
             int PL = PL_max;
             size_t smem = plane_bytes * PL + 16;
             int n_planes = (g.nx + 1) * (g.ny + 1) * nb;
@@ -373,11 +373,20 @@ static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint
         max_run = std::max(max_run, h_yr[GY + k]);
     }
     int* d_ti; double* d_td;
-    ASW_TRY(ws_get(ctx, WS_TABLE0, ti.size(), &d_ti));
-    ASW_TRY(ws_get(ctx, WS_TABLE1, td.size(), &d_td));
-    ASW_CUDA(ctx, cudaMemcpyAsync(d_ti, ti.data(), ti.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-    ASW_CUDA(ctx, cudaMemcpyAsync(d_td, td.data(), td.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // the tables are host temporaries
+    ASW_TRY(ws_get(ctx, WS_GRID_TI, ti.size(), &d_ti));
+    ASW_TRY(ws_get(ctx, WS_GRID_TD, td.size(), &d_td));
+    {
+        // the tables depend on the geometry only: uploaded (and the stream synchronised, they are host temporaries) on the
+        // first call with this geometry; a batch of equal-sized pairs stays asynchronous on the ctx stream
+        char key[128];
+        snprintf(key, sizeof(key), "grid:%d:%d:%.17g:%.17g", H, W, rate_s, rate_r);
+        const bool have_i = table_cached(ctx, 2, WS_GRID_TI, key), have_d = table_cached(ctx, 3, WS_GRID_TD, key);
+        if (!have_i || !have_d) {
+            ASW_CUDA(ctx, cudaMemcpyAsync(d_ti, ti.data(), ti.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            ASW_CUDA(ctx, cudaMemcpyAsync(d_td, td.data(), td.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
     GridTables tb;
     tb.klut = d_ti; tb.xr = d_ti + 256; tb.yr = tb.xr + 2 * GX;
     tb.xq = d_td; tb.yq = d_td + W; tb.gq = tb.yq + H; tb.max_run = max_run;
@@ -386,9 +395,9 @@ static asw_status dev_bilateral_grid(asw_ctx* ctx, const uint8_t* dL, const uint
         const size_t plane_bytes = (size_t)Zd * (Wdd | 1) * 12;
         const int PL_max = std::min(std::min(128 / std::max(Zd, Wdd), (int)((96 * 1024) / plane_bytes)),
                                     (int)((size_t)GRID_CONV_MAX * 128 / ((size_t)Zd * (Wdd | 1))));
-        const bool fused = PL_max >= 1 && !getenv("ASW_GRID_UNFUSED");
+        const bool fused = PL_max >= 1 && !asw_dev("ASW_GRID_UNFUSED");
         // 16-bit counts: a count never exceeds the pixels of one spatial cell (every pass is a convex combination)
-        if (fused && (size_t)max_run * max_run <= 65535 && !getenv("ASW_GRID_C32"))
+        if (fused && (size_t)max_run * max_run <= 65535 && !asw_dev("ASW_GRID_C32"))
             ASW_TRY((grid_batches<uint16_t>(ctx, gl, gr, H, W, min_d, n_cand, batch, g, tb, S, (uint16_t*)C, keys, agg_dev)));
         else
             ASW_TRY((grid_batches<int>(ctx, gl, gr, H, W, min_d, n_cand, batch, g, tb, S, C, keys, agg_dev)));

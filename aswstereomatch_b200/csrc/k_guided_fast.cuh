@@ -263,6 +263,7 @@ k_gff_q(const float4* __restrict__ ab, const float4* __restrict__ Gi, GffGeom g,
         if (o < c_len) atomicMin(&keys[pix0 + o * g.W], best[o]);
 }
 
+#ifdef ASW_DEV_KERNELS   // host side of the tiled pair: the product build launches the streaming kernel instead
 __global__ void k_reciprocal4(const float4* __restrict__ in, size_t n, float4* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -291,3 +292,4 @@ static asw_status gff_launch(asw_ctx* ctx, const Feat* fref, const Feat* ftgt, c
                             ab, Gi, g, tp.c0, slice_mm, d_label0, dc2, keys, agg)));
     return ASW_OK;
 }
+#endif

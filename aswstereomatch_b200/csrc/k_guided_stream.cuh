@@ -569,8 +569,7 @@ static asw_status gfs_launch(asw_ctx* ctx, const FeatF* fref, const FeatF* ftgt,
     const int strips = cdiv(g.W, QW), groups = cdiv(cn, GFS_NS);
     // bands: enough CTAs for ~4 resident sets, every band at least 2K rows, at least 2 (one top, one bottom)
     int nb = cdiv(4 * ctx->sm_count, strips * groups);
-    const char* e = getenv("ASW_GFS_BANDS");
-    if (e && atoi(e) > 0) nb = atoi(e);
+    if (ctx->tune[ASW_TUNE_GFS_BANDS] > 0) nb = ctx->tune[ASW_TUNE_GFS_BANDS];
     nb = std::max(2, std::min(nb, g.H / (2 * K)));
     g.D = cn; g.nbands = nb;
     TadStream ts;

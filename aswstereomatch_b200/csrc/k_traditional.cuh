@@ -18,12 +18,35 @@
 
 struct TradGeom {
     int H, W, win, h, nw, cidx;
+    int mode;        // 0: computeAdaptiveWeight (A.cpp:1016-1156), 1: computeAdaptiveWeight_direct8 (A.cpp:1167-1319)
     int sign;        // LEFT: target column = max(0, x - d) ; RIGHT: min(x + d, W-1)
     int d_first;     // first candidate offset evaluated by this launch
     int n_cand;      // candidates in this launch (<= TRAD_Q per thread pass)
 };
 
 #define TRAD_Q 6
+
+// tap n of the weight list -> (dy, dx) = neighbour whose gray difference weights the tap, (ky, kx) = cost sample offset
+// from the window's top-left corner.
+//  mode 0: weight list skips the centre (A.cpp:1050-1053); the sample list skips centre + 1 and is TRANSPOSED
+//          (pc / win is used as the column offset, A.cpp:1088-1102).
+//  mode 1: 8-direction subset (A.cpp:1191-1199, 1239-1247): row-major (j, i) with i == j || i == 0 || j == 0 (the
+//          "anti-diagonal" test i + j == win - 1 only ever matches (h, h)): 2 taps per row j != 0, win - 1 in row 0;
+//          weight and sample use the same offset.
+__host__ __device__ __forceinline__ void trad_tap(int mode, int n, int win, int cidx, int* dy, int* dx, int* ky, int* kx) {
+    const int h = win / 2;
+    if (mode == 0) {
+        const int pw = n < cidx ? n : n + 1, pc = n <= cidx ? n : n + 1;
+        *dy = pw / win - h; *dx = pw % win - h;
+        *kx = pc / win; *ky = pc % win;
+    } else {
+        int j, i;
+        if (n < 2 * h) { j = -h + n / 2; i = (n & 1) ? 0 : j; }
+        else if (n < 4 * h) { const int m = n - 2 * h; j = 0; i = m < h ? m - h : m - h + 1; }
+        else { const int m = n - 4 * h; j = 1 + m / 2; i = (m & 1) ? j : 0; }
+        *dy = j; *dx = i; *ky = j + h; *kx = i + h;
+    }
+}
 
 __device__ __forceinline__ int trad_shift(int x, int d, int sign, int W) {
     return sign > 0 ? max(0, x - d) : min(x + d, W - 1);
@@ -161,6 +184,7 @@ __device__ __forceinline__ void trad_tile_body(const uint8_t* __restrict__ refU,
     }
 }
 
+#ifdef ASW_DEV_KERNELS
 // grid: (tiles_x, tiles_y, candidate chunks of TR_Q); block (32, 8)
 __global__ void __launch_bounds__(TR_TW * TR_TH)
 k_trad_tile(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, const float* __restrict__ table,
@@ -215,6 +239,7 @@ k_trad_tile(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, co
         atomicMin(&keys[p], best);
     }
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // default variant: same tiling, but the weight product is evaluated in one SFU op instead of two
@@ -301,6 +326,7 @@ __device__ __forceinline__ void trad_fast_body(const float* __restrict__ refF, c
     }
 }
 
+#ifdef ASW_DEV_KERNELS
 __global__ void __launch_bounds__(TR_TW * TR_TH)
 k_trad_fast(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, const float* __restrict__ c2, float a2,
             TradGeom g, unsigned long long* __restrict__ keys, float* __restrict__ agg) {
@@ -352,6 +378,7 @@ k_trad_fast(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, co
         atomicMin(&keys[p], best);
     }
 }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // linear-addressing variant of the single-SFU-op kernel (the default).  Two observations remove every clamp
@@ -456,10 +483,8 @@ k_trad_lin(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, con
         TF[i] = (float)tgt[(size_t)clampi(y0t - h + r, 0, H - 1) * W + clampi(oxt + c, 0, W - 1)];
     }
     for (int n = tid; n < g.nw; n += TR_TW * TR_TH) {
-        const int pw = n < g.cidx ? n : n + 1;                    // weight tap skips the centre (A.cpp:1044-1053)
-        const int pc = n <= g.cidx ? n : n + 1;                   // sample tap skips centre + 1 (A.cpp:1088-1102)
-        const int dy = pw / win - h, dx = pw % win - h;
-        const int kx = pc / win, ky = pc % win;                   // pc / win is the COLUMN offset: transposed
+        int dy, dx, ky, kx;
+        trad_tap(g.mode, n, win, g.cidx, &dy, &dx, &ky, &kx);
         taps[n] = make_int4(dy * IWr + dx, dy * IWt + dx, ky * IWr + kx, (ky * IWt) | (kx << 20));
         c2s[n] = __ldg(&c2[n]);
     }
@@ -748,9 +773,29 @@ static void trad_build_table(int win, double gamma_c, double gamma_g, std::vecto
     }
 }
 
+// c2[n] = 2 g_n log2(e) / gamma_g - log2(9), g_n = spatial distance of tap n (k = 3 -> k * k = 9): the spatial part of
+// w_L w_R = 9 * 2^-(a2 (dL + dR) + c2[n]), a2 = log2(e) / gamma_c.  Cached on the device per parameter set.
+static asw_status trad_upload_c2(asw_ctx* ctx, const TradGeom& g, double gamma_g, float** dc2) {
+    char key[96];
+    snprintf(key, sizeof(key), "c2:%d:%d:%.17g", g.mode, g.win, gamma_g);
+    ASW_TRY(ws_get(ctx, WS_TRAD_C2, (size_t)g.nw, dc2));
+    if (table_cached(ctx, 0, WS_TRAD_C2, key)) return ASW_OK;
+    std::vector<float> c2(g.nw);
+    const double log2e = 1.4426950408889634;
+    for (int i = 0; i < g.nw; i++) {
+        int dy, dx, ky, kx;
+        trad_tap(g.mode, i, g.win, g.cidx, &dy, &dx, &ky, &kx);
+        c2[i] = (float)(2.0 * sqrt((double)(dx * dx + dy * dy)) * log2e / gamma_g - log2(9.0));
+    }
+    ASW_CUDA(ctx, cudaMemcpyAsync(*dc2, c2.data(), c2.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // c2 is a host temporary (first call with these parameters only)
+    return ASW_OK;
+}
+
+// mode 0: computeAdaptiveWeight (A.cpp:1016-1156); mode 1: computeAdaptiveWeight_direct8 (A.cpp:1167-1319, LEFT only)
 static asw_status dev_traditional(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, double gamma_c,
                                   double gamma_g, int disp_type, int win, int min_d, int num_d, float* disp_dev,
-                                  float* agg_dev) {
+                                  float* agg_dev, int mode = 0) {
     size_t n = (size_t)H * W;
     uint8_t *gl, *gr;
     ASW_TRY(ws_get(ctx, WS_GRAY_L, n, &gl));
@@ -761,79 +806,84 @@ static asw_status dev_traditional(asw_ctx* ctx, const uint8_t* dL, const uint8_t
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
     ASW_TRY(init_keys(ctx, keys, n));
     TradGeom g;
-    g.H = H; g.W = W; g.win = win; g.h = win / 2; g.nw = win * win - 1; g.cidx = win * win / 2;
+    g.H = H; g.W = W; g.win = win; g.h = win / 2; g.nw = mode == 0 ? win * win - 1 : 3 * (win - 1); g.cidx = win * win / 2;
+    g.mode = mode;
     g.sign = disp_type == ASW_DISPARITY_LEFT ? 1 : -1;
     g.d_first = min_d;
     g.n_cand = num_d + 1;                                    // A.cpp:1021, 1074: <= max_offset
     const uint8_t* ref = disp_type == ASW_DISPARITY_LEFT ? gl : gr;
     const uint8_t* tgt = disp_type == ASW_DISPARITY_LEFT ? gr : gl;
     const int h = win / 2, IH = TR_TH + 2 * h, IWr = TR_TW + 2 * h, IWt = TR_TW + 2 * h + TR_Q - 1;
-    const bool exact = getenv("ASW_TRAD_EXACT") != nullptr;
-    size_t smem_fast = ((size_t)IH * IWr + (size_t)IH * IWt) * sizeof(float);
-    if (!exact && getenv("ASW_TRAD_DIAG") && win <= 41) {
-        // diagonal-blocked kernel (measured 15-25 % slower than the tiled single-SFU-op kernel below: kept selectable): per-side weights 2^(-(delta a2 + c2h[n])), c2h[n] = g_n log2(e)/gamma_g - log2(3)
+    const double log2e = 1.4426950408889634;
+    const size_t smem_fast = ((size_t)IH * IWr + (size_t)IH * IWt) * sizeof(float);
+    const size_t smem_lin = smem_fast + (size_t)5 * g.nw * sizeof(float);
+    const dim3 grid(cdiv(W, TR_TW), cdiv(H, TR_TH), cdiv(g.n_cand, TR_Q));
+#ifdef ASW_DEV_KERNELS
+    if (mode == 0 && !asw_dev("ASW_TRAD_EXACT") && asw_dev("ASW_TRAD_DIAG") && win <= 41) {
+        // diagonal-blocked kernel (measured 15-25 % slower than k_trad_lin): per-side weights 2^(-(delta a2 + c2h[n]))
         std::vector<float> c2h(g.nw);
-        const double log2e = 1.4426950408889634;
         for (int i = 0; i < g.nw; i++) {
             int pw = i < g.cidx ? i : i + 1;
             int dj = pw / win - h, di = pw % win - h;
             c2h[i] = (float)(sqrt((double)(di * di + dj * dj)) * log2e / gamma_g - log2(3.0));
         }
         float* dc2;
-        ASW_TRY(ws_get(ctx, WS_TABLE1, c2h.size(), &dc2));
+        ASW_TRY(ws_get(ctx, WS_TRAD_C2, c2h.size(), &dc2));
+        ctx->table_key[0].clear();
         ASW_CUDA(ctx, cudaMemcpyAsync(dc2, c2h.data(), c2h.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // c2h is a host temporary
+        ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         const float a2 = (float)(log2e / gamma_c);
         if (g.sign > 0) ASW_TRY((trad_diag_all<1>(ctx, ref, tgt, dc2, a2, g, keys, agg_dev)));
         else ASW_TRY((trad_diag_all<-1>(ctx, ref, tgt, dc2, a2, g, keys, agg_dev)));
         return keys_to_disp(ctx, keys, n, disp_dev);
     }
-    if (!exact && smem_fast <= 200 * 1024) {
-        // c2[n] = 2 g_n log2(e)/gamma_g - log2(9), a2 = log2(e)/gamma_c  (k = 3 -> k*k = 9)
-        std::vector<float> c2(g.nw);
-        const double log2e = 1.4426950408889634;
-        for (int i = 0; i < g.nw; i++) {
-            int pw = i < g.cidx ? i : i + 1;
-            int dj = pw / win - h, di = pw % win - h;
-            c2[i] = (float)(2.0 * sqrt((double)(di * di + dj * dj)) * log2e / gamma_g - log2(9.0));
-        }
+    if (mode == 0 && !asw_dev("ASW_TRAD_EXACT") && asw_dev("ASW_TRAD_FAST") && smem_fast <= 200 * 1024) {
         float* dc2;
-        ASW_TRY(ws_get(ctx, WS_TABLE1, c2.size(), &dc2));
-        ASW_CUDA(ctx, cudaMemcpyAsync(dc2, c2.data(), c2.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-        ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // c2 is a host temporary
-        dim3 grid(cdiv(W, TR_TW), cdiv(H, TR_TH), cdiv(g.n_cand, TR_Q));
-        const size_t smem_lin = smem_fast + (size_t)5 * g.nw * sizeof(float);
-        if (!getenv("ASW_TRAD_FAST") && smem_lin <= 200 * 1024 && (size_t)IH * IWt < (1u << 20)) {
-            if (g.sign > 0) {
-                cudaFuncSetAttribute(k_trad_lin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin);
-                LAUNCH(ctx, "trad_aggregate", (k_trad_lin<1><<<grid, dim3(TR_TW, TR_TH), smem_lin, ctx->stream>>>(
-                                                  ref, tgt, dc2, (float)(log2e / gamma_c), g, keys, agg_dev)));
-            } else {
-                cudaFuncSetAttribute(k_trad_lin<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin);
-                LAUNCH(ctx, "trad_aggregate", (k_trad_lin<-1><<<grid, dim3(TR_TW, TR_TH), smem_lin, ctx->stream>>>(
-                                                  ref, tgt, dc2, (float)(log2e / gamma_c), g, keys, agg_dev)));
-            }
-            return keys_to_disp(ctx, keys, n, disp_dev);
-        }
+        ASW_TRY(trad_upload_c2(ctx, g, gamma_g, &dc2));
         cudaFuncSetAttribute(k_trad_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
         LAUNCH(ctx, "trad_aggregate", (k_trad_fast<<<grid, dim3(TR_TW, TR_TH), smem_fast, ctx->stream>>>(
                                           ref, tgt, dc2, (float)(log2e / gamma_c), g, keys, agg_dev)));
         return keys_to_disp(ctx, keys, n, disp_dev);
     }
-    std::vector<float> table;
-    trad_build_table(win, gamma_c, gamma_g, table);
-    float* dtable;
-    ASW_TRY(ws_get(ctx, WS_TABLE0, table.size(), &dtable));
-    ASW_CUDA(ctx, cudaMemcpyAsync(dtable, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // table is a host temporary
-    size_t smem = ((size_t)win * 256 + (size_t)IH * IWr + (size_t)IH * IWt) * sizeof(float) + (size_t)IH * (IWr + IWt);
-    if (smem <= 200 * 1024 && !getenv("ASW_TRAD_GENERIC")) {
-        cudaFuncSetAttribute(k_trad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dim3 grid(cdiv(W, TR_TW), cdiv(H, TR_TH), cdiv(g.n_cand, TR_Q));
-        LAUNCH(ctx, "trad_aggregate", (k_trad_tile<<<grid, dim3(TR_TW, TR_TH), smem, ctx->stream>>>(ref, tgt, dtable, g, keys, agg_dev)));
-    } else {
-        dim3 grid(cdiv(W, 128), H, cdiv(g.n_cand, TRAD_Q));
-        LAUNCH(ctx, "trad_aggregate", (k_trad_aggregate<<<grid, 128, 0, ctx->stream>>>(ref, tgt, dtable, g, keys, agg_dev)));
+#endif
+    // the product kernel: tiled, clamp-free inner loop, one ex2 per (tap, candidate)
+    if (!asw_dev("ASW_TRAD_EXACT") && !asw_dev("ASW_TRAD_GENERIC") && smem_lin <= 200 * 1024 && (size_t)IH * IWt < (1u << 20)) {
+        float* dc2;
+        ASW_TRY(trad_upload_c2(ctx, g, gamma_g, &dc2));
+        if (g.sign > 0) {
+            cudaFuncSetAttribute(k_trad_lin<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin);
+            LAUNCH(ctx, "trad_aggregate", (k_trad_lin<1><<<grid, dim3(TR_TW, TR_TH), smem_lin, ctx->stream>>>(
+                                              ref, tgt, dc2, (float)(log2e / gamma_c), g, keys, agg_dev)));
+        } else {
+            cudaFuncSetAttribute(k_trad_lin<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_lin);
+            LAUNCH(ctx, "trad_aggregate", (k_trad_lin<-1><<<grid, dim3(TR_TW, TR_TH), smem_lin, ctx->stream>>>(
+                                              ref, tgt, dc2, (float)(log2e / gamma_c), g, keys, agg_dev)));
+        }
+        return keys_to_disp(ctx, keys, n, disp_dev);
     }
+    if (mode != 0) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "8-direction ASW: window too large for the tiled kernel%s%s");
+    // windows whose tile does not fit shared memory: the size-generic kernel over the exact weight table
+    // (float(3 exp(-(delta / gamma_c + g / gamma_g))) for every tap and gray difference, built in double as A.cpp:1065)
+    float* dtable;
+    ASW_TRY(ws_get(ctx, WS_TRAD_TABLE, (size_t)g.nw * 256, &dtable));
+    {
+        char key[96];
+        snprintf(key, sizeof(key), "tab:%d:%.17g:%.17g", win, gamma_c, gamma_g);
+        if (!table_cached(ctx, 1, WS_TRAD_TABLE, key)) {
+            std::vector<float> table;
+            trad_build_table(win, gamma_c, gamma_g, table);
+            ASW_CUDA(ctx, cudaMemcpyAsync(dtable, table.data(), table.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+            ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));      // table is a host temporary (first call only)
+        }
+    }
+#ifdef ASW_DEV_KERNELS
+    const size_t smem = ((size_t)win * 256 + (size_t)IH * IWr + (size_t)IH * IWt) * sizeof(float) + (size_t)IH * (IWr + IWt);
+    if (smem <= 200 * 1024 && !asw_dev("ASW_TRAD_GENERIC")) {
+        cudaFuncSetAttribute(k_trad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        LAUNCH(ctx, "trad_aggregate", (k_trad_tile<<<grid, dim3(TR_TW, TR_TH), smem, ctx->stream>>>(ref, tgt, dtable, g, keys, agg_dev)));
+        return keys_to_disp(ctx, keys, n, disp_dev);
+    }
+#endif
+    LAUNCH(ctx, "trad_aggregate", (k_trad_aggregate<<<dim3(cdiv(W, 128), H, cdiv(g.n_cand, TRAD_Q)), 128, 0, ctx->stream>>>(ref, tgt, dtable, g, keys, agg_dev)));
     return keys_to_disp(ctx, keys, n, disp_dev);
 }

@@ -215,7 +215,7 @@ static asw_status dev_weighted_median(asw_ctx* ctx, const uint8_t* dL, const uin
     float alpha_s = (float)((1.0 / rate_s) * (-1));
     const int nn = win * win, Wr = W + v.max_off;
     const size_t planes = (size_t)nn * H * ((size_t)W + Wr) * sizeof(float);
-    if (!getenv("ASW_WM_SCAN") && planes <= ((size_t)6 << 30)) {
+    if (!asw_dev("ASW_WM_SCAN") && planes <= ((size_t)6 << 30)) {
         float *WLp, *WRp;
         ASW_TRY(ws_get(ctx, WS_GEO_L, (size_t)nn * H * W, &WLp));
         ASW_TRY(ws_get(ctx, WS_GEO_R, (size_t)nn * H * Wr, &WRp));

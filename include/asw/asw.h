@@ -64,6 +64,11 @@ const char* asw_version(void);
 asw_status asw_sync(asw_ctx* ctx);
 void* asw_stream(asw_ctx* ctx);                       /* the ctx's cudaStream_t */
 
+/* tuning knobs (0 restores the built-in choice): row bands per strip of the streaming guided filter, disparities per CTA
+ * of the BLO(1) kernel, MiB of (a,b) workspace per chunk of the generic guided filter */
+enum { ASW_TUNE_GFS_BANDS = 0, ASW_TUNE_BLO_DCH = 1, ASW_TUNE_GF_CHUNK_MB = 2, ASW_TUNE_COUNT = 3 };
+asw_status asw_set_tuning(asw_ctx* ctx, int key, int value);
+
 /* pinned host memory for callers that want full PCIe bandwidth */
 void* asw_host_alloc(size_t bytes);
 void asw_host_free(void* p);
@@ -83,6 +88,11 @@ int asw_method_candidates(int algorithm_type, int num_disparity);
 asw_status asw_adaptive_weight(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
                                asw_f32_image* disparity, double gamma_c, double gamma_g, int disp_type,
                                int win_size, int min_disparity, int num_disparity);
+/* computeAdaptiveWeight_direct8 (A.h:135-136, A.cpp:1167-1319): DISPARITY_LEFT only (the reference's RIGHT branch indexes its
+ * weight lists out of bounds, A.cpp:1291) */
+asw_status asw_adaptive_weight_direct8(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                                       asw_f32_image* disparity, int disp_type, int win_size, int min_disparity,
+                                       int num_disparity);
 /* computeAdaptiveWeight_geodesic (A.h:141-142, A.cpp:1436-1534) */
 asw_status asw_adaptive_weight_geodesic(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
                                         asw_f32_image* disparity, int disp_type, int win_size,
@@ -167,8 +177,8 @@ asw_status asw_batch_download(asw_batch* b, int index, asw_f32_image* disparity)
  * (48-bit orderable(cost) << 16 | d) in a device buffer; a MIN all-reduce over ranks (NCCL via
  * torch.distributed, or asw_keys_min_merge for peer buffers) then asw_keys_to_disparity
  * reproduces strict-< / lowest-d / NaN-never-wins exactly.
- * Methods: GuidedF_2, traditional, geodesic, bilateral grid, BLO(1).  [d_begin, d_end) indexes the candidates the
- * method scans: num_disparity of them (GuidedF_2, BLO(1)) or num_disparity + 1 (traditional, geodesic, grid).
+ * Methods: GuidedF_2, traditional, 8-direction, geodesic, bilateral grid, BLO(1).  [d_begin, d_end) indexes the candidates the
+ * method scans: num_disparity of them (GuidedF_2, BLO(1)) or num_disparity + 1 (traditional, 8-direction, geodesic, grid).
  * BLO(1) keeps the full range's normaliser (the reference takes it from the last disparity, A.cpp:2588). */
 asw_status asw_split_local_keys(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
                                 int algorithm_type, int disp_type, int win_size, int min_disparity,

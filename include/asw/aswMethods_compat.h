@@ -100,6 +100,12 @@ inline Mat computeAdaptiveWeight(Mat leftImg, Mat rightImg, double gamma_c = 30,
     return detail::run(leftImg, rightImg, [&](asw_ctx* c, const asw_u8_image* l, const asw_u8_image* r, asw_f32_image* d) {
         return asw_adaptive_weight(c, l, r, d, gamma_c, gamma_g, dispType, winSize, minDisparity, numDisparity); });
 }
+// A.h:135-136
+inline Mat computeAdaptiveWeight_direct8(Mat leftImg, Mat rightImg, DisparityType dispType = DISPARITY_LEFT, int winSize = 7,
+                                         int minDisparity = 186, int numDisparity = 144) {
+    return detail::run(leftImg, rightImg, [&](asw_ctx* c, const asw_u8_image* l, const asw_u8_image* r, asw_f32_image* d) {
+        return asw_adaptive_weight_direct8(c, l, r, d, dispType, winSize, minDisparity, numDisparity); });
+}
 // A.h:141-142
 inline Mat computeAdaptiveWeight_geodesic(Mat leftImg, Mat rightImg, DisparityType dispType = DISPARITY_LEFT,
                                           int winSize = 7, int minDisparity = 186, int numDisparity = 144) {

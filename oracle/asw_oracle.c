@@ -507,6 +507,75 @@ int orc_asw_traditional(const uint8_t* L, const uint8_t* R, int H, int W, double
 }
 
 /* ------------------------------------------------------------------ */
+/* 8-direction ASW, computeAdaptiveWeight_direct8 (A.cpp:1167-1319), LEFT only: the RIGHT branch indexes the
+ * weight lists with the loop variable i in [-h, h] instead of count (A.cpp:1291), i.e. out of bounds.
+ * Taps: window offsets (j, i), j = row, i = column, with i == j || i == 0 || j == 0 || i + j == win - 1
+ * (A.cpp:1199, 1247) -- the last test was meant as the anti-diagonal but only ever matches (h, h), which i == j
+ * already covers: 3 (win - 1) taps (main diagonal, centre row, centre column), not 4 (win - 1), so the
+ * count < 4 (win - 1) guard (A.cpp:1243) never fires.  No transposition here: weight and sample use the same
+ * (j, i).  gamma_c = 30, gamma_g = win * 2 / 3 in INTEGER arithmetic (A.cpp:1175), k = 3, D + 1 candidates. */
+/* ------------------------------------------------------------------ */
+int orc_asw_direct8(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, int win, int min_d,
+                    int num_d, float* disp, float* agg) {
+    if (!L || !R || !disp || H <= 0 || W <= 0 || num_d < 0 || win <= 0 || (win & 1) == 0) return ORC_BAD_ARG;
+    if (disp_type != 0) return ORC_UNSUPPORTED;
+    size_t n = (size_t)H * W;
+    int max_off = min_d + num_d, h = win / 2;
+    double k = 3, gamma_c = 30, gamma_g = (double)(win * 2 / 3);
+    if (gamma_g == 0) return ORC_BAD_ARG;                      /* win = 1: division by zero in the reference */
+    uint8_t* lg = (uint8_t*)malloc(n);
+    uint8_t* rg = (uint8_t*)malloc(n);
+    orc_bgr2gray(L, (int)n, lg);
+    orc_bgr2gray(R, (int)n, rg);
+    int* tj = (int*)malloc(sizeof(int) * win * win);
+    int* ti = (int*)malloc(sizeof(int) * win * win);
+    int nw = 0;
+    for (int j = -h; j <= h; j++)                              /* A.cpp:1191-1199 */
+        for (int i = -h; i <= h; i++) {
+            if (i == 0 && j == 0) continue;
+            if (i == j || i == 0 || j == 0 || (i + j) == win - 1) { tj[nw] = j; ti[nw] = i; nw++; }
+        }
+    float* wl = (float*)malloc(n * nw * sizeof(float));
+    float* wr = (float*)malloc(n * nw * sizeof(float));
+#pragma omp parallel for schedule(static)
+    for (int t = 0; t < nw; t++) {                             /* A.cpp:1203-1218 */
+        int j = tj[t], i = ti[t];
+        double delta_g = sqrt((double)(i * i + j * j));
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                int nx = clampi(x + i, 0, W - 1), ny = clampi(y + j, 0, H - 1);
+                double dc1 = fabs((double)(lg[(size_t)ny * W + nx] - lg[(size_t)y * W + x]));
+                double dc2 = fabs((double)(rg[(size_t)ny * W + nx] - rg[(size_t)y * W + x]));
+                wl[(size_t)t * n + (size_t)y * W + x] = (float)(k * exp(-(dc1 / gamma_c + delta_g / gamma_g)));
+                wr[(size_t)t * n + (size_t)y * W + x] = (float)(k * exp(-(dc2 / gamma_c + delta_g / gamma_g)));
+            }
+    }
+    double* best = (double*)malloc(n * sizeof(double));
+    for (size_t i = 0; i < n; i++) { best[i] = DBL_MAX; disp[i] = 0.0f; }
+    for (int offset = min_d; offset <= max_off; offset++) {    /* A.cpp:1225 */
+#pragma omp parallel for schedule(static)
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                double num = 0, den = 0;
+                int xr = x - offset > 0 ? x - offset : 0;
+                for (int t = 0; t < nw; t++) {                 /* A.cpp:1239-1262 */
+                    int nx = clampi(x + ti[t], 0, W - 1), ny = clampi(y + tj[t], 0, H - 1);
+                    int nxr = nx - offset > 0 ? nx - offset : 0;
+                    float w = wl[(size_t)t * n + (size_t)y * W + x] * wr[(size_t)t * n + (size_t)y * W + xr];
+                    num += (double)w * fabs((double)(lg[(size_t)ny * W + nx] - rg[(size_t)ny * W + nxr]));
+                    den += (double)w;
+                }
+                double E = num / den;
+                size_t p = (size_t)y * W + x;
+                if (agg) agg[(size_t)(offset - min_d) * n + p] = (float)E;
+                if (E < best[p]) { best[p] = E; disp[p] = (float)offset; }
+            }
+    }
+    free(best); free(wl); free(wr); free(tj); free(ti); free(lg); free(rg);
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------ */
 /* geodesic ASW (A.cpp:1321-1534)                                      */
 /* ------------------------------------------------------------------ */
 static inline float color_dist(const uint8_t* a, const uint8_t* b) {       /* A.cpp:1321-1326 */
@@ -1034,12 +1103,13 @@ int orc_stereo_matching(const uint8_t* L, const uint8_t* R, int H, int W, int di
                         int algorithm, int win, int min_d, int num_d, float* disp) {
     switch (algorithm) {
     case 2:  return orc_asw_traditional(L, R, H, W, 30, 20, disp_type, win, min_d, num_d, disp, 0);
+    case 3:  return orc_asw_direct8(L, R, H, W, disp_type, win, min_d, num_d, disp, 0);           /* A.cpp:61 */
     case 4:  return orc_asw_geodesic(L, R, H, W, disp_type, win, min_d, num_d, disp, 0);
     case 5:  return orc_asw_bilateral_grid(L, R, H, W, disp_type, 10, 10, min_d, num_d, disp, 0);
     case 6:  return orc_asw_blo1(L, R, H, W, disp_type, 0.015, win, min_d, num_d, disp, 0);
     case 7:  return orc_asw_guidedf(L, R, H, W, disp_type, 1e-6, win, min_d, num_d, disp, 0);
     case 8:  return orc_asw_guidedf2(L, R, H, W, disp_type, 1e-6, win, min_d, num_d, disp, 0);
     case 10: return orc_asw_weighted_median(L, R, H, W, disp_type, win, 10, 10, min_d, num_d, disp, 0);
-    default: return ORC_UNSUPPORTED;   /* BM, SGBM, 8-direction, GuidedF_3, NCC: out of scope */
+    default: return ORC_UNSUPPORTED;   /* BM, SGBM, GuidedF_3, NCC: out of scope */
     }
 }

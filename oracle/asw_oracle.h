@@ -69,6 +69,8 @@ int orc_guided_filter(const uint8_t* guide, int C, const float* p, int H, int W,
 int orc_asw_traditional(const uint8_t* L, const uint8_t* R, int H, int W, double gamma_c,
                         double gamma_g, int disp_type, int win, int min_d, int num_d,
                         float* disp, float* agg);                       /* A.cpp:1016-1156 */
+int orc_asw_direct8(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, int win,
+                    int min_d, int num_d, float* disp, float* agg);     /* A.cpp:1167-1319, LEFT only */
 int orc_asw_geodesic(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, int win,
                      int min_d, int num_d, float* disp, float* agg);    /* A.cpp:1321-1534 */
 int orc_geodesic_dist(const uint8_t* img, int H, int W, int win, float* dist /*[H][W][win*win]*/);

@@ -159,6 +159,10 @@ def asw_traditional(L, R, gamma_c=30.0, gamma_g=20.0, disp_type=0, win=35, min_d
                    (C.c_double(gamma_c), C.c_double(gamma_g), int(disp_type), int(win), int(min_d), int(num_d)), agg)
 
 
+def asw_direct8(L, R, disp_type=0, win=35, min_d=0, num_d=16, agg=False):
+    return _method(lib().orc_asw_direct8, L, R, num_d + 1, (int(disp_type), int(win), int(min_d), int(num_d)), agg)
+
+
 def asw_geodesic(L, R, disp_type=0, win=35, min_d=0, num_d=16, agg=False):
     return _method(lib().orc_asw_geodesic, L, R, num_d + 1,
                    (int(disp_type), int(win), int(min_d), int(num_d)), agg)

@@ -43,6 +43,8 @@ def test_traditional_wide_many_candidates(ctx, H, W, D, win, disp_type, seed, di
     """rows longer than one tile / 128-pixel segment and >= 32 candidates, both views, for the default tiled kernel
     and for the selectable diagonal-blocked kernel (interior and edge segments, full chunks plus remainder)"""
     import os
+    if diag and not ctx.has_dev_kernels():
+        pytest.skip("the diagonal-blocked kernel is compiled only with -DASW_DEV_KERNELS")
     L, R, _ = make_pair(H, W, D, seed)
     if diag:
         os.environ["ASW_TRAD_DIAG"] = "1"
@@ -55,10 +57,16 @@ def test_traditional_wide_many_candidates(ctx, H, W, D, win, disp_type, seed, di
     assert (d == d_ref).mean() >= AGREE
 
 
+def needs_dev(ctx):
+    if not ctx.has_dev_kernels():
+        pytest.skip("superseded kernels are compiled only with -DASW_DEV_KERNELS (python __graft_entry__.py --dev)")
+
+
 @pytest.mark.parametrize("env", ["ASW_TRAD_DIAG", "ASW_TRAD_EXACT"])
 def test_traditional_other_kernels(ctx, env):
-    """the diagonal-blocked kernel and the exact-table kernel stay selectable and agree with the oracle"""
+    """development builds: the diagonal-blocked kernel and the exact-table kernel agree with the oracle"""
     import os
+    needs_dev(ctx)
     L, R, _ = make_pair(40, 72, 8, 26)
     os.environ[env] = "1"
     try:
@@ -169,9 +177,54 @@ def test_dispatcher_literals(ctx, alg):
     assert (d == d_ref).mean() >= AGREE
 
 
+def test_size_generic_fallbacks_of_the_product_build(ctx):
+    """the product build keeps one tuned path per method plus size-generic kernels; these sizes reach the generic ones:
+    a 101 x 101 traditional window (tile > shared memory -> k_trad_aggregate over the exact table), a fine range grid
+    (sR = 2.8: the (z, w) plane does not fit -> global splat + 4 pass launches), an 11 x 11 geodesic window (generic DP),
+    a 21 x 21 guided / refine window (two-pass guided filter, dense weighted-median refine)"""
+    L, R, _ = make_pair(40, 56, 3, 51)
+    d, e = ctx.computeAdaptiveWeight(L, R, 30, 20, 0, 101, 0, 3, agg=True, strict=True)
+    d_ref, e_ref = orc.asw_traditional(L, R, 30, 20, 0, 101, 0, 3, agg=True)
+    assert rel_err(e, e_ref) <= REL_TOL and (d == d_ref).mean() >= AGREE
+    d, e = ctx.computeAdaptiveWeight_bilateralGrid(L, R, 0, 10, 2.8, 0, 3, agg=True, strict=True)
+    d_ref, e_ref = orc.asw_bilateral_grid(L, R, 0, 10, 2.8, 0, 3, agg=True)
+    fin = np.isfinite(e_ref)
+    assert np.array_equal(np.isfinite(e), fin) and np.array_equal(e[fin], e_ref[fin]) and np.array_equal(d, d_ref)
+    d, e = ctx.computeAdaptiveWeight_geodesic(L, R, 0, 11, 0, 3, agg=True, strict=True)
+    d_ref, e_ref = orc.asw_geodesic(L, R, 0, 11, 0, 3, agg=True)
+    assert rel_err(e, e_ref) <= REL_TOL and (d == d_ref).mean() >= AGREE
+    L, R, _ = make_pair(90, 110, 6, 52)
+    out, parts = ctx.guidedf2_lr_refine(L, R, 1e-4, 21, 0, 6, parts=True)
+    ref, rparts = orc.guidedf2_lr_refine(L, R, 1e-4, 21, 0, 6)
+    assert (parts["dl"] == rparts["dl"]).mean() >= AGREE and (parts["dr"] == rparts["dr"]).mean() >= AGREE
+    v = orc.lr_check(parts["dl"], parts["dr"], 0.0)
+    assert np.array_equal(parts["valid"], v)
+    assert np.array_equal(out, orc.wmedian_refine(L, orc.fill_invalid(parts["dl"], v), v, 21, 10, 10))
+
+
+@pytest.mark.parametrize("H,W,D,win,seed", [(44, 60, 6, 9, 21), (40, 50, 5, 35, 3), (30, 41, 4, 3, 5), (33, 147, 17, 15, 8)])
+def test_direct8(ctx, H, W, D, win, seed):
+    """computeAdaptiveWeight_direct8 (A.cpp:1167-1319): 3 (win - 1) taps (diagonal, row, column), gamma_g = win * 2 / 3 in
+    integers, D + 1 candidates; LEFT only (the RIGHT branch indexes out of bounds, A.cpp:1291)"""
+    L, R, _ = make_pair(H, W, D, seed)
+    d, e = ctx.computeAdaptiveWeight_direct8(L, R, 0, win, 0, D, agg=True, strict=True)
+    d_ref, e_ref = orc.asw_direct8(L, R, 0, win, 0, D, agg=True)
+    assert e.shape == (D + 1, H, W)
+    assert rel_err(e, e_ref) <= REL_TOL
+    assert (d == d_ref).mean() >= AGREE
+    assert np.array_equal(ctx.stereoMatching(L, R, 0, asw.ADAPTIVE_WEIGHT_8DIRECT, win, 0, D, strict=True), d)
+    assert ctx.computeAdaptiveWeight_direct8(L, R, 1, win, 0, D).size == 0
+
+
+def test_direct8_reference_golden(ctx):
+    g = np.load("tests/golden/ref_methods_44x60_d6.npz")
+    d = ctx.computeAdaptiveWeight_direct8(g["L"], g["R"], 0, 9, 0, 6, strict=True)
+    assert (d == g["direct8_w9"]).mean() >= AGREE
+
+
 def test_dispatcher_out_of_scope(ctx):
     L, R, _ = make_pair(32, 40, 4, 1)
-    for alg in (asw.BM, asw.SGBM, asw.ADAPTIVE_WEIGHT_8DIRECT, asw.ADAPTIVE_WEIGHT_GUIDED_FILTER_3, asw.NCC):
+    for alg in (asw.BM, asw.SGBM, asw.ADAPTIVE_WEIGHT_GUIDED_FILTER_3, asw.NCC):
         assert ctx.stereoMatching(L, R, 0, alg, 9, 0, 4).size == 0
         with pytest.raises(asw.AswError):
             ctx.stereoMatching(L, R, 0, alg, 9, 0, 4, strict=True)
@@ -208,10 +261,11 @@ def test_weighted_median_dispatcher_and_limits(ctx):
                                      ("ASW_TRAD_FAST", "trad"), ("ASW_BLO_TILED", "blo1"), ("ASW_GEO_DIAG_REM", "geo"),
                                      ("ASW_GEO_GENERIC", "geo"), ("ASW_REFINE_DENSE", "refine")])
 def test_selectable_fallback_paths(ctx, env, alg):
-    """every kernel the default path replaced stays selectable through an environment switch and keeps agreeing with the
-    oracle (32-bit grid counts / global splat, scan-based weighted median, clamped traditional kernel, tiled BLO(1),
-    diagonal-kernel remainder and thread-per-pixel geodesic, dense weighted-median refine)"""
+    """development builds (-DASW_DEV_KERNELS): every kernel the default path replaced stays selectable through an
+    environment switch and keeps agreeing with the oracle (32-bit grid counts / global splat, scan-based weighted median,
+    clamped traditional kernel, tiled BLO(1), diagonal-kernel remainder and thread-per-pixel geodesic, dense refine)"""
     import os
+    needs_dev(ctx)
     L, R, _ = make_pair(48, 72, 33 if alg == "geo" else 8, 41)
     os.environ[env] = "1"
     try:
