@@ -14,7 +14,7 @@ import weakref
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libasw_b200.so")
+LIB_PATH = os.environ.get("ASW_B200_LIB") or os.path.join(_HERE, "libasw_b200.so")   # the override is for A/B builds
 
 # P.h:4-24
 DISPARITY_LEFT, DISPARITY_RIGHT = 0, 1

@@ -483,7 +483,15 @@ static asw_status dev_cost_sad_box(asw_ctx* ctx, const uint8_t* dL, const uint8_
     LAUNCH(ctx, "bgr2gray", (k_bgr2gray_pad<<<dim3(cdiv(W, 256), H), 256, 0, ctx->stream>>>(v.ref, H, W, 0, 0, gref)));
     LAUNCH(ctx, "bgr2gray", (k_bgr2gray_pad<<<dim3(cdiv(v.Wp, 256), H), 256, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, gtgt)));
     if (win - 1 < SADBOX_COLS / 2) {
-        int bands = std::max(1, std::min(cdiv(H, 4 * win), cdiv(4 * ctx->sm_count, cdiv(W, SADBOX_COLS - (win - 1)) * num_d)));
+        // bands: a band is entered once (win - 1 warm-up rows); pick the count that minimises (waves of the 8 CTAs an SM
+        // holds) x (rows a CTA walks)
+        const int per_band = cdiv(W, SADBOX_COLS - (win - 1)) * num_d, slots = 8 * ctx->sm_count;
+        int bands = 1; long long best_cost = -1;
+        for (int b = 1; b <= std::max(1, H / (2 * win)); b++) {
+            const int rows = cdiv(cdiv(H, b), 4) * 4;
+            const long long cost = (long long)cdiv(per_band * cdiv(H, rows), slots) * (rows + win - 1);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; bands = b; }
+        }
         int band_rows = cdiv(cdiv(H, bands), 4) * 4;
         dim3 grid(cdiv(W, SADBOX_COLS - (win - 1)), cdiv(H, band_rows), num_d);
 #define SAD_BOX_LAUNCH(WT) LAUNCH(ctx, "sad_box", (k_sad_box_u8<4, WT><<<grid, SADBOX_COLS, 0, ctx->stream>>>(gref, gtgt, H, W, v.Wp, v.x0_base, v.x0_step, win, band_rows, vol)))

@@ -382,6 +382,193 @@ k_blo1_agg2(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, co
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Streaming BLO(1) aggregation for the dispatcher's level set (sampleRateR = 0.015 -> step 3, 86 levels, A.cpp:70).
+//
+// One thread owns one halo column of one disparity and walks DOWN a band of rows with the vertical window sums of ALL 86
+// levels in registers: V_k = sum over the WIN rows of |L-k| |R_d-k| c_d.  Moving one row down is, per level, the product of
+// the entering pixel minus the product of the leaving pixel; the pair is evaluated with two packed instructions
+// ((L-k)(R-k) = a - k b + k^2 for both pixels: FFMA2 + FADD2, exact integers) and two FFMAs with |.| operands -- 4 issue
+// slots per level and row, no vertical halo (a band is entered once), no shared memory and no barrier in this phase.
+// The horizontal window needs the neighbouring columns: the 86 sums of a row go to shared memory ([level][column],
+// conflict-free both ways), and every output pixel adds the WIN columns of the (at most) two levels it consumes
+// (A.cpp:2656-2667).  Costs are written as a [slices][H][W] volume (4 B per evaluation) for the WTA pass.
+// Against k_blo1_agg2: no per-level barrier triple (2 barriers per ROW of 86 levels), 2.65 x halo re-evaluation -> 1.15 x
+// (columns only), every level of a row in flight at once (86 independent FMA chains per thread).
+// NORM = true computes the normalisers N_k = box(M_{D-1}) with unit costs into the per-pixel pair plane.
+// ---------------------------------------------------------------------------------------------
+#define BLS_COLS 256
+#define BLS_NL 86
+#define BLS_STEP 3
+#ifndef BLS_VARIANT_NR
+#define BLS_VARIANT_NR 24         // levels kept in registers
+#define BLS_VARIANT_NBUF 1        // shared-memory row buffers (2: one CTA per SM, one barrier per row; measured slower)
+#endif
+
+// one level of the window update: V += |(L-k)(R-k)|_in c_in - |(L-k)(R-k)|_out c_out  (nco = -c_out)
+#define BLS_UPDATE(v, li)                                                                                       \
+    {                                                                                                           \
+        const float k_ = (float)((li) * BLS_STEP), k2_ = (float)((li) * BLS_STEP * (li) * BLS_STEP);            \
+        float2 t_ = __ffma2_rn(make_float2(bi, bo), make_float2(-k_, -k_), make_float2(ai, ao));                \
+        t_ = __fadd2_rn(t_, make_float2(k2_, k2_));                /* (L-k)(R-k) of both pixels, exact */        \
+        v = fmaf(fabsf(t_.x), ci, v);                              /* + |L-k| |R-k| c  (A.cpp:2571-2583) */      \
+        v = fmaf(fabsf(t_.y), nco, v);                                                                          \
+    }
+
+template <int WIN, bool NORM, int NR, int NBUF>
+__global__ void __launch_bounds__(BLS_COLS, NBUF == 2 ? 1 : 2)
+k_blo1_stream(const uint8_t* __restrict__ lg, const uint8_t* __restrict__ rpad, const float* __restrict__ cost,
+              const float* __restrict__ Nk, float* __restrict__ Nk_out, BloGeom g, int band_rows, int slice0,
+              float* __restrict__ vol) {
+    constexpr int h = WIN / 2, SW = BLS_COLS - (WIN - 1);
+    // levels [0, NR) keep their window sum in a register; the others live in the thread's own cells of the shared row
+    // buffer (it receives every sum once per row anyway) and make one extra shared-memory round trip per row: 86 sums
+    // plus the working set of the horizontal phase do not fit 128 registers, and a spill would go through L2
+    // NBUF = 2 (one CTA per SM, up to 255 registers: NR = 86) double-buffers the row buffer and needs one barrier per row.
+    static_assert(NBUF == 1 || NR == BLS_NL, "the double-buffered variant keeps every level in registers");
+    extern __shared__ float sm_bls[];                              // [NBUF][BLS_NL][BLS_COLS]
+    const int cx = threadIdx.x;
+    const int x0 = blockIdx.x * SW;
+    const int yb0 = blockIdx.y * band_rows, yb1 = min(g.H, yb0 + band_rows);
+    const int di = g.di_lo + blockIdx.z;
+    const int H = g.H, W = g.W;
+    const size_t n = (size_t)H * W;
+    const int sx = border_idx(x0 - h + cx, W, 1);                  // boxFilter BORDER_REFLECT_101
+    const uint8_t* lcol = lg + sx;
+    const uint8_t* rcol = rpad + (g.x0_base + g.x0_step * di) + sx;
+    const float* ccol = cost + (size_t)di * n + sx;
+    // (a, b, c) = (L R, L + R, c_d) of one halo pixel
+    auto load_px = [&](int r, float& a, float& b, float& c) {
+        const int sy = border_idx(r, H, 1);
+        const int l = lcol[(size_t)sy * W], rr = rcol[(size_t)sy * g.Wp];
+        a = (float)(l * rr); b = (float)(l + rr);
+        c = NORM ? 1.0f : __ldg(&ccol[(size_t)sy * W]);
+    };
+    float* scol = sm_bls + cx;
+    float V[NR];
+    int buf = 0;
+    // window of the band's first row: rows yb0 - h .. yb0 + h, two rows per step (an "update" whose leaving pixel has
+    // the sign of an entering one), the last row alone; register levels first, then the shared-memory levels
+#pragma unroll
+    for (int li = 0; li < NR; li++) V[li] = 0.0f;
+    for (int r = yb0 - h; r <= yb0 + h; r += 2) {
+        float ai, bi, ci, ao, bo, co;
+        load_px(r, ai, bi, ci);
+        load_px(r + 1, ao, bo, co);
+        const float nco = r + 1 <= yb0 + h ? co : 0.0f;
+#pragma unroll
+        for (int li = 0; li < NR; li++) BLS_UPDATE(V[li], li)
+    }
+    if (NR < BLS_NL) {
+        float T[BLS_NL - NR + (NR == BLS_NL ? 1 : 0)];
+#pragma unroll
+        for (int li = NR; li < BLS_NL; li++) T[li - NR] = 0.0f;
+        for (int r = yb0 - h; r <= yb0 + h; r += 2) {
+            float ai, bi, ci, ao, bo, co;
+            load_px(r, ai, bi, ci);
+            load_px(r + 1, ao, bo, co);
+            const float nco = r + 1 <= yb0 + h ? co : 0.0f;
+#pragma unroll
+            for (int li = NR; li < BLS_NL; li++) BLS_UPDATE(T[li - NR], li)
+        }
+#pragma unroll
+        for (int li = NR; li < BLS_NL; li++) scol[li * BLS_COLS] = T[li - NR];
+    }
+    const float inv = 1.0f / (float)(WIN * WIN);
+    const int x = x0 + cx - h;                                      // output column of this thread
+    const bool consumer = cx >= h && cx < BLS_COLS - h && x < W;
+    // raw operands of a halo pixel (consumed one phase later: see the loop)
+    auto load_raw = [&](int r, int& l, int& rr, float& c) {
+        const int sy = border_idx(r, H, 1);
+        l = lcol[(size_t)sy * W]; rr = rcol[(size_t)sy * g.Wp];
+        c = NORM ? 1.0f : __ldg(&ccol[(size_t)sy * W]);
+    };
+    // what the horizontal phase needs from global memory is requested one row ahead
+    int I_nx = 0;
+    float2 nk_nx = make_float2(1.0f, 1.0f);
+    if (consumer) {
+        const size_t p0 = (size_t)yb0 * W + x;
+        I_nx = lg[p0];
+        if (!NORM) nk_nx = __ldg((const float2*)&Nk[p0 * 2]);
+    }
+    for (int y = yb0; y < yb1; y++) {
+        const size_t p = (size_t)y * W + (consumer ? x : 0);
+        const int I = I_nx;
+        const float2 nk = nk_nx;
+        float* const srow = sm_bls + buf * (BLS_NL * BLS_COLS);
+#pragma unroll
+        for (int li = 0; li < NR; li++) srow[cx + li * BLS_COLS] = V[li];
+        __syncthreads();
+        // requests that stay in flight during the horizontal phase: the pixels entering / leaving the window of the next
+        // row, and the next row's intensity / normaliser pair
+        int li_, ri_, lo_, ro_;
+        float ci, co;
+        load_raw(y + 1 + h, li_, ri_, ci);
+        load_raw(y - h, lo_, ro_, co);
+        if (consumer && y + 1 < yb1) {
+            I_nx = lg[p + W];
+            if (!NORM) nk_nx = __ldg((const float2*)&Nk[(p + W) * 2]);
+        }
+        if (consumer) {
+            const int lo = I / BLS_STEP;                           // level index of the lower key (A.cpp:2658)
+            const bool isl = (I - lo * BLS_STEP) == 0;             // discretInten membership (A.cpp:2656); 255 = 85 * 3
+            const int hi = min(lo + 1, BLS_NL - 1);
+            const float* slo = srow + lo * BLS_COLS + (cx - h);
+            const float* shi = srow + hi * BLS_COLS + (cx - h);
+            // WIN columns of both levels; batches of HB loads bound the registers the loads in flight take
+            constexpr int HB = WIN % 7 == 0 ? 7 : (WIN % 5 == 0 ? 5 : 3);
+            float s0 = 0.0f, s1 = 0.0f, u0 = 0.0f, u1 = 0.0f;
+#pragma unroll 1
+            for (int j0 = 0; j0 < WIN / HB * HB; j0 += HB) {
+                float a_[HB], b_[HB];
+#pragma unroll
+                for (int j = 0; j < HB; j++) { a_[j] = slo[j0 + j]; b_[j] = shi[j0 + j]; }
+#pragma unroll
+                for (int j = 0; j < HB; j++) {
+                    if (j & 1) { s1 += a_[j]; u1 += b_[j]; } else { s0 += a_[j]; u0 += b_[j]; }
+                }
+            }
+#pragma unroll
+            for (int j = WIN / HB * HB; j < WIN; j++) { s0 += slo[j]; u0 += shi[j]; }
+            const float jl = (s0 + s1) * inv, jh = (u0 + u1) * inv;
+            if (NORM) {                                            // N_k = box(M_{D-1})  (A.cpp:2588)
+                Nk_out[p * 2] = jl;
+                if (!isl) Nk_out[p * 2 + 1] = jh;
+            } else {
+                const float jbl = __fdiv_rn(jl, nk.x);            // A.cpp:2594
+                float cst = jbl;                                   // I is a level: cost = JB_{I,d}
+                if (!isl) {
+                    const int klo = lo * BLS_STEP, khi = min(klo + BLS_STEP, 255);
+                    cst = __fadd_rn(__fmul_rn((float)(I - klo), jbl), __fmul_rn((float)(khi - I), __fdiv_rn(jh, nk.y)));   // A.cpp:2666-2667
+                }
+                vol[(size_t)(di - slice0) * n + p] = cst;
+            }
+        }
+        if (NBUF == 1) __syncthreads(); else buf ^= 1;              // two buffers: the next row's stores go to the other one
+        // the raw operands are consumed only here: the compiler may not hoist their first use (and with it the wait for
+        // the loads) above the horizontal phase
+        asm volatile("" : "+r"(li_), "+r"(ri_), "+r"(lo_), "+r"(ro_));
+        if (y + 1 < yb1) {
+            const float ai = (float)(li_ * ri_), bi = (float)(li_ + ri_), ao = (float)(lo_ * ro_), bo = (float)(lo_ + ro_);
+            const float nco = -co;
+#pragma unroll
+            for (int li = 0; li < NR; li++) BLS_UPDATE(V[li], li)
+            // shared-memory levels in groups of 4: the fence keeps the compiler from hoisting every load of the row
+            // (one register each) above the arithmetic
+#pragma unroll
+            for (int l0 = NR; l0 < BLS_NL; l0 += 4) {
+                float v4[4];
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (l0 + q < BLS_NL) v4[q] = scol[(l0 + q) * BLS_COLS];
+#pragma unroll
+                for (int q = 0; q < 4; q++) if (l0 + q < BLS_NL) { BLS_UPDATE(v4[q], l0 + q) scol[(l0 + q) * BLS_COLS] = v4[q]; }
+                asm volatile("" ::: "memory");
+            }
+        }
+    }
+}
+#undef BLS_UPDATE
+
 template <int WIN>
 static asw_status launch_blo1_agg2(asw_ctx* ctx, const uint8_t* gref, const uint8_t* gtgt, const float* cost, float* Nk,
                                    const BloGeom& g, int min_d, unsigned long long* keys, float* agg_dev) {
@@ -399,6 +586,48 @@ static asw_status launch_blo1_agg2(asw_ctx* ctx, const uint8_t* gref, const uint
     }
     dim3 grid(cdiv(g.W, SW), cdiv(g.H, TH), cdiv(g.di_hi - g.di_lo, dch));
     LAUNCH(ctx, "blo1_aggregate", (k_blo1_agg2<WIN, false><<<grid, BLO2_THREADS, smem, ctx->stream>>>(gref, gtgt, cost, Nk, nullptr, g, dch, min_d, keys, agg_dev)));
+    return ASW_OK;
+}
+
+// streaming kernel (step 3 / 86 levels): normalisers, then the cost volume of slices [di_lo, di_hi), then the WTA pass
+template <int WIN>
+static asw_status launch_blo1_stream(asw_ctx* ctx, const uint8_t* gref, const uint8_t* gtgt, const float* cost, float* Nk,
+                                     const BloGeom& g, int min_d, unsigned long long* keys, float* agg_dev) {
+    constexpr int SW = BLS_COLS - (WIN - 1);
+    constexpr int NR = BLS_VARIANT_NR, NBUF = BLS_VARIANT_NBUF;
+    const size_t smem = (size_t)NBUF * BLS_NL * BLS_COLS * sizeof(float);
+    const size_t n = (size_t)g.H * g.W;
+    const int cnt = g.di_hi - g.di_lo, strips = cdiv(g.W, SW);
+    cudaFuncSetAttribute(k_blo1_stream<WIN, false, NR, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_blo1_stream<WIN, true, NR, NBUF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // bands: a band is entered once (WIN - 1 warm-up rows), so they are as tall as the CTA count allows: ~4 waves of
+    // 2 CTAs per SM for the aggregation, one wave for the single-slice normaliser launch
+    // The band count minimises (waves of resident CTAs) x (rows a CTA walks, warm-up included).
+    const int slots = ctx->sm_count * (NBUF == 2 ? 1 : 2);
+    auto rows_for = [&](int slices, int) {
+        int best_rows = g.H; long long best_cost = -1;
+        for (int bands = 1; bands <= std::max(1, g.H / (2 * WIN)); bands++) {
+            const int rows = cdiv(g.H, bands);
+            const long long cost = (long long)cdiv(strips * slices * cdiv(g.H, rows), slots) * (rows + WIN - 1);
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_rows = rows; }
+        }
+        return best_rows;
+    };
+    {
+        BloGeom gn = g;
+        gn.di_lo = g.D - 1; gn.di_hi = g.D;                          // the LAST disparity's M (A.cpp:2588)
+        const int br = rows_for(1, 2 * ctx->sm_count);
+        LAUNCH(ctx, "blo1_norm", (k_blo1_stream<WIN, true, NR, NBUF><<<dim3(strips, cdiv(g.H, br), 1), BLS_COLS, smem, ctx->stream>>>(
+                                     gref, gtgt, cost, nullptr, Nk, gn, br, 0, nullptr)));
+    }
+    float* vol = agg_dev;                                             // the capture volume is [num_d][H][W]: slice di at di
+    int slice0 = 0;
+    if (!vol) { ASW_TRY(ws_get(ctx, WS_VOL1, n * (size_t)cnt, &vol)); slice0 = g.di_lo; }
+    const int br = rows_for(cnt, 8 * ctx->sm_count);
+    LAUNCH(ctx, "blo1_aggregate", (k_blo1_stream<WIN, false, NR, NBUF><<<dim3(strips, cdiv(g.H, br), cnt), BLS_COLS, smem, ctx->stream>>>(
+                                      gref, gtgt, cost, Nk, nullptr, g, br, slice0, vol)));
+    LAUNCH(ctx, "wta_keys", (k_wta_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+                                vol + (size_t)(g.di_lo - slice0) * n, cnt, n, min_d + g.di_lo, keys)));
     return ASW_OK;
 }
 
@@ -439,6 +668,18 @@ static asw_status dev_blo1_range(asw_ctx* ctx, const uint8_t* dL, const uint8_t*
     const bool templated = !generic && (win == 5 || win == 7 || win == 9 || win == 15 || win == 25 || win == 35);
     if (!templated)   // exact integer normalisers for the tiled fallback (the register-resident kernel computes its own)
         LAUNCH(ctx, "blo1_norm", (k_blo1_norm<<<dim3(tiles.x, tiles.y, g.nl), BLO_THREADS, smem_n, ctx->stream>>>(gref, gtgt, g, Nk)));
+    // the dispatcher's level set (sampleRateR = 0.015: step 3, 86 levels, 255 among them) takes the streaming kernel
+    if (templated && g.step == BLS_STEP && g.nl == BLS_NL && !g.last255 && !asw_dev("ASW_BLO_AGG2")) {
+        switch (win) {
+            case 5: ASW_TRY(launch_blo1_stream<5>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+            case 7: ASW_TRY(launch_blo1_stream<7>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+            case 9: ASW_TRY(launch_blo1_stream<9>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+            case 15: ASW_TRY(launch_blo1_stream<15>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+            case 25: ASW_TRY(launch_blo1_stream<25>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+            default: ASW_TRY(launch_blo1_stream<35>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
+        }
+        return keys_to_disp(ctx, keys, n, disp_dev);
+    }
     switch (generic ? 0 : win) {
         case 5: ASW_TRY(launch_blo1_agg2<5>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;
         case 7: ASW_TRY(launch_blo1_agg2<7>(ctx, gref, gtgt, cost, Nk, g, min_d, keys, agg_dev)); break;

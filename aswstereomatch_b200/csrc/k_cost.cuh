@@ -169,17 +169,23 @@ k_sad_box_u8(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, i
     }
 }
 
-// WTA over a materialised volume -> 64-bit keys (strict <, ascending d, NaN/inf never win)
-__global__ void k_wta_keys(const float* __restrict__ vol, int D, size_t n, int d_first,
-                           unsigned long long* __restrict__ keys) {
+// WTA over a materialised volume -> 64-bit keys (strict <, ascending d, NaN/inf never win).  The D loads of a thread are
+// independent: 8 slices in flight per thread, streaming (evict-first) loads.
+__global__ void __launch_bounds__(256)
+k_wta_keys(const float* __restrict__ vol, int D, size_t n, int d_first, unsigned long long* __restrict__ keys) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    unsigned long long best = WTA_KEY_EMPTY;
-    for (int d = 0; d < D; d++) {
-        unsigned long long k = wta_key(vol[(size_t)d * n + i], d_first + d);
-        best = min(best, k);
+    float best = __int_as_float(0x7f800000);             // a cost of +inf (or NaN) never wins: the key stays empty
+    int bd = -1;
+    const float* p = vol + i;
+    for (int d0 = 0; d0 < D; d0 += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (d0 + u < D) v[u] = __ldcs(p + (size_t)(d0 + u) * n);
+#pragma unroll
+        for (int u = 0; u < 8; u++) if (d0 + u < D && v[u] < best) { best = v[u]; bd = d0 + u; }
     }
-    keys[i] = min(keys[i], best);
+    if (bd >= 0) keys[i] = min(keys[i], wta_key(best, d_first + bd));
 }
 __global__ void k_fill_u64(unsigned long long* __restrict__ p, size_t n, unsigned long long v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
