@@ -39,6 +39,11 @@ struct asw_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;   // batch transfers overlap the compute stream
+    // second compute stream + workspace bank: the two views of an LR frame are independent until the consistency check and
+    // run concurrently (view_begin / view_end); `stream` is always the stream the current view launches on
+    cudaStream_t stream_main = nullptr, stream_view = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int ws_bank = 0;
     cudaEvent_t ev_copy = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;      // asw_timer_*
     cudaEvent_t ev_p0 = nullptr, ev_p1 = nullptr;      // per-kernel profiling
@@ -62,7 +67,7 @@ struct asw_ctx {
     // tuning knobs (asw_set_tuning; 0 = the built-in choice)
     int tune[ASW_TUNE_COUNT] = {0};
     // host-built tables are cached per parameter set: nothing is uploaded (and nothing synchronises) on a repeated call
-    std::string table_key[4];
+    std::string table_key[8];
 };
 
 // workspace slots
@@ -97,7 +102,8 @@ static inline asw_status asw_fail(asw_ctx* ctx, asw_status st, const char* fmt, 
 // cached host-built table: true when slot `ks` already holds the table described by `what` (same buffer generation)
 static inline bool table_cached(asw_ctx* ctx, int ks, int ws_slot, const char* what) {
     char key[160];
-    snprintf(key, sizeof(key), "%u|%s", ctx->bufs[ws_slot].gen, what);
+    snprintf(key, sizeof(key), "%u|%s", ctx->bufs[ws_slot + ctx->ws_bank * WS_COUNT].gen, what);
+    ks += 4 * ctx->ws_bank;
     if (ctx->table_key[ks] == key) return true;
     ctx->table_key[ks] = key;
     return false;
@@ -105,11 +111,13 @@ static inline bool table_cached(asw_ctx* ctx, int ks, int ws_slot, const char* w
 
 // reserve a workspace slot (grow-only; contents undefined after growth)
 static inline asw_status ws_reserve(asw_ctx* ctx, int slot, size_t bytes, void** out) {
-    if ((int)ctx->bufs.size() < WS_COUNT) ctx->bufs.resize(WS_COUNT);
+    if ((int)ctx->bufs.size() < 2 * WS_COUNT) ctx->bufs.resize(2 * WS_COUNT);
+    slot += ctx->ws_bank * WS_COUNT;
     DevBuf& b = ctx->bufs[slot];
     if (b.cap < bytes) {
         if (b.p) {
             ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->stream_view) ASW_CUDA(ctx, cudaStreamSynchronize(ctx->ws_bank ? ctx->stream_main : ctx->stream_view));
             ASW_CUDA(ctx, cudaFree(b.p));
             b.p = nullptr; b.cap = 0;
         }
@@ -165,6 +173,23 @@ static inline asw_status prof_end(asw_ctx* ctx, const char* name) {
     } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Run what follows on the second compute stream with the second workspace bank (ordered after everything already on the
+// main stream), until view_switch_back() / view_join().  Used for the right view of an LR frame.
+static inline asw_status view_begin(asw_ctx* ctx) {
+    ASW_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream_main));
+    ASW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_view, ctx->ev_fork, 0));
+    ctx->stream = ctx->stream_view; ctx->ws_bank = 1;
+    return ASW_OK;
+}
+// back to the main stream / bank; the second stream keeps running
+static inline void view_switch_back(asw_ctx* ctx) { ctx->stream = ctx->stream_main; ctx->ws_bank = 0; }
+// the main stream waits for everything launched on the second one
+static inline asw_status view_join(asw_ctx* ctx) {
+    ASW_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream_view));
+    ASW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream_main, ctx->ev_join, 0));
+    return ASW_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

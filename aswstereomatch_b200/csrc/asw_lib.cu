@@ -39,10 +39,13 @@ extern "C" asw_status asw_create(int device, asw_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return ASW_ERR_CUDA;
     asw_ctx* ctx = new asw_ctx();
     ctx->device = device;
-    ctx->bufs.resize(WS_COUNT);
+    ctx->bufs.resize(2 * WS_COUNT);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream_view, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->h2d_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess ||
@@ -50,6 +53,9 @@ extern "C" asw_status asw_create(int device, asw_ctx** out) {
         cudaEventCreate(&ctx->ev_p0) != cudaSuccess || cudaEventCreate(&ctx->ev_p1) != cudaSuccess) {
         // release whatever was created before the failure (the handles start out null)
         if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+        if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+        if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+        if (ctx->stream_view) cudaStreamDestroy(ctx->stream_view);
         if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
         if (ctx->ev_t1) cudaEventDestroy(ctx->ev_t1);
         if (ctx->ev_p0) cudaEventDestroy(ctx->ev_p0);
@@ -60,6 +66,7 @@ extern "C" asw_status asw_create(int device, asw_ctx** out) {
         delete ctx;
         return ASW_ERR_CUDA;
     }
+    ctx->stream_main = ctx->stream;
     *out = ctx;
     return ASW_OK;
 }
@@ -67,15 +74,17 @@ extern "C" void asw_destroy(asw_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->h2d_stream);
-    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream_main);
+    cudaStreamSynchronize(ctx->stream_view);
     cudaStreamSynchronize(ctx->d2h_stream);
     for (auto& b : ctx->bufs) if (b.p) cudaFree(b.p);
     if (ctx->flush.p) cudaFree(ctx->flush.p);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaEventDestroy(ctx->ev_t0); cudaEventDestroy(ctx->ev_t1);
     cudaEventDestroy(ctx->ev_p0); cudaEventDestroy(ctx->ev_p1); cudaEventDestroy(ctx->ev_copy);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
     cudaStreamDestroy(ctx->h2d_stream); cudaStreamDestroy(ctx->d2h_stream);
-    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->stream_main); cudaStreamDestroy(ctx->stream_view);
     delete ctx;
 }
 extern "C" const char* asw_last_error(const asw_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
@@ -83,6 +92,7 @@ extern "C" asw_status asw_sync(asw_ctx* ctx) {
     if (!ctx) return ASW_ERR_BAD_ARG;
     ASW_CUDA(ctx, cudaStreamSynchronize(ctx->h2d_stream));
     ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream_view));
     ASW_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
     return ASW_OK;
 }
@@ -597,8 +607,15 @@ static asw_status dev_guidedf2_lr_refine(asw_ctx* ctx, const uint8_t* dL, const 
     ASW_TRY(ws_get(ctx, WS_DISP_R, n, &dr));
     ASW_TRY(ws_get(ctx, WS_FILLED, n, &filled));
     ASW_TRY(ws_get(ctx, WS_MASK, n, &valid));
-    ASW_TRY(dev_guidedf2(ctx, dL, dR, H, W, ASW_DISPARITY_LEFT, eps, win, min_d, num_d, dl, nullptr));
-    ASW_TRY(dev_guidedf2(ctx, dL, dR, H, W, ASW_DISPARITY_RIGHT, eps, win, min_d, num_d, dr, nullptr));
+    // the two views are independent until the consistency check: the right one runs on the second stream / workspace bank
+    // (small frames gain the most: its kernels fill the tails of the left view's; with per-kernel profiling on, every
+    // launch synchronises and the views simply alternate)
+    ASW_TRY(view_begin(ctx));
+    const asw_status st_r = dev_guidedf2(ctx, dL, dR, H, W, ASW_DISPARITY_RIGHT, eps, win, min_d, num_d, dr, nullptr);
+    view_switch_back(ctx);
+    const asw_status st_l = st_r == ASW_OK ? dev_guidedf2(ctx, dL, dR, H, W, ASW_DISPARITY_LEFT, eps, win, min_d, num_d, dl, nullptr) : st_r;
+    ASW_TRY(view_join(ctx));
+    ASW_TRY(st_l);
     ASW_TRY(dev_lr_refine(ctx, dL, dl, dr, H, W, tol, win, rate_s, rate_r, valid, filled, out));
     if (dl_out) *dl_out = dl;
     if (dr_out) *dr_out = dr;
