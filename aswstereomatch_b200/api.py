@@ -51,7 +51,7 @@ EXPORTS = [
     "asw_device_count", "asw_create", "asw_destroy", "asw_last_error", "asw_version", "asw_sync", "asw_stream",
     "asw_set_tuning", "asw_host_alloc", "asw_host_free", "asw_stereo_matching", "asw_method_candidates", "asw_adaptive_weight",
     "asw_adaptive_weight_direct8", "asw_adaptive_weight_geodesic", "asw_adaptive_weight_bilateral_grid", "asw_adaptive_weight_blo1",
-    "asw_adaptive_weight_guidedf", "asw_adaptive_weight_guidedf_2", "asw_adaptive_weight_weighted_median",
+    "asw_adaptive_weight_guidedf", "asw_adaptive_weight_guidedf_2", "asw_adaptive_weight_guidedf_3", "asw_ncc", "asw_cost_ncc", "asw_adaptive_weight_weighted_median",
     "asw_capture_aggregated", "asw_cost_tad_cg", "asw_cost_sad_box", "asw_wta", "asw_guided_filter",
     "asw_geodesic_dist", "asw_lr_check", "asw_fill_invalid", "asw_wmedian_refine", "asw_guidedf2_lr_refine",
     "asw_batch_create", "asw_batch_destroy", "asw_batch_set_active", "asw_batch_upload", "asw_batch_run_guidedf2_lr_refine",
@@ -97,6 +97,9 @@ def load_library():
         "asw_adaptive_weight_blo1": (ci, [vp, pu8, pu8, pf32, ci, cd, ci, ci, ci]),
         "asw_adaptive_weight_guidedf": (ci, [vp, pu8, pu8, pf32, ci, cd, ci, ci, ci]),
         "asw_adaptive_weight_guidedf_2": (ci, [vp, pu8, pu8, pf32, ci, cd, ci, ci, ci]),
+        "asw_adaptive_weight_guidedf_3": (ci, [vp, pu8, pu8, pf32, ci, cd, ci, ci, ci]),
+        "asw_ncc": (ci, [vp, pu8, pu8, pf32, ci, ci, ci, ci]),
+        "asw_cost_ncc": (ci, [vp, pu8, pu8, vp, ci, ci, ci, ci]),
         "asw_adaptive_weight_weighted_median": (ci, [vp, pu8, pu8, pf32, ci, ci, cd, cd, ci, ci]),
         "asw_capture_aggregated": (ci, [vp, vp, C.c_size_t]),
         "asw_cost_tad_cg": (ci, [vp, pu8, pu8, vp, cd, cd, cd, ci, ci, ci]),
@@ -287,6 +290,27 @@ class Context:
         return self._method(self.lib.asw_adaptive_weight_guidedf_2, leftImg, rightImg,
                             (int(dispType), float(eps), int(winSize), int(minDisparity), int(numDisparity)),
                             numDisparity, agg, strict)
+
+    def computeAdaptiveWeight_GuidedF_3(self, leftImg, rightImg, dispType=DISPARITY_LEFT, eps=1e-6, winSize=35,
+                                        minDisparity=186, numDisparity=144, agg=False, strict=False):
+        return self._method(self.lib.asw_adaptive_weight_guidedf_3, leftImg, rightImg,
+                            (int(dispType), float(eps), int(winSize), int(minDisparity), int(numDisparity)),
+                            numDisparity, agg, strict)
+
+    def computeNCC(self, leftImg, rightImg, dispType=DISPARITY_LEFT, winSize=7, minDisparity=0, numDisparity=30, strict=False):
+        """computeNCC, Mat overload (A.h:124-125)"""
+        return self._method(self.lib.asw_ncc, leftImg, rightImg,
+                            (int(dispType), int(winSize), int(minDisparity), int(numDisparity)), 0, False, strict)
+
+    def computeNCC_volume(self, leftImg, rightImg, dispType=DISPARITY_LEFT, winSize=7, minDisparity=0, numDisparity=30):
+        """computeNCC, vector overload (A.h:126-128): the normalised [D][H][W] cost volume"""
+        La, Ls = _u8(leftImg)
+        Ra, Rs = _u8(rightImg)
+        H, W = La.shape[:2]
+        vol = np.empty((numDisparity, H, W), np.float32)
+        self._chk(self.lib.asw_cost_ncc(self.h, C.byref(Ls), C.byref(Rs), vol.ctypes.data, int(dispType), int(winSize),
+                                        int(minDisparity), int(numDisparity)))
+        return vol
 
     def computeAdaptiveWeight_WeightedMedian(self, leftImg, rightImg, dispType=DISPARITY_LEFT, winSize=35,
                                              sampleRateS=10.0, sampleRateR=10.0, minDisparity=186,

@@ -77,7 +77,7 @@ enum {
     WS_MASK, WS_FILLED, WS_OUT, WS_SLICE_MM, WS_GRAY_L, WS_GRAY_R, WS_GEO_L, WS_GEO_R, WS_GRID_S, WS_GRID_C,
     WS_TABLE0, WS_TABLE1, WS_MISC0, WS_MISC1, WS_MISC2, WS_MISC3, WS_CAPTURE, WS_GUIDE_RDEN,
     WS_FEATF_REF, WS_FEATF_TGT, WS_GUIDE_NM, WS_GUIDE_RD2, WS_AFF, WS_REFINE_LIST,
-    WS_TRAD_C2, WS_TRAD_TABLE, WS_GRID_TI, WS_GRID_TD, WS_COUNT
+    WS_TRAD_C2, WS_TRAD_TABLE, WS_GRID_TI, WS_GRID_TD, WS_IMG_PAD, WS_GUIDE6, WS_COUNT
 };
 
 static inline asw_status asw_fail(asw_ctx* ctx, asw_status st, const char* fmt, const char* a = "", const char* b = "") {

@@ -8,6 +8,7 @@
 #include "k_guided_fast.cuh"
 #include "k_guided_stream.cuh"
 #include "k_refine.cuh"
+#include "k_ncc.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -549,6 +550,90 @@ static asw_status dev_guidedf(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR
         GuidePrep gp;
         ASW_TRY(prep_guide(ctx, guide6, H, W, 6, win, eps, &gp));
         ASW_TRY(dev_gf_generic_slice(ctx, gp, cost + (size_t)i * n, H, W, 6, win, q + (size_t)i * n));
+    }
+    unsigned long long* keys;
+    ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
+    ASW_TRY(init_keys(ctx, keys, n));
+    LAUNCH(ctx, "wta_keys", (k_wta_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(q, num_d, n, min_d, keys)));
+    return keys_to_disp(ctx, keys, n, disp_dev);
+}
+
+// NCC set-up on device: gray (RGB2GRAY on BGR bytes) reference, padded target, statistics of both
+struct NccDev { uint8_t *ref, *tgt; float *mr, *mt; double *sr, *st; ViewGeom v; };
+static asw_status dev_ncc_setup(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type, int win,
+                                int min_d, int num_d, NccDev* s) {
+    const size_t n = (size_t)H * W;
+    s->v = make_view(dL, dR, H, W, disp_type, min_d, num_d);
+    const size_t nt = (size_t)H * s->v.Wp;
+    ASW_TRY(ws_get(ctx, WS_GRAY_L, n, &s->ref));
+    ASW_TRY(ws_get(ctx, WS_GRAY_R, nt, &s->tgt));
+    ASW_TRY(ws_get(ctx, WS_TMP0, n, &s->mr));
+    ASW_TRY(ws_get(ctx, WS_TMP1, nt, &s->mt));
+    ASW_TRY(ws_get(ctx, WS_MISC2, n, &s->sr));
+    ASW_TRY(ws_get(ctx, WS_MISC3, nt, &s->st));
+    LAUNCH(ctx, "rgb2gray", (k_rgb2gray_on_bgr_pad<<<dim3(cdiv(W, 256), H), 256, 0, ctx->stream>>>(s->v.ref, H, W, 0, 0, s->ref)));
+    LAUNCH(ctx, "rgb2gray", (k_rgb2gray_on_bgr_pad<<<dim3(cdiv(s->v.Wp, 256), H), 256, 0, ctx->stream>>>(s->v.tgt, H, W, s->v.pad_l, s->v.pad_r, s->tgt)));
+    LAUNCH(ctx, "ncc_stats", (k_ncc_stats<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(s->ref, H, W, win, s->mr, s->sr)));
+    LAUNCH(ctx, "ncc_stats", (k_ncc_stats<<<dim3(cdiv(s->v.Wp, 128), H), 128, 0, ctx->stream>>>(s->tgt, H, s->v.Wp, win, s->mt, s->st)));
+    return ASW_OK;
+}
+// computeNCC, vector overload (A.cpp:924-1013): vol [num_d][n], every slice min-max normalised
+static asw_status dev_cost_ncc(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type, int win,
+                               int min_d, int num_d, float* vol) {
+    const size_t n = (size_t)H * W;
+    NccDev s;
+    ASW_TRY(dev_ncc_setup(ctx, dL, dR, H, W, disp_type, win, min_d, num_d, &s));
+    uint32_t* mm;
+    ASW_TRY(ws_get(ctx, WS_SLICE_MM, (size_t)2 * num_d, &mm));
+    LAUNCH(ctx, "init_slice_mm", (k_init_slice_mm<<<cdiv(num_d, 128), 128, 0, ctx->stream>>>(mm, num_d)));
+    LAUNCH(ctx, "ncc_cost", (k_ncc_cost<false><<<dim3(cdiv(W, 128), H, num_d), 128, 0, ctx->stream>>>(
+                                s.ref, s.mr, s.sr, s.tgt, s.mt, s.st, H, W, s.v.Wp, win, s.v.x0_base, s.v.x0_step, 0, min_d, vol, nullptr)));
+    LAUNCH(ctx, "minmax_f32", (k_minmax_f32_slices<<<dim3(std::max(1, ctx->sm_count * 2 / num_d), num_d), 256, 0, ctx->stream>>>(vol, n, mm)));
+    LAUNCH(ctx, "normalize_slices", (k_normalize_slices<<<dim3((unsigned)((n + 255) / 256), num_d), 256, 0, ctx->stream>>>(vol, n, mm)));
+    return ASW_OK;
+}
+// computeNCC, Mat overload (A.cpp:812-912; the dispatcher's NCC): LEFT scans offsets min .. max - 1 and keeps the MINIMUM
+// raw cost; RIGHT never writes its map (cost > DBL_MAX never holds)
+static asw_status dev_ncc(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type, int win, int min_d,
+                          int num_d, float* disp_dev) {
+    const size_t n = (size_t)H * W;
+    unsigned long long* keys;
+    ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
+    ASW_TRY(init_keys(ctx, keys, n));
+    if (disp_type == ASW_DISPARITY_LEFT && num_d > 1) {
+        NccDev s;
+        ASW_TRY(dev_ncc_setup(ctx, dL, dR, H, W, disp_type, win, min_d, num_d, &s));
+        LAUNCH(ctx, "ncc_cost", (k_ncc_cost<true><<<dim3(cdiv(W, 128), H, num_d - 1), 128, 0, ctx->stream>>>(
+                                    s.ref, s.mr, s.sr, s.tgt, s.mt, s.st, H, W, s.v.Wp, win, s.v.x0_base, s.v.x0_step, 0, min_d, nullptr, keys)));
+    }
+    return keys_to_disp(ctx, keys, n, disp_dev);
+}
+// computeAdaptiveWeight_GuidedF_3 (A.cpp:3063-3137): NCC cost; LEFT filters with the 6-channel merge of the left image and the
+// shifted right one, RIGHT builds the merge but hands the plain right image to the filter (A.cpp:3104)
+static asw_status dev_guidedf3(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int disp_type, double eps,
+                               int win, int min_d, int num_d, float* disp_dev, float* agg_dev) {
+    const size_t n = (size_t)H * W;
+    float* cost;
+    ASW_TRY(ws_get(ctx, WS_VOL0, n * num_d, &cost));
+    ASW_TRY(dev_cost_ncc(ctx, dL, dR, H, W, disp_type, win, min_d, num_d, cost));
+    float* q = agg_dev;
+    if (!q) ASW_TRY(ws_get(ctx, WS_VOL1, n * num_d, &q));
+    if (disp_type == ASW_DISPARITY_LEFT) {
+        ViewGeom v = make_view(dL, dR, H, W, disp_type, min_d, num_d);
+        uint8_t *tpad, *guide6;
+        ASW_TRY(ws_get(ctx, WS_IMG_PAD, (size_t)H * v.Wp * 3, &tpad));
+        ASW_TRY(ws_get(ctx, WS_GUIDE6, n * 6, &guide6));
+        LAUNCH(ctx, "pad_bgr", (k_pad_cols_bgr<<<dim3(cdiv(v.Wp, 128), H), 128, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, tpad)));
+        for (int i = 0; i < num_d; i++) {
+            LAUNCH(ctx, "merge_guide6", (k_merge_guide6<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(v.ref, tpad, H, W, v.Wp, num_d - i - 1, 1, guide6)));
+            GuidePrep gp;
+            ASW_TRY(prep_guide(ctx, guide6, H, W, 6, win, eps, &gp));
+            ASW_TRY(dev_gf_generic_slice(ctx, gp, cost + (size_t)i * n, H, W, 6, win, q + (size_t)i * n));
+        }
+    } else {
+        GuidePrep gp;
+        ASW_TRY(prep_guide(ctx, dR, H, W, 3, win, eps, &gp));
+        for (int i = 0; i < num_d; i++) ASW_TRY(dev_gf_generic_slice(ctx, gp, cost + (size_t)i * n, H, W, 3, win, q + (size_t)i * n));
     }
     unsigned long long* keys;
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));

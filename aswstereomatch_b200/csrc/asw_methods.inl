@@ -187,7 +187,7 @@ extern "C" asw_status asw_guidedf2_lr_refine(asw_ctx* ctx, const asw_u8_image* L
 // -------------------------------------------------------------------------------------------------
 // per-method entry points
 // -------------------------------------------------------------------------------------------------
-enum MethodId { M_TRAD, M_GEO, M_GRID, M_BLO1, M_GF1, M_GF2, M_WMED, M_D8 };
+enum MethodId { M_TRAD, M_GEO, M_GRID, M_BLO1, M_GF1, M_GF2, M_WMED, M_D8, M_GF3, M_NCC };
 struct MethodArgs {
     int id, disp_type, win, min_d, num_d;
     double p0, p1;   // method-specific: (gamma_c, gamma_g) | (rate_s, rate_r) | (rate_r) | (eps)
@@ -218,6 +218,8 @@ static asw_status dev_run_method(asw_ctx* ctx, const MethodArgs& m, const uint8_
     switch (m.id) {
     case M_GF2: return dev_guidedf2(ctx, dL, dR, H, W, m.disp_type, m.p0, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
     case M_GF1: return dev_guidedf(ctx, dL, dR, H, W, m.disp_type, m.p0, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
+    case M_GF3: return dev_guidedf3(ctx, dL, dR, H, W, m.disp_type, m.p0, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
+    case M_NCC: return dev_ncc(ctx, dL, dR, H, W, m.disp_type, m.win, m.min_d, m.num_d, disp_dev);
     case M_TRAD: return dev_traditional(ctx, dL, dR, H, W, m.p0, m.p1, m.disp_type, m.win, m.min_d, m.num_d, disp_dev, agg_dev);
     case M_D8:    // gamma_c = 30, gamma_g = win * 2 / 3 in integer arithmetic (A.cpp:1175)
         if (m.win * 2 / 3 == 0) return asw_fail(ctx, ASW_ERR_BAD_ARG, "8-direction ASW: window too small (gamma_g = 0)%s%s");
@@ -277,6 +279,34 @@ extern "C" asw_status asw_adaptive_weight_guidedf(asw_ctx* ctx, const asw_u8_ima
     MethodArgs m = {M_GF1, disp_type, win, min_d, num_d, eps, 0};
     return run_method_host(ctx, m, L, R, disp);
 }
+extern "C" asw_status asw_adaptive_weight_guidedf_3(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, asw_f32_image* disp,
+                                                    int disp_type, double eps, int win, int min_d, int num_d) {
+    MethodArgs m = {M_GF3, disp_type, win, min_d, num_d, eps, 0};
+    return run_method_host(ctx, m, L, R, disp);
+}
+extern "C" asw_status asw_ncc(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, asw_f32_image* disp, int disp_type, int win,
+                              int min_d, int num_d) {
+    MethodArgs m = {M_NCC, disp_type, win, min_d, num_d, 0, 0};
+    if (ctx && ctx->capture_host) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "the Mat-returning computeNCC has no cost volume; use asw_cost_ncc%s%s");
+    return run_method_host(ctx, m, L, R, disp);
+}
+extern "C" asw_status asw_cost_ncc(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, float* host_volume, int disp_type,
+                                   int win, int min_d, int num_d) {
+    ASW_TRY(check_pair(ctx, L, R, nullptr));
+    if (!host_volume || num_d <= 0 || min_d < 0 || (disp_type != 0 && disp_type != 1) || win <= 0 || win % 2 == 0)
+        return asw_fail(ctx, ASW_ERR_BAD_ARG, "bad cost arguments%s%s");                                  // A.cpp:939-942
+    ASW_CUDA(ctx, cudaSetDevice(ctx->device));
+    int H = L->rows, W = L->cols;
+    size_t n = (size_t)H * W;
+    uint8_t *dL, *dR;
+    ASW_TRY(upload_pair(ctx, L, R, &dL, &dR));
+    float* vol;
+    ASW_TRY(ws_get(ctx, WS_VOL0, n * num_d, &vol));
+    ASW_TRY(dev_cost_ncc(ctx, dL, dR, H, W, disp_type, win, min_d, num_d, vol));
+    ASW_CUDA(ctx, cudaMemcpyAsync(host_volume, vol, n * num_d * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ASW_OK;
+}
 extern "C" asw_status asw_adaptive_weight_guidedf_2(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, asw_f32_image* disp,
                                                     int disp_type, double eps, int win, int min_d, int num_d) {
     MethodArgs m = {M_GF2, disp_type, win, min_d, num_d, eps, 0};
@@ -300,8 +330,10 @@ static bool dispatcher_args(int algorithm, int disp_type, int win, int min_d, in
     case ASW_ALG_ADAPTIVE_WEIGHT_BLO1: *m = {M_BLO1, disp_type, win, min_d, num_d, 0.015, 0}; return true;        // A.cpp:70
     case ASW_ALG_ADAPTIVE_WEIGHT_GUIDED_FILTER: *m = {M_GF1, disp_type, win, min_d, num_d, 1e-6, 0}; return true; // A.cpp:73
     case ASW_ALG_ADAPTIVE_WEIGHT_GUIDED_FILTER_2: *m = {M_GF2, disp_type, win, min_d, num_d, 1e-6, 0}; return true; // A.cpp:76
+    case ASW_ALG_ADAPTIVE_WEIGHT_GUIDED_FILTER_3: *m = {M_GF3, disp_type, win, min_d, num_d, 1e-6, 0}; return true; // A.cpp:79
+    case ASW_ALG_NCC: *m = {M_NCC, disp_type, win, min_d, num_d, 0, 0}; return true;                              // A.cpp:85
     case ASW_ALG_ADAPTIVE_WEIGHT_MEDIAN: *m = {M_WMED, disp_type, win, min_d, num_d, 10, 10}; return true;        // A.cpp:82
-    default: return false;   // BM, SGBM, GuidedF_3, NCC: outside the hot path
+    default: return false;   // BM, SGBM: OpenCV's own matchers, outside the hot path
     }
 }
 // candidates the dispatcher's method scans for a named numDisparity (D + 1 where the reference loop runs to

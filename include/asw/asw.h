@@ -113,6 +113,14 @@ asw_status asw_adaptive_weight_guidedf(asw_ctx* ctx, const asw_u8_image* left, c
 asw_status asw_adaptive_weight_guidedf_2(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
                                          asw_f32_image* disparity, int disp_type, double eps, int win_size,
                                          int min_disparity, int num_disparity);
+/* computeAdaptiveWeight_GuidedF_3 (A.h:170-172, A.cpp:3063-3137): NCC cost, 6-channel guide (LEFT) */
+asw_status asw_adaptive_weight_guidedf_3(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                                         asw_f32_image* disparity, int disp_type, double eps, int win_size,
+                                         int min_disparity, int num_disparity);
+/* computeNCC, Mat overload (A.h:124-125, A.cpp:812-912; the dispatcher's NCC).  As in the reference, LEFT scans offsets
+ * min .. max - 1 and keeps the minimum raw cost; RIGHT leaves the map at 0 */
+asw_status asw_ncc(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right, asw_f32_image* disparity,
+                   int disp_type, int win_size, int min_disparity, int num_disparity);
 /* computeAdaptiveWeight_WeightedMedian (A.h:176-179, A.cpp:3228-3383) */
 asw_status asw_adaptive_weight_weighted_median(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
                                                asw_f32_image* disparity, int disp_type, int win_size,
@@ -133,6 +141,9 @@ asw_status asw_cost_tad_cg(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_
 asw_status asw_cost_sad_box(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
                             float* host_volume, int disp_type, int win_size, int min_disparity,
                             int num_disparity);
+/* computeNCC, vector overload (A.h:126-128, A.cpp:924-1013): [num_disparity][rows][cols], slices min-max normalised */
+asw_status asw_cost_ncc(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right, float* host_volume,
+                        int disp_type, int win_size, int min_disparity, int num_disparity);
 /* the inlined WTA blocks (A.cpp:3032-3048 ...): strict <, ascending d, NaN never wins, untouched = 0 */
 asw_status asw_wta(asw_ctx* ctx, const float* host_volume, int num_slices, int rows, int cols,
                    int min_disparity, asw_f32_image* disparity);

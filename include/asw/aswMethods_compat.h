@@ -126,6 +126,18 @@ inline Mat computeAdaptiveWeight_BLO1(Mat leftImg, Mat rightImg, DisparityType d
     return detail::run(leftImg, rightImg, [&](asw_ctx* c, const asw_u8_image* l, const asw_u8_image* r, asw_f32_image* d) {
         return asw_adaptive_weight_blo1(c, l, r, d, dispType, sampleRateR, winSize, minDisparity, numDisparity); });
 }
+// A.h:170-172
+inline Mat computeAdaptiveWeight_GuidedF_3(Mat leftImg, Mat rightImg, DisparityType dispType = DISPARITY_LEFT,
+                                           double eps = 1e-6, int winSize = 35, int minDisparity = 186, int numDisparity = 144) {
+    return detail::run(leftImg, rightImg, [&](asw_ctx* c, const asw_u8_image* l, const asw_u8_image* r, asw_f32_image* d) {
+        return asw_adaptive_weight_guidedf_3(c, l, r, d, dispType, eps, winSize, minDisparity, numDisparity); });
+}
+// A.h:124-125
+inline Mat computeNCC(Mat leftImg, Mat rightImg, DisparityType dispType = DISPARITY_LEFT, int winSize = 7,
+                      int minDisparity = 0, int numDisparity = 30) {
+    return detail::run(leftImg, rightImg, [&](asw_ctx* c, const asw_u8_image* l, const asw_u8_image* r, asw_f32_image* d) {
+        return asw_ncc(c, l, r, d, dispType, winSize, minDisparity, numDisparity); });
+}
 // A.h:164-166
 inline Mat computeAdaptiveWeight_GuidedF(Mat leftImg, Mat rightImg, DisparityType dispType = DISPARITY_LEFT,
                                          double eps = 1e-8, int winSize = 35, int minDisparity = 186, int numDisparity = 144) {

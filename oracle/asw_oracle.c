@@ -437,6 +437,157 @@ int orc_asw_guidedf(const uint8_t* L, const uint8_t* R, int H, int W, int disp_t
 }
 
 /* ------------------------------------------------------------------ */
+/* NCC cost (getInputImgNCC A.cpp:767-800, computeNCC A.cpp:812-1013) and GuidedF_3 (A.cpp:3063-3137).
+ * Quirks reproduced: computeNCC converts with COLOR_RGB2GRAY although the data is BGR (the R and B weights are
+ * swapped); the window mean comes from boxFilter (BORDER_REFLECT_101) while the window pixels come from a
+ * BORDER_REFLECT-padded copy; the "correlation" is sum(l r) / (sum(l l) * sum(r r)) -- no square root; the products
+ * are rounded to float (Mat::mul on CV_32F) and summed in double in window row-major order (cv::sum); the target's
+ * windows and means are taken from the PADDED target image (padding of the padding at its outer columns).
+ * The Mat-returning overload (the dispatcher's NCC) scans offsets min .. max-1 (strict <, A.cpp:852), keeps the
+ * MINIMUM raw double cost for LEFT and never writes anything for RIGHT (its > test starts from DBL_MAX).       */
+/* ------------------------------------------------------------------ */
+static void rgb2gray_on_bgr(const uint8_t* bgr, size_t npix, uint8_t* gray) {    /* COLOR_RGB2GRAY applied to BGR bytes */
+    for (size_t i = 0; i < npix; i++) {
+        int c0 = bgr[3 * i], c1 = bgr[3 * i + 1], c2 = bgr[3 * i + 2];
+        gray[i] = (uint8_t)((9798 * c0 + 19235 * c1 + 3735 * c2 + (1 << 14)) >> 15);
+    }
+}
+/* per pixel of a gray image: mean = boxFilter(u8 -> 32F) and s2 = sum over the window of fl((p - mean)^2), double */
+static void ncc_stats(const uint8_t* g, int H, int W, int win, float* mean, double* s2) {
+    int h = win / 2;
+    double scale = 1.0 / ((double)win * win);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            long sum = 0;
+            for (int j = -h; j <= h; j++)
+                for (int i = -h; i <= h; i++) sum += g[(size_t)border_idx(y + j, H, 1) * W + border_idx(x + i, W, 1)];
+            float m = (float)((double)sum * scale);
+            double acc = 0;
+            for (int j = -h; j <= h; j++)
+                for (int i = -h; i <= h; i++) {
+                    float v = (float)g[(size_t)border_idx(y + j, H, 0) * W + border_idx(x + i, W, 0)] + (-m);
+                    acc += (double)(v * v);
+                }
+            mean[(size_t)y * W + x] = m; s2[(size_t)y * W + x] = acc;
+        }
+}
+/* raw cost of one (pixel, offset): reference-side window at (y, x) of image a (width Wa), target-side window at (y, xt) of
+ * image b (width Wb) */
+static double ncc_raw(const uint8_t* a, int Wa, const float* ma, const double* s2a, const uint8_t* b, int Wb,
+                      const float* mb, const double* s2b, int H, int win, int y, int x, int xt) {
+    int h = win / 2;
+    float m0 = ma[(size_t)y * Wa + x], m1 = mb[(size_t)y * Wb + xt];
+    double sxy = 0;
+    for (int j = -h; j <= h; j++) {
+        int sy = border_idx(y + j, H, 0);
+        for (int i = -h; i <= h; i++) {
+            float u = (float)a[(size_t)sy * Wa + border_idx(x + i, Wa, 0)] + (-m0);
+            float v = (float)b[(size_t)sy * Wb + border_idx(xt + i, Wb, 0)] + (-m1);
+            sxy += (double)(u * v);
+        }
+    }
+    return sxy / (s2a[(size_t)y * Wa + x] * s2b[(size_t)y * Wb + xt]);
+}
+/* shared set-up: gray images, the padded target, the statistics of both.  LEFT: reference = left, target = right padded on
+ * the left, window column x + max_off - offset; RIGHT: reference = right, target = left padded on the right, x + offset */
+typedef struct { uint8_t *ref, *tgt; float *mr, *mt; double *sr, *st; int Wt; } NccSetup;
+static void ncc_setup(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, int win, int max_off, NccSetup* s) {
+    size_t n = (size_t)H * W;
+    uint8_t* lg = (uint8_t*)malloc(n); uint8_t* rg = (uint8_t*)malloc(n);
+    rgb2gray_on_bgr(L, n, lg); rgb2gray_on_bgr(R, n, rg);                  /* A.cpp:829-836 */
+    s->Wt = W + max_off;
+    if (disp_type == 0) { s->ref = lg; s->tgt = pad_cols_reflect_u8(rg, H, W, 1, max_off, 0); free(rg); }
+    else { s->ref = rg; s->tgt = pad_cols_reflect_u8(lg, H, W, 1, 0, max_off); free(lg); }
+    s->mr = (float*)malloc(n * sizeof(float)); s->sr = (double*)malloc(n * sizeof(double));
+    s->mt = (float*)malloc((size_t)H * s->Wt * sizeof(float)); s->st = (double*)malloc((size_t)H * s->Wt * sizeof(double));
+    ncc_stats(s->ref, H, W, win, s->mr, s->sr);
+    ncc_stats(s->tgt, H, s->Wt, win, s->mt, s->st);
+}
+static void ncc_free(NccSetup* s) { free(s->ref); free(s->tgt); free(s->mr); free(s->mt); free(s->sr); free(s->st); }
+
+/* computeNCC, vector overload (A.cpp:924-1013): [num_d][H][W], every slice min-max normalised to [0, 1] */
+int orc_cost_ncc(const uint8_t* L, const uint8_t* R, int H, int W, int min_d, int num_d, int disp_type, int win, float* vol) {
+    if (!L || !R || !vol || H <= 0 || W <= 0 || num_d <= 0 || min_d < 0 || win <= 0 || (win & 1) == 0) return ORC_BAD_ARG;
+    size_t n = (size_t)H * W;
+    int max_off = min_d + num_d - 1;
+    NccSetup s;
+    ncc_setup(L, R, H, W, disp_type, win, max_off, &s);
+#pragma omp parallel for schedule(dynamic)
+    for (int di = 0; di < num_d; di++) {
+        int offset = min_d + di;
+        float* raw = (float*)malloc(n * sizeof(float));
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                int xt = disp_type == 0 ? x + max_off - offset : x + offset;
+                raw[(size_t)y * W + x] = (float)ncc_raw(s.ref, W, s.mr, s.sr, s.tgt, s.Wt, s.mt, s.st, H, win, y, x, xt);
+            }
+        orc_normalize_minmax_f32(raw, (long)n, vol + (size_t)di * n);        /* A.cpp:974-976 */
+        free(raw);
+    }
+    ncc_free(&s);
+    return ORC_OK;
+}
+/* computeNCC, Mat overload (A.cpp:812-912): the dispatcher's NCC */
+int orc_asw_ncc(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, int win, int min_d, int num_d, float* disp) {
+    if (!L || !R || !disp || H <= 0 || W <= 0 || num_d <= 0 || min_d < 0 || win <= 0 || (win & 1) == 0) return ORC_BAD_ARG;
+    size_t n = (size_t)H * W;
+    int max_off = min_d + num_d - 1;
+    for (size_t i = 0; i < n; i++) disp[i] = 0.0f;
+    if (disp_type != 0) return ORC_OK;             /* RIGHT: cost > DBL_MAX never holds (A.cpp:892): nothing is written */
+    NccSetup s;
+    ncc_setup(L, R, H, W, 0, win, max_off, &s);
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            double best = DBL_MAX;
+            for (int offset = min_d; offset < max_off; offset++) {        /* strict <: the last candidate is never scanned */
+                double c = ncc_raw(s.ref, W, s.mr, s.sr, s.tgt, s.Wt, s.mt, s.st, H, win, y, x, x + max_off - offset);
+                if (c < best) { best = c; disp[(size_t)y * W + x] = (float)offset; }
+            }
+        }
+    ncc_free(&s);
+    return ORC_OK;
+}
+/* computeAdaptiveWeight_GuidedF_3 (A.cpp:3063-3137): NCC cost, 6-channel guide for LEFT; the RIGHT branch builds the same
+ * merge but hands the plain right image to the filter (A.cpp:3104) */
+int orc_asw_guidedf3(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, double eps, int win, int min_d,
+                     int num_d, float* disp, float* agg) {
+    if (!L || !R || !disp || H <= 0 || W <= 0 || num_d <= 0 || win <= 0) return ORC_BAD_ARG;
+    size_t n = (size_t)H * W;
+    int max_off = min_d + num_d - 1;
+    float* cost = (float*)malloc(n * num_d * sizeof(float));
+    int rc = orc_cost_ncc(L, R, H, W, min_d, num_d, disp_type, win, cost);
+    if (rc != ORC_OK) { free(cost); return rc; }
+    float* q = agg ? agg : (float*)malloc(n * num_d * sizeof(float));
+    uint8_t* rb = pad_cols_reflect_u8(R, H, W, 3, max_off, 0);
+    int Wp = W + max_off;
+#pragma omp parallel for schedule(dynamic)
+    for (int i = 0; i < num_d; i++) {
+        if (disp_type == 0) {
+            uint8_t* guide = (uint8_t*)malloc(n * 6);
+            int x0 = num_d - i - 1;                                         /* A.cpp:3084 */
+            for (int y = 0; y < H; y++)
+                for (int x = 0; x < W; x++) {
+                    const uint8_t* pl = L + ((size_t)y * W + x) * 3;
+                    const uint8_t* pr = rb + ((size_t)y * Wp + x0 + x) * 3;
+                    uint8_t* g6 = guide + ((size_t)y * W + x) * 6;
+                    g6[0] = pl[0]; g6[1] = pl[1]; g6[2] = pl[2]; g6[3] = pr[0]; g6[4] = pr[1]; g6[5] = pr[2];
+                }
+            orc_guided_filter(guide, 6, cost + i * n, H, W, win, eps, q + i * n);
+            free(guide);
+        } else {
+            orc_guided_filter(R, 3, cost + i * n, H, W, win, eps, q + i * n);   /* A.cpp:3104 */
+        }
+    }
+    free(rb);
+    orc_wta(q, num_d, H, W, min_d, disp);
+    if (!agg) free(q);
+    free(cost);
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------ */
 /* traditional (Yoon-Kweon) ASW (A.cpp:1016-1156)                      */
 /* ------------------------------------------------------------------ */
 int orc_asw_traditional(const uint8_t* L, const uint8_t* R, int H, int W, double gamma_c,
@@ -1109,7 +1260,9 @@ int orc_stereo_matching(const uint8_t* L, const uint8_t* R, int H, int W, int di
     case 6:  return orc_asw_blo1(L, R, H, W, disp_type, 0.015, win, min_d, num_d, disp, 0);
     case 7:  return orc_asw_guidedf(L, R, H, W, disp_type, 1e-6, win, min_d, num_d, disp, 0);
     case 8:  return orc_asw_guidedf2(L, R, H, W, disp_type, 1e-6, win, min_d, num_d, disp, 0);
+    case 9:  return orc_asw_guidedf3(L, R, H, W, disp_type, 1e-6, win, min_d, num_d, disp, 0);     /* A.cpp:79 */
     case 10: return orc_asw_weighted_median(L, R, H, W, disp_type, win, 10, 10, min_d, num_d, disp, 0);
-    default: return ORC_UNSUPPORTED;   /* BM, SGBM, GuidedF_3, NCC: out of scope */
+    case 11: return orc_asw_ncc(L, R, H, W, disp_type, win, min_d, num_d, disp);                  /* A.cpp:85 */
+    default: return ORC_UNSUPPORTED;   /* BM, SGBM: third-party algorithms, out of scope */
     }
 }

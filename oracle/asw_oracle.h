@@ -81,6 +81,12 @@ int orc_asw_blo1(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type
                  int win, int min_d, int num_d, float* disp, float* agg); /* A.cpp:2505-2725 */
 int orc_asw_guidedf(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, double eps,
                     int win, int min_d, int num_d, float* disp, float* agg); /* A.cpp:2867-2963 */
+int orc_cost_ncc(const uint8_t* L, const uint8_t* R, int H, int W, int min_d, int num_d, int disp_type, int win,
+                 float* vol);                                           /* A.cpp:767-800, 924-1013 */
+int orc_asw_ncc(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, int win, int min_d, int num_d,
+                float* disp);                                           /* A.cpp:812-912 (dispatcher's NCC) */
+int orc_asw_guidedf3(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, double eps, int win,
+                     int min_d, int num_d, float* disp, float* agg);     /* A.cpp:3063-3137 */
 int orc_asw_guidedf2(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, double eps,
                      int win, int min_d, int num_d, float* disp, float* agg); /* A.cpp:2976-3050 */
 int orc_asw_weighted_median(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type,

@@ -191,6 +191,29 @@ def asw_guidedf(L, R, disp_type=0, eps=1e-6, win=9, min_d=0, num_d=16, agg=False
                    (int(disp_type), C.c_double(eps), int(win), int(min_d), int(num_d)), agg)
 
 
+def asw_guidedf3(L, R, disp_type=0, eps=1e-6, win=9, min_d=0, num_d=16, agg=False):
+    return _method(lib().orc_asw_guidedf3, L, R, num_d,
+                   (int(disp_type), C.c_double(eps), int(win), int(min_d), int(num_d)), agg)
+
+
+def asw_ncc(L, R, disp_type=0, win=9, min_d=0, num_d=16):
+    L, pl = _u8(L)
+    R, pr = _u8(R)
+    H, W = L.shape[:2]
+    disp = np.empty((H, W), np.float32)
+    _chk(lib().orc_asw_ncc(pl, pr, H, W, int(disp_type), int(win), int(min_d), int(num_d), disp.ctypes.data_as(f32p)), "asw_ncc")
+    return disp
+
+
+def cost_ncc(L, R, min_d, num_d, win, disp_type=0):
+    L, pl = _u8(L)
+    R, pr = _u8(R)
+    H, W = L.shape[:2]
+    vol = np.empty((num_d, H, W), np.float32)
+    _chk(lib().orc_cost_ncc(pl, pr, H, W, int(min_d), int(num_d), int(disp_type), int(win), vol.ctypes.data_as(f32p)), "cost_ncc")
+    return vol
+
+
 def asw_guidedf2(L, R, disp_type=0, eps=1e-6, win=9, min_d=0, num_d=16, agg=False):
     return _method(lib().orc_asw_guidedf2, L, R, num_d,
                    (int(disp_type), C.c_double(eps), int(win), int(min_d), int(num_d)), agg)

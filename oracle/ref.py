@@ -115,6 +115,23 @@ def asw_guidedf2(L, R, disp_type=0, eps=1e-6, win=9, min_d=0, num_d=16):
     return _method("ref_adaptive_weight_guidedf_2", L, R, (int(disp_type), C.c_double(eps), int(win), int(min_d), int(num_d)))
 
 
+def asw_guidedf3(L, R, disp_type=0, eps=1e-6, win=9, min_d=0, num_d=16):
+    return _method("ref_adaptive_weight_guidedf_3", L, R, (int(disp_type), C.c_double(eps), int(win), int(min_d), int(num_d)))
+
+
+def asw_ncc(L, R, disp_type=0, win=9, min_d=0, num_d=16):
+    return _method("ref_ncc", L, R, (int(disp_type), int(win), int(min_d), int(num_d)))
+
+
+def cost_ncc(L, R, min_d, num_d, win, disp_type=0):
+    L, pl = _u8(L)
+    R, pr = _u8(R)
+    H, W = L.shape[:2]
+    vol = np.empty((num_d, H, W), np.float32)
+    ok = _chk(lib().ref_cost_ncc(pl, pr, H, W, int(min_d), int(num_d), int(disp_type), int(win), vol.ctypes.data_as(f32p)), "cost_ncc")
+    return vol if ok else None
+
+
 def asw_weighted_median(L, R, disp_type=0, win=9, rate_s=10.0, rate_r=10.0, min_d=0, num_d=16):
     return _method("ref_adaptive_weight_weighted_median", L, R, (int(disp_type), int(win), C.c_double(rate_s),
                                                                   C.c_double(rate_r), int(min_d), int(num_d)))

@@ -99,6 +99,23 @@ int ref_adaptive_weight_weighted_median(const uint8_t* L, const uint8_t* R, int 
     GUARD(return put_f32(computeAdaptiveWeight_WeightedMedian(wrap_u8(L, H, W, 3), wrap_u8(R, H, W, 3), (DisparityType)disp_type,
                                                               win, rate_s, rate_r, min_d, num_d), H, W, disp);)
 }
+int ref_adaptive_weight_guidedf_3(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, double eps, int win,
+                                  int min_d, int num_d, float* disp) {
+    GUARD(return put_f32(computeAdaptiveWeight_GuidedF_3(wrap_u8(L, H, W, 3), wrap_u8(R, H, W, 3), (DisparityType)disp_type, eps,
+                                                         win, min_d, num_d), H, W, disp);)
+}
+/* computeNCC, Mat overload (A.h:124-125) */
+int ref_ncc(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type, int win, int min_d, int num_d, float* disp) {
+    GUARD(return put_f32(computeNCC(wrap_u8(L, H, W, 3), wrap_u8(R, H, W, 3), (DisparityType)disp_type, win, min_d, num_d), H, W, disp);)
+}
+/* computeNCC, vector overload (A.h:126-128): vol [num_d][H][W] */
+int ref_cost_ncc(const uint8_t* L, const uint8_t* R, int H, int W, int min_d, int num_d, int disp_type, int win, float* vol) {
+    GUARD(std::vector<cv::Mat> costs;
+          computeNCC(wrap_u8(L, H, W, 3), wrap_u8(R, H, W, 3), costs, (DisparityType)disp_type, win, min_d, num_d);
+          if ((int)costs.size() != num_d) return -1;
+          for (int d = 0; d < num_d; d++) { int rc = put_f32(costs[d], H, W, vol + (size_t)d * H * W); if (rc) return rc; }
+          return 0;)
+}
 /* computeSimilarity 7-arg (A.h:112-114): vol [num_d][H][W] */
 int ref_cost_tad_cg(const uint8_t* L, const uint8_t* R, int H, int W, int min_d, int num_d, int disp_type, double regularity,
                     double thres_c, double thres_g, float* vol) {

@@ -118,8 +118,22 @@ def test_config1_window_equals_reference():
 def test_dispatcher_equals_reference():
     """stereoMatching with its own literals (A.cpp:46-88)"""
     L, R, _ = make_pair(40, 56, 6, 17)
-    for alg in (2, 4, 5, 6, 7, 8, 10):
+    for alg in (2, 3, 4, 5, 6, 7, 8, 9, 10, 11):
         assert np.array_equal(orc.stereo_matching(L, R, 0, alg, 9, 0, 6), ref.stereo_matching(L, R, 0, alg, 9, 0, 6)), alg
+
+
+@needs_ref
+@pytest.mark.parametrize("H,W,D,win,seed", [(40, 56, 6, 9, 3), (33, 47, 5, 5, 8), (30, 40, 4, 15, 2)])
+def test_direct8_ncc_guidedf3_equal_reference(H, W, D, win, seed):
+    """rows f-3 / f-4: the 8-direction method (LEFT; its RIGHT branch indexes out of bounds), the NCC cost in both overloads
+    and GuidedF_3, both views"""
+    L, R, _ = make_pair(H, W, D, seed)
+    assert np.array_equal(orc.asw_direct8(L, R, 0, win, 0, D), ref.asw_direct8(L, R, 0, win, 0, D))
+    for dt in (0, 1):
+        assert np.array_equal(orc.cost_ncc(L, R, 0, D, win, dt), ref.cost_ncc(L, R, 0, D, win, dt))
+        assert np.array_equal(orc.asw_guidedf3(L, R, dt, 1e-6, win, 0, D), ref.asw_guidedf3(L, R, dt, 1e-6, win, 0, D))
+        assert np.array_equal(orc.asw_ncc(L, R, dt, win, 0, D), ref.asw_ncc(L, R, dt, win, 0, D))
+    assert not ref.asw_ncc(L, R, 1, win, 0, D).any()                # the RIGHT branch of the Mat overload never writes
 
 
 @needs_ref
@@ -168,5 +182,10 @@ def test_golden_from_reference_own_code(gold):
     assert eq(orc.asw_guidedf2(L, R, 0, 1e-4, 9, 0, D), gold["guidedf2_w9_eps1e-4"])
     assert eq(orc.asw_guidedf2(L, R, 0, 1e-6, 15, 0, D), gold["guidedf2_w15_eps1e-6"])
     assert eq(orc.asw_weighted_median(L, R, 0, 7, 10, 10, 0, D), gold["wmedian_w7"])
-    for alg in (2, 4, 5, 6, 7, 8, 10):
+    assert eq(orc.asw_direct8(L, R, 0, 9, 0, D), gold["direct8_w9"])
+    assert eq(orc.cost_ncc(L, R, 0, D, 7, 0), gold["cost_ncc_w7"])
+    assert eq(orc.asw_guidedf3(L, R, 0, 1e-6, 9, 0, D), gold["guidedf3_w9"])
+    assert eq(orc.asw_guidedf3(L, R, 1, 1e-6, 9, 0, D), gold["guidedf3_w9_right"])
+    assert eq(orc.asw_ncc(L, R, 0, 9, 0, D), gold["ncc_w9"])
+    for alg in (2, 3, 4, 5, 6, 7, 8, 9, 10, 11):
         assert eq(orc.stereo_matching(L, R, 0, alg, 9, 0, D), gold[f"dispatch_alg{alg}_w9"]), alg

@@ -222,9 +222,26 @@ def test_direct8_reference_golden(ctx):
     assert (d == g["direct8_w9"]).mean() >= AGREE
 
 
+@pytest.mark.parametrize("H,W,D,win,seed", [(40, 56, 6, 9, 3), (33, 47, 5, 5, 8), (64, 90, 9, 7, 4)])
+def test_ncc_and_guidedf3(ctx, H, W, D, win, seed):
+    """row f-4: computeNCC (both overloads, A.cpp:812-1013) and GuidedF_3 (A.cpp:3063-3137), both views"""
+    L, R, _ = make_pair(H, W, D, seed)
+    for dt in (0, 1):
+        v = ctx.computeNCC_volume(L, R, dt, win, 0, D)
+        v_ref = orc.cost_ncc(L, R, 0, D, win, dt)
+        assert np.abs(v - v_ref).max() <= 1e-6
+        d, q = ctx.computeAdaptiveWeight_GuidedF_3(L, R, dt, 1e-6, win, 0, D, agg=True, strict=True)
+        d_ref, q_ref = orc.asw_guidedf3(L, R, dt, 1e-6, win, 0, D, agg=True)
+        assert rel_err(q, q_ref) <= REL_TOL
+        assert (d == d_ref).mean() >= AGREE
+        assert (ctx.computeNCC(L, R, dt, win, 0, D, strict=True) == orc.asw_ncc(L, R, dt, win, 0, D)).mean() >= AGREE
+    assert np.array_equal(ctx.stereoMatching(L, R, 0, asw.NCC, win, 0, D, strict=True), ctx.computeNCC(L, R, 0, win, 0, D))
+    assert ctx.computeNCC(L, R, 0, 8, 0, D).size == 0                # even window: empty Mat (A.cpp:824-827)
+
+
 def test_dispatcher_out_of_scope(ctx):
     L, R, _ = make_pair(32, 40, 4, 1)
-    for alg in (asw.BM, asw.SGBM, asw.ADAPTIVE_WEIGHT_GUIDED_FILTER_3, asw.NCC):
+    for alg in (asw.BM, asw.SGBM):
         assert ctx.stereoMatching(L, R, 0, alg, 9, 0, 4).size == 0
         with pytest.raises(asw.AswError):
             ctx.stereoMatching(L, R, 0, alg, 9, 0, 4, strict=True)

@@ -59,7 +59,17 @@ def test_methods_against_reference_golden(ctx, gold):
     assert agree(ctx.computeAdaptiveWeight_WeightedMedian(L, R, 0, 7, 10, 10, 0, D, strict=True), gold["wmedian_w7"]) >= AGREE
 
 
-@pytest.mark.parametrize("alg", [2, 4, 5, 6, 7, 8, 10])
+def test_ncc_family_against_reference_golden(ctx, gold):
+    L, R, D = gold["L"], gold["R"], int(gold["D"])
+    assert np.abs(ctx.computeNCC_volume(L, R, 0, 7, 0, D) - gold["cost_ncc_w7"]).max() <= 1e-6      # same double sums: ~exact
+    assert agree(ctx.computeAdaptiveWeight_GuidedF_3(L, R, 0, 1e-6, 9, 0, D, strict=True), gold["guidedf3_w9"]) >= AGREE
+    assert agree(ctx.computeAdaptiveWeight_GuidedF_3(L, R, 1, 1e-6, 9, 0, D, strict=True), gold["guidedf3_w9_right"]) >= AGREE
+    assert agree(ctx.computeNCC(L, R, 0, 9, 0, D, strict=True), gold["ncc_w9"]) >= AGREE
+    assert not ctx.computeNCC(L, R, 1, 9, 0, D, strict=True).any()
+    assert agree(ctx.computeAdaptiveWeight_direct8(L, R, 0, 9, 0, D, strict=True), gold["direct8_w9"]) >= AGREE
+
+
+@pytest.mark.parametrize("alg", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11])
 def test_dispatcher_against_reference_golden(ctx, gold, alg):
     L, R, D = gold["L"], gold["R"], int(gold["D"])
     assert agree(ctx.stereoMatching(L, R, 0, alg, 9, 0, D, strict=True), gold[f"dispatch_alg{alg}_w9"]) >= AGREE

@@ -41,7 +41,11 @@ def main():
     out["guidedf2_w9_eps1e-4"] = ref.asw_guidedf2(L, R, 0, 1e-4, 9, 0, D)
     out["guidedf2_w15_eps1e-6"] = ref.asw_guidedf2(L, R, 0, 1e-6, 15, 0, D)
     out["wmedian_w7"] = ref.asw_weighted_median(L, R, 0, 7, 10, 10, 0, D)
-    for alg in (2, 4, 5, 6, 7, 8, 10):                                        # the dispatcher with its literals, win 9
+    out["cost_ncc_w7"] = ref.cost_ncc(L, R, 0, D, 7, 0)                       # computeNCC vector overload
+    out["guidedf3_w9"] = ref.asw_guidedf3(L, R, 0, 1e-6, 9, 0, D)
+    out["guidedf3_w9_right"] = ref.asw_guidedf3(L, R, 1, 1e-6, 9, 0, D)
+    out["ncc_w9"] = ref.asw_ncc(L, R, 0, 9, 0, D)                             # computeNCC Mat overload
+    for alg in (2, 3, 4, 5, 6, 7, 8, 9, 10, 11):                              # the dispatcher with its literals, win 9
         out[f"dispatch_alg{alg}_w9"] = ref.stereo_matching(L, R, 0, alg, 9, 0, D)
     for k, v in out.items():
         assert v is not None, k
