@@ -53,7 +53,7 @@ EXPORTS = [
     "asw_adaptive_weight_direct8", "asw_adaptive_weight_geodesic", "asw_adaptive_weight_bilateral_grid", "asw_adaptive_weight_blo1",
     "asw_adaptive_weight_guidedf", "asw_adaptive_weight_guidedf_2", "asw_adaptive_weight_guidedf_3", "asw_ncc", "asw_cost_ncc", "asw_adaptive_weight_weighted_median",
     "asw_capture_aggregated", "asw_cost_tad_cg", "asw_cost_sad_box", "asw_wta", "asw_guided_filter",
-    "asw_geodesic_dist", "asw_lr_check", "asw_fill_invalid", "asw_wmedian_refine", "asw_guidedf2_lr_refine",
+    "asw_geodesic_dist", "asw_lr_check", "asw_fill_invalid", "asw_wmedian_refine", "asw_guidedf2_lr_refine", "asw_disparity_to_u8",
     "asw_batch_create", "asw_batch_destroy", "asw_batch_set_active", "asw_batch_upload", "asw_batch_run_guidedf2_lr_refine",
     "asw_batch_run_method", "asw_batch_download", "asw_split_local_keys", "asw_keys_alloc", "asw_keys_download",
     "asw_keys_upload", "asw_keys_min_merge", "asw_keys_to_disparity", "asw_keys_flip_sign", "asw_pool_create",
@@ -111,6 +111,7 @@ def load_library():
         "asw_fill_invalid": (ci, [vp, pf32, pmask, pf32]),
         "asw_wmedian_refine": (ci, [vp, pu8, pf32, pmask, ci, cd, cd, pf32]),
         "asw_guidedf2_lr_refine": (ci, [vp, pu8, pu8, pf32, cd, ci, ci, ci, cf, cd, cd, pf32, pf32, pmask]),
+        "asw_disparity_to_u8": (ci, [vp, pf32, pmask]),
         "asw_batch_create": (ci, [vp, ci, ci, ci, C.POINTER(vp)]),
         "asw_batch_destroy": (None, [vp]),
         "asw_batch_set_active": (ci, [vp, ci]),
@@ -404,6 +405,13 @@ class Context:
                                                   int(win), int(min_d), int(num_d), float(tol), float(rate_s),
                                                   float(rate_r), None, None, None))
         return out
+
+    def disparity_to_u8(self, disp):
+        """the driver's 8-bit output (aswStereoMatch.cpp:97-98): convertTo(CV_8UC1) + normalize(0, 255, NORM_MINMAX)"""
+        a, as_ = _f32_in(disp)
+        m, ms = _mask_out(a.shape[0], a.shape[1])
+        self._chk(self.lib.asw_disparity_to_u8(self.h, C.byref(as_), C.byref(ms)))
+        return m
 
     # ---- disparity split ----
     def split_local_keys(self, L, R, algorithm, disp_type, win, min_d, num_d, d_begin, d_end):

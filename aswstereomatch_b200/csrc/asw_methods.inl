@@ -158,6 +158,24 @@ extern "C" asw_status asw_wmedian_refine(asw_ctx* ctx, const asw_u8_image* img, 
     return ASW_OK;
 }
 
+// driver post-processing on the device (aswStereoMatch.cpp:97-98): the 8-bit, min-max stretched map the driver writes
+extern "C" asw_status asw_disparity_to_u8(asw_ctx* ctx, const asw_f32_image* disp, asw_mask_image* out) {
+    if (!ctx) return ASW_ERR_BAD_ARG;
+    ASW_TRY(check_f32(ctx, disp)); ASW_TRY(check_mask(ctx, out));
+    if (out->rows != disp->rows || out->cols != disp->cols) return asw_fail(ctx, ASW_ERR_SIZE_MISMATCH, "map sizes differ%s%s");
+    ASW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t n = (size_t)disp->rows * disp->cols;
+    float* d; uint8_t* o; int* mm;
+    ASW_TRY(ws_get(ctx, WS_DISP_L, n, &d)); ASW_TRY(ws_get(ctx, WS_MASK, n, &o)); ASW_TRY(ws_get(ctx, WS_MISC0, (size_t)64, &mm));
+    ASW_TRY(upload_f32(ctx, disp, d));
+    LAUNCH(ctx, "init_mm", (k_init_mm_u8<<<1, 1, 0, ctx->stream>>>(mm)));
+    LAUNCH(ctx, "disp_round_minmax", (k_disp_round_minmax<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d, n, o, mm)));
+    LAUNCH(ctx, "disp_normalize_u8", (k_disp_normalize_u8<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(o, n, mm)));
+    ASW_TRY(download_mask(ctx, o, out));
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ASW_OK;
+}
+
 static bool valid_disp_args(int disp_type, int min_d, int num_d) {
     return (disp_type == 0 || disp_type == 1) && min_d >= 0 && num_d > 0;
 }

@@ -215,3 +215,27 @@ k_lr_fill_compact(const float* __restrict__ dl, const float* __restrict__ dr, in
         list[atomicAdd(count, 1)] = (int)p;
     }
 }
+
+// driver post-processing (aswStereoMatch.cpp:97-98): convertTo(CV_8UC1) (cvRound + saturate) and its min / max ...
+__global__ void k_disp_round_minmax(const float* __restrict__ d, size_t n, uint8_t* __restrict__ out, int* __restrict__ mm) {
+    int mn = 255, mx = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int v = min(max(__float2int_rn(d[i]), 0), 255);
+        out[i] = (uint8_t)v;
+        mn = min(mn, v); mx = max(mx, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) { atomicMin(&mm[0], mn); atomicMax(&mm[1], mx); }
+}
+// ... then normalize(0, 255, NORM_MINMAX) of the u8 map: double scale / shift, applied in float with one fused multiply-add
+__global__ void k_disp_normalize_u8(uint8_t* __restrict__ io, size_t n, const int* __restrict__ mm) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double span = (double)(mm[1] - mm[0]);
+    const double scale = 255.0 * (span > 2.220446049250313e-16 ? 1.0 / span : 0.0);
+    const double shift = 0.0 - (double)mm[0] * scale;
+    io[i] = (uint8_t)min(max(__float2int_rn(fmaf((float)io[i], (float)scale, (float)shift)), 0), 255);
+}

@@ -168,6 +168,9 @@ asw_status asw_guidedf2_lr_refine(asw_ctx* ctx, const asw_u8_image* left, const 
                                   int num_disparity, float lr_tol, double rate_s, double rate_r,
                                   asw_f32_image* raw_left, asw_f32_image* raw_right, asw_mask_image* valid);
 
+/* driver post-processing (aswStereoMatch.cpp:97-98): disparityMap.convertTo(CV_8UC1) + normalize(0, 255, NORM_MINMAX) */
+asw_status asw_disparity_to_u8(asw_ctx* ctx, const asw_f32_image* disparity, asw_mask_image* out_u8);
+
 /* ---- device-resident batches (config 5; inputs live in HBM between upload and run) ---- */
 typedef struct asw_batch asw_batch;
 asw_status asw_batch_create(asw_ctx* ctx, int n_pairs, int rows, int cols, asw_batch** out);

@@ -1250,6 +1250,29 @@ int orc_wmedian_refine(const uint8_t* img, const float* filled, const uint8_t* v
 /* ------------------------------------------------------------------ */
 /* dispatcher (A.cpp:46-88)                                            */
 /* ------------------------------------------------------------------ */
+/* driver post-processing (aswStereoMatch.cpp:97-98): disparityMap.convertTo(CV_8UC1) then
+ * normalize(0, 255, NORM_MINMAX) on the u8 map: scale = 255 / (max - min) (0 if max == min), shift = -min * scale in
+ * double, applied in float as saturate_cast<uchar>(fma(v, (float)scale, (float)shift)) (pinned against cv2 4.13) */
+/* ------------------------------------------------------------------ */
+void orc_disparity_to_u8(const float* disp, int H, int W, uint8_t* out) {
+    size_t n = (size_t)H * W;
+    int mn = 255, mx = 0;
+    for (size_t i = 0; i < n; i++) {
+        long v = lrintf(disp[i]);                                  /* convertTo(CV_8UC1): cvRound + saturate */
+        out[i] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+        if (out[i] < mn) mn = out[i];
+        if (out[i] > mx) mx = out[i];
+    }
+    double scale = 255.0 * ((double)(mx - mn) > DBL_EPSILON ? 1.0 / (double)(mx - mn) : 0.0);
+    double shift = 0.0 - (double)mn * scale;
+    float sf = (float)scale, hf = (float)shift;
+    for (size_t i = 0; i < n; i++) {
+        long v = lrintf(fmaf((float)out[i], sf, hf));
+        out[i] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+    }
+}
+
+/* ------------------------------------------------------------------ */
 int orc_stereo_matching(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type,
                         int algorithm, int win, int min_d, int num_d, float* disp) {
     switch (algorithm) {

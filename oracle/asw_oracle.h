@@ -99,6 +99,9 @@ void orc_fill_invalid(const float* d, const uint8_t* valid, int H, int W, float*
 int orc_wmedian_refine(const uint8_t* img, const float* filled, const uint8_t* valid, int H, int W,
                        int win, double rate_s, double rate_r, float* out);
 
+/* driver post-processing (aswStereoMatch.cpp:97-98): convertTo(CV_8UC1) + normalize(0, 255, NORM_MINMAX) */
+void orc_disparity_to_u8(const float* disp, int H, int W, uint8_t* out);
+
 /* dispatcher literals (A.cpp:46-88); algorithm ids as P.h:10-24 */
 int orc_stereo_matching(const uint8_t* L, const uint8_t* R, int H, int W, int disp_type,
                         int algorithm, int win, int min_d, int num_d, float* disp);

@@ -253,6 +253,13 @@ def wmedian_refine(img, filled, valid, win=9, rate_s=10.0, rate_r=10.0):
     return out
 
 
+def disparity_to_u8(disp):
+    d, pd = _f32(disp)
+    out = np.empty(d.shape, np.uint8)
+    lib().orc_disparity_to_u8(pd, d.shape[0], d.shape[1], out.ctypes.data_as(u8p))
+    return out
+
+
 def stereo_matching(L, R, disp_type, algorithm, win=15, min_d=0, num_d=64):
     L, pl = _u8(L)
     R, pr = _u8(R)

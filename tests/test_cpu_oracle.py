@@ -202,3 +202,13 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "from oracle" not in txt and "import oracle" not in txt and "liborc" not in txt, f
+
+
+def test_driver_post_processing_matches_cv2():
+    """aswStereoMatch.cpp:97-98 (convertTo(CV_8UC1) + normalize(0, 255, NORM_MINMAX)) against the real OpenCV"""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(3)
+    for lo, hi in ((0, 63), (3, 200), (17, 17), (0, 255), (40, 41)):
+        d = rng.integers(lo, hi + 1, (45, 61)).astype(np.float32)
+        want = cv2.normalize(d.astype(np.uint8), None, 0, 255, cv2.NORM_MINMAX)
+        assert np.array_equal(orc.disparity_to_u8(d), want), (lo, hi)

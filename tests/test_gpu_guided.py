@@ -168,3 +168,11 @@ def test_batch_resident_matches_single(ctx):
         assert np.array_equal(b.download(i), ctx.guidedf2_lr_refine(L, R, 1e-4, 9, 0, 16))
     ctx.sync()
     b.close()
+
+
+def test_driver_post_processing(ctx):
+    """the driver's 8-bit output map (aswStereoMatch.cpp:97-98) on the device, bit-exact"""
+    rng = np.random.default_rng(4)
+    for lo, hi in ((0, 63), (3, 200), (17, 17), (0, 255)):
+        d = rng.integers(lo, hi + 1, (77, 131)).astype(np.float32)
+        assert np.array_equal(ctx.disparity_to_u8(d), orc.disparity_to_u8(d))
