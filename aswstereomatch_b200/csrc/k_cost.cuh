@@ -130,12 +130,21 @@ k_sad_box_u8(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, i
     const int hr = cx / nquad, hq = cx - hr * nquad;
     float* plane = vol + (size_t)di * H * W;
     int buf = 0;
+    // the RB entering and RB leaving differences of a batch are requested one batch ahead: their latency hides behind the
+    // horizontal phase instead of stalling the running sum
+    int ain[RB], aout[RB];
+#pragma unroll
+    for (int r = 0; r < RB; r++) { ain[r] = ad(y_begin + r + h); aout[r] = ad(y_begin + r - h); }
     for (int y = y_begin; y < y_end; y += RB) {
 #pragma unroll
         for (int r = 0; r < RB; r++) {
-            s += ad(y + r + h);
+            s += ain[r];
             vs[buf][r][cx] = s;
-            s -= ad(y + r - h);
+            s -= aout[r];
+        }
+        if (y + RB < y_end) {
+#pragma unroll
+            for (int r = 0; r < RB; r++) { ain[r] = ad(y + RB + r + h); aout[r] = ad(y + RB + r - h); }
         }
         __syncthreads();
         if (quads) {
