@@ -61,6 +61,11 @@ def test_config3a_grid_full_dimensions(ctx):
     assert np.array_equal(np.isnan(e), np.isnan(e_ref)) and np.array_equal(np.isfinite(e), fin)
     assert np.array_equal(e[fin], e_ref[fin])
     assert np.array_equal(d, d_ref)
+    # the far end of the candidate range (d = 113 .. 128: wide max(0, x - d) clamp region), 16 candidates
+    d, e = ctx.computeAdaptiveWeight_bilateralGrid(L, R, 0, 10, 10, 113, 15, agg=True, strict=True)
+    d_ref, e_ref = orc.asw_bilateral_grid(L, R, 0, 10, 10, 113, 15, agg=True)
+    fin = np.isfinite(e_ref)
+    assert np.array_equal(np.isfinite(e), fin) and np.array_equal(e[fin], e_ref[fin]) and np.array_equal(d, d_ref)
     full = ctx.computeAdaptiveWeight_bilateralGrid(L, R, 0, 10, 10, 0, 128, strict=True)
     assert full.shape == (720, 1280) and full.min() >= 0 and full.max() <= 128
     assert np.array_equal(full, ctx.stereoMatching(L, R, 0, asw.ADAPTIVE_WEIGHT_BILATERAL_GRID, 15, 0, 128, strict=True))   # dispatcher literals: sS = sR = 10
@@ -88,12 +93,13 @@ def test_config4_geodesic_full_size_band(ctx):
     H, W, D, win = 720, 1280, 128, 35
     L, R, gt = make_pair(H, W, D, 5)
     d, e = ctx.computeAdaptiveWeight_geodesic(L, R, 0, win, 0, D, agg=True, strict=True)
-    y0, y1 = 400, 402
-    lo, hi = y0 - 18, y1 + 18
-    d_ref, e_ref = orc.asw_geodesic(L[lo:hi], R[lo:hi], 0, win, 0, D, agg=True)
-    rows = slice(y0 - lo, y1 - lo)
-    assert slice_err(e[:, y0:y1], e_ref[:, rows]) <= REL_TOL
-    assert (d[y0:y1] == d_ref[rows]).mean() >= AGREE
+    # a middle band and the image's top and bottom rows (BORDER_REFLECT of the DP source, clamped aggregation samples)
+    for y0, y1 in ((400, 402), (0, 2), (H - 2, H)):
+        lo, hi = max(0, y0 - 18), min(H, y1 + 18)
+        d_ref, e_ref = orc.asw_geodesic(L[lo:hi], R[lo:hi], 0, win, 0, D, agg=True)
+        rows = slice(y0 - lo, y1 - lo)
+        assert slice_err(e[:, y0:y1], e_ref[:, rows]) <= REL_TOL
+        assert (d[y0:y1] == d_ref[rows]).mean() >= AGREE
     # the candidate remainder (d = 128) is summed by another kernel in the unsplit run than in rank 1's: equal costs up to
     # rounding, so a pixel whose two best candidates are within 1e-6 of each other may flip
     assert split_agreement(ctx, L, R, asw.ADAPTIVE_WEIGHT_GEODESIC, win, D, d) >= 0.9999

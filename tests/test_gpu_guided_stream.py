@@ -60,6 +60,13 @@ def test_stream_small_eps_large_range(ctx):
     check_left(ctx, 90, 130, 12, 9, 1e-6, 31)
 
 
+def test_stream_small_eps_half_hd(ctx):
+    """eps = 1e-6 at 960 x 540 x 24: the fp32 window sums of the streaming kernel against the oracle's double accumulation
+    where a = cov / (var + eps) amplifies most, on a frame large enough for every band / strip variant"""
+    orc.set_num_threads(os.cpu_count() or 1)
+    check_left(ctx, 540, 960, 24, 9, 1e-6, 33)
+
+
 def test_stream_right_view_and_refine(ctx):
     L, R, _ = make_pair(77, 131, 14, 41)
     out, parts = ctx.guidedf2_lr_refine(L, R, 1e-4, 9, 0, 14, parts=True)
