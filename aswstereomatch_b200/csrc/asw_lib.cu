@@ -554,7 +554,7 @@ static asw_status dev_guidedf(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR
     unsigned long long* keys;
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
     ASW_TRY(init_keys(ctx, keys, n));
-    LAUNCH(ctx, "wta_keys", (k_wta_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(q, num_d, n, min_d, keys)));
+    LAUNCH(ctx, "wta_keys", (k_wta_keys<<<(unsigned)((n / 4 + 256) / 256), 256, 0, ctx->stream>>>(q, num_d, n, min_d, keys)));
     return keys_to_disp(ctx, keys, n, disp_dev);
 }
 
@@ -638,7 +638,7 @@ static asw_status dev_guidedf3(asw_ctx* ctx, const uint8_t* dL, const uint8_t* d
     unsigned long long* keys;
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
     ASW_TRY(init_keys(ctx, keys, n));
-    LAUNCH(ctx, "wta_keys", (k_wta_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(q, num_d, n, min_d, keys)));
+    LAUNCH(ctx, "wta_keys", (k_wta_keys<<<(unsigned)((n / 4 + 256) / 256), 256, 0, ctx->stream>>>(q, num_d, n, min_d, keys)));
     return keys_to_disp(ctx, keys, n, disp_dev);
 }
 

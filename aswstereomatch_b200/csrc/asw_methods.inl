@@ -65,7 +65,7 @@ extern "C" asw_status asw_wta(asw_ctx* ctx, const float* host_volume, int D, int
     ASW_TRY(ws_get(ctx, WS_OUT, n, &dd));
     ASW_CUDA(ctx, cudaMemcpyAsync(vol, host_volume, n * D * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     ASW_TRY(init_keys(ctx, keys, n));
-    LAUNCH(ctx, "wta_keys", (k_wta_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(vol, D, n, min_d, keys)));
+    LAUNCH(ctx, "wta_keys", (k_wta_keys<<<(unsigned)((n / 4 + 256) / 256), 256, 0, ctx->stream>>>(vol, D, n, min_d, keys)));
     ASW_TRY(keys_to_disp(ctx, keys, n, dd));
     ASW_TRY(download_f32(ctx, dd, disp));
     ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

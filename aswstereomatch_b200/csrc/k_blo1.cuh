@@ -626,7 +626,7 @@ static asw_status launch_blo1_stream(asw_ctx* ctx, const uint8_t* gref, const ui
     const int br = rows_for(cnt, 8 * ctx->sm_count);
     LAUNCH(ctx, "blo1_aggregate", (k_blo1_stream<WIN, false, NR, NBUF><<<dim3(strips, cdiv(g.H, br), cnt), BLS_COLS, smem, ctx->stream>>>(
                                       gref, gtgt, cost, Nk, nullptr, g, br, slice0, vol)));
-    LAUNCH(ctx, "wta_keys", (k_wta_keys<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(
+    LAUNCH(ctx, "wta_keys", (k_wta_keys<<<(unsigned)((n / 4 + 256) / 256), 256, 0, ctx->stream>>>(
                                 vol + (size_t)(g.di_lo - slice0) * n, cnt, n, min_d + g.di_lo, keys)));
     return ASW_OK;
 }

@@ -178,23 +178,40 @@ k_sad_box_u8(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, i
     }
 }
 
-// WTA over a materialised volume -> 64-bit keys (strict <, ascending d, NaN/inf never win).  The D loads of a thread are
-// independent: 8 slices in flight per thread, streaming (evict-first) loads.
+// WTA over a materialised volume -> 64-bit keys (strict <, ascending d, NaN/inf never win).  One thread = 4 adjacent pixels
+// (16-byte loads where the slice pitch allows); the D loads of a thread are independent: 8 slices = 128 bytes in flight per
+// thread, streaming (evict-first) loads.
 __global__ void __launch_bounds__(256)
 k_wta_keys(const float* __restrict__ vol, int D, size_t n, int d_first, unsigned long long* __restrict__ keys) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;
-    float best = __int_as_float(0x7f800000);             // a cost of +inf (or NaN) never wins: the key stays empty
-    int bd = -1;
-    const float* p = vol + i;
+    const float INF = __int_as_float(0x7f800000);          // a cost of +inf (or NaN) never wins: the key stays empty
+    float best[4] = {INF, INF, INF, INF};
+    int bd[4] = {-1, -1, -1, -1};
+    const bool vec = (n & 3) == 0;                           // every slice starts 16-byte aligned
+    const int cnt = (int)min((size_t)4, n - i);
     for (int d0 = 0; d0 < D; d0 += 8) {
-        float v[8];
+        float4 v[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) if (d0 + u < D) v[u] = __ldcs(p + (size_t)(d0 + u) * n);
+        for (int u = 0; u < 8; u++) {
+            if (d0 + u < D) {
+                const float* p = vol + (size_t)(d0 + u) * n + i;
+                if (vec) v[u] = __ldcs((const float4*)p);
+                else { v[u].x = p[0]; v[u].y = cnt > 1 ? p[1] : INF; v[u].z = cnt > 2 ? p[2] : INF; v[u].w = cnt > 3 ? p[3] : INF; }
+            }
+        }
 #pragma unroll
-        for (int u = 0; u < 8; u++) if (d0 + u < D && v[u] < best) { best = v[u]; bd = d0 + u; }
+        for (int u = 0; u < 8; u++) {
+            if (d0 + u < D) {
+                const float q[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) if (q[k] < best[k]) { best[k] = q[k]; bd[k] = d0 + u; }
+            }
+        }
     }
-    if (bd >= 0) keys[i] = min(keys[i], wta_key(best, d_first + bd));
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        if (k < cnt && bd[k] >= 0) keys[i + k] = min(keys[i + k], wta_key(best[k], d_first + bd[k]));
 }
 __global__ void k_fill_u64(unsigned long long* __restrict__ p, size_t n, unsigned long long v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
