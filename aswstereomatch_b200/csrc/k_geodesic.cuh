@@ -411,7 +411,20 @@ static asw_status geo_tile_segments(asw_ctx* ctx, const float* dref, const float
 // replicas.  Staging is asynchronous: the next 12-tap chunk of distance rows (and the next window row's colours)
 // are copied global -> shared with cp.async (4-byte, clamped columns) while the current chunk is evaluated.
 // ------------------------------------------------------------------------------------------------
-#define GD_DRW 160           // staged target-distance row: 4*31 + 28 + 8 cells
+#ifndef GEO_FULL_KC
+// full candidate chunks: 8 candidates per thread x 8 warps = 64 candidates per CTA, 2 CTAs per SM (128 registers).
+// Measured at config 4 (1280 x 720, 129 candidates, 35 x 35): 4 x 8 warps (round 1) 32.0 ms; 8 x 4 warps 29.9 (3 CTAs) /
+// 27.6 (4 CTAs); 8 x 8 warps 25.9; 8 x 16 warps 25.6 ms
+#define GEO_FULL_KC 8
+#define GEO_FULL_NW 8
+#define GEO_FULL_MINB 2      // resident CTAs the register budget is cut for
+#endif
+#ifndef GEO_SAD_I2F
+#define GEO_SAD_I2F 1
+#endif
+#define GEO_FULL_CAND (GEO_FULL_KC * GEO_FULL_NW)
+// staged target-distance row: 4*31 + KC (NW - 1) + KC + 4 cells
+#define GD_DRW (GEO_FULL_CAND > 32 ? 4 * 31 + GEO_FULL_CAND + 4 + 0 : 160)
 __device__ __forceinline__ void gd_cp_async4(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
 }
@@ -430,15 +443,33 @@ __device__ __forceinline__ float2 gd_sad4_acc_pair(uint32_t a0, uint32_t b0, uin
     f.x = __uint_as_float((uint32_t)r); f.y = __uint_as_float((uint32_t)(r >> 32));
     return f;
 }
+// 16-byte shared-memory loads the compiler cannot split: with 8 candidates per thread not every element of the last quad is
+// used, and ptxas otherwise narrows that load to LDS.64 + LDS whose 16-byte lane stride is a 2- / 4-way bank conflict
+__device__ __forceinline__ float4 gd_lds128(const float* p) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
+__device__ __forceinline__ uint4 gd_lds128(const uint32_t* p) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
+}
 __device__ __forceinline__ void gd_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void gd_cp_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // BORDER: the segment touches the image edge where the window's sample column is clamped BEFORE the disparity
 // shift (right edge for LEFT, left edge for RIGHT).  Those taps read the target colour at the shifted EDGE column,
 // which depends on the candidate only: 4 values per thread and window row, selected per evaluation.
-// NW warps per CTA = 4 NW candidates per CTA (8 for full chunks of 32; fewer for the candidate remainder).
-template <int SIGN, bool BORDER, int NW>
-__global__ void __launch_bounds__(32 * NW, NW == 8 ? 2 : 1)
+// A thread owns 4 adjacent pixels x KC ADJACENT candidates; NW warps per CTA = KC NW candidates per CTA.  Full chunks of 32
+// candidates run KC = 8, NW = 4: the 11 distinct target operands of the 32 evaluations are one aligned 12-wide window
+// (3 LDS.128 for distances, 3 for colours) -- 8 LDS.128 per tap and 32 evaluations, against 12 for two 4 x 4 threads.  The
+// kernel is bound by the shared-memory pipe, so that ratio is its speed.  The candidate remainder runs KC = 4 with as many
+// warps as it needs.
+template <int SIGN, bool BORDER, int NW, int KC>
+__global__ void __launch_bounds__(32 * NW, KC == 8 ? GEO_FULL_MINB : (NW == 8 ? 2 : 1))
 k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, const uint32_t* __restrict__ pref,
                const uint32_t* __restrict__ ptgt, GeoGeom g, int seg_first, int cand_first,
                unsigned long long* __restrict__ keys, float* __restrict__ agg) {
@@ -453,25 +484,26 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
     uint32_t* CR = CL + 2 * 4 * CLW;                          // [2][4][CRW]
     const int tid = threadIdx.x, pg = tid & 31, ds = tid >> 5;
     const int y = blockIdx.y, xb = (seg_first + blockIdx.x) * GT_X;
-    const int c0 = cand_first + blockIdx.z * 32;
+    const int c0 = cand_first + blockIdx.z * (KC * NW);
     const int d_lo = g.d_first + c0;
     const size_t n = (size_t)H * W;
     const size_t rowoff = (size_t)y * W;
-    // staged cell 0 <-> image column (before clamping).  LEFT: a thread's 8-wide window starts at
-    // x - (d_lo + 4 ds) - 4 = oDR + (4 pg - 4 ds + 28); RIGHT: at x + d_lo + 4 ds = oDR + (4 pg + 4 ds)
-    const int oDR = SIGN > 0 ? xb - d_lo - 32 : xb + d_lo;
+    // staged cell 0 <-> image column (before clamping).  LEFT: a thread's (KC + 4)-wide window starts at
+    // x - (d_lo + KC ds) - KC = oDR + (4 pg - KC ds + KC (NW - 1)); RIGHT: at x + d_lo + KC ds = oDR + (4 pg + KC ds)
+    static_assert(KC % 4 == 0 && 4 * 31 + KC * (NW - 1) + KC + 4 <= GD_DRW, "staged target row too narrow");
+    const int oDR = SIGN > 0 ? xb - d_lo - KC * NW : xb + d_lo;
     const int oCL = xb - h;
     const int oCR = oDR - h;
-    const int e0 = SIGN > 0 ? 4 * pg - 4 * ds + 28 : 4 * pg + 4 * ds;   // window start (cells), multiple of 4
-    // accumulators: the 16 (pixel, candidate) pairs of a thread are evaluated as 6 packed pairs that share a target
-    // operand -- (p, k) and (p+1, k+SIGN), p even, sit on the same diagonal -- plus 4 singles, so that the FMA-pipe
+    const int e0 = SIGN > 0 ? 4 * pg - KC * ds + KC * (NW - 1) : 4 * pg + KC * ds;   // window start (cells), multiple of 4
+    // accumulators: the 4 KC (pixel, candidate) pairs of a thread are evaluated as 2 (KC - 1) packed pairs that share a
+    // target operand -- (p, k) and (p+1, k+SIGN), p even, sit on the same diagonal -- plus 4 singles, so that the FMA-pipe
     // work of two evaluations issues as one FMUL2 / FADD2 / FFMA2
-    float2 fnp[2][3], fdp[2][3];
+    float2 fnp[2][KC - 1], fdp[2][KC - 1];
     float fns[2][2], fds[2][2];
 #pragma unroll
     for (int a = 0; a < 2; a++) {
 #pragma unroll
-        for (int q = 0; q < 3; q++) { fnp[a][q] = make_float2(0.f, 0.f); fdp[a][q] = make_float2(0.f, 0.f); }
+        for (int q = 0; q < KC - 1; q++) { fnp[a][q] = make_float2(0.f, 0.f); fdp[a][q] = make_float2(0.f, 0.f); }
         fns[a][0] = fns[a][1] = fds[a][0] = fds[a][1] = 0.0f;
     }
 
@@ -527,12 +559,12 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
         const float* dr = DRs + (c & 1) * GT_TC * GD_DRW + e0;
         const uint32_t* cl = CL + (j & 1) * 4 * CLW + 4 * pg;
         const uint32_t* cr = CR + (j & 1) * 4 * CRW + e0;
-        uint32_t edge[4];
+        uint32_t edge[KC];
         if (BORDER) {
             const int ny = clampi(y - h + j, 0, H - 1);
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int d = d_lo + 4 * ds + k;
+            for (int k = 0; k < KC; k++) {
+                const int d = d_lo + KC * ds + k;
                 edge[k] = __ldg(ptgt + (size_t)ny * W + (SIGN > 0 ? max(0, W - 1 - d) : min(d, W - 1)));
             }
         }
@@ -547,14 +579,19 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
             if (tt < i1 - i0) {
                 const int i = i0 + tt, r = tt & 3;
                 const float4 dl4 = *(const float4*)(dl + tt * GT_X);
-                const float4 dra = *(const float4*)(dr + tt * GD_DRW), drb = *(const float4*)(dr + tt * GD_DRW + 4);
                 // colour cell of pixel quad start: oCL + (4 pg + i) -> copy r at aligned index 4 pg + i - r
                 const uint4 cl4 = *(const uint4*)(clb[r] + tt);
-                const uint4 cra = *(const uint4*)(crb4[r] + tt), crb = *(const uint4*)(crb4[r] + tt + 4);
                 const float dlv[4] = {dl4.x, dl4.y, dl4.z, dl4.w};
-                const float drv[8] = {dra.x, dra.y, dra.z, dra.w, drb.x, drb.y, drb.z, drb.w};
                 const uint32_t clv[4] = {cl4.x, cl4.y, cl4.z, cl4.w};
-                const uint32_t crv[8] = {cra.x, cra.y, cra.z, cra.w, crb.x, crb.y, crb.z, crb.w};
+                float drv[KC + 4];
+                uint32_t crv[KC + 4];
+#pragma unroll
+                for (int m = 0; m < (KC + 4) / 4; m++) {
+                    const float4 d4 = gd_lds128(dr + tt * GD_DRW + 4 * m);
+                    const uint4 c4 = gd_lds128(crb4[r] + tt + 4 * m);
+                    drv[4 * m] = d4.x; drv[4 * m + 1] = d4.y; drv[4 * m + 2] = d4.z; drv[4 * m + 3] = d4.w;
+                    crv[4 * m] = c4.x; crv[4 * m + 1] = c4.y; crv[4 * m + 2] = c4.z; crv[4 * m + 3] = c4.w;
+                }
                 bool clamped[4];
 #pragma unroll
                 for (int p = 0; p < 4; p++) {
@@ -573,19 +610,24 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
                     const int pe = 2 * a;
                     const float2 dl2 = make_float2(dlv[pe], dlv[pe + 1]);
 #pragma unroll
-                    for (int q = 0; q < 3; q++) {
+                    for (int q = 0; q < KC - 1; q++) {
                         const int k = SIGN > 0 ? q : q + 1;                   // (pe, k) and (pe+1, k+SIGN): same window cell
-                        const int w = SIGN > 0 ? pe - k + 4 : pe + k;
+                        const int w = SIGN > 0 ? pe - k + KC : pe + k;
                         const float2 t2 = __fmul2_rn(dl2, make_float2(drv[w], drv[w]));          // A.cpp:1488-1489
                         const uint32_t cr0 = BORDER ? (clamped[pe] ? edge[k] : crv[w]) : crv[w];
                         const uint32_t cr1 = BORDER ? (clamped[pe + 1] ? edge[k + SIGN] : crv[w]) : crv[w];
+#if GEO_SAD_I2F
+                        // byte SADs converted on the ALU side (I2FP): the FMA pipe is the loaded one in this kernel
+                        const float2 cd2 = make_float2((float)gd_sad4_acc(clv[pe], cr0, 0u), (float)gd_sad4_acc(clv[pe + 1], cr1, 0u));
+#else
                         const float2 cd2 = __fadd2_rn(gd_sad4_acc_pair(clv[pe], cr0, clv[pe + 1], cr1, 0x4B000000u), m23);
+#endif
                         fnp[a][q] = __ffma2_rn(t2, cd2, fnp[a][q]);
                         fdp[a][q] = __fadd2_rn(fdp[a][q], t2);
                     }
                     // singles: (pe, ks0) and (pe+1, ks1) have no partner on their diagonal
-                    const int ks0 = SIGN > 0 ? 3 : 0, ks1 = SIGN > 0 ? 0 : 3;
-                    const int w0 = SIGN > 0 ? pe - ks0 + 4 : pe + ks0, w1 = SIGN > 0 ? pe + 1 - ks1 + 4 : pe + 1 + ks1;
+                    const int ks0 = SIGN > 0 ? KC - 1 : 0, ks1 = SIGN > 0 ? 0 : KC - 1;
+                    const int w0 = SIGN > 0 ? pe - ks0 + KC : pe + ks0, w1 = SIGN > 0 ? pe + 1 - ks1 + KC : pe + 1 + ks1;
                     const float t0 = __fmul_rn(dlv[pe], drv[w0]), t1 = __fmul_rn(dlv[pe + 1], drv[w1]);
                     fns[a][0] = fmaf(t0, sadbits(pe, ks0, w0) - 8388608.0f, fns[a][0]);
                     fds[a][0] = __fadd_rn(fds[a][0], t0);
@@ -602,14 +644,14 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
         if (x >= W) continue;
         unsigned long long best = WTA_KEY_EMPTY;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int c = c0 + 4 * ds + k;
+        for (int k = 0; k < KC; k++) {
+            const int c = c0 + KC * ds + k;
             if (c >= g.n_cand) continue;
             // (p, k) lives in: pair slot q of half a = p/2 (x for even p with k = q (LEFT) / q+1 (RIGHT), y for odd p
             // with the partner's k), or one of the two singles of that half
             const int a = p >> 1, odd = p & 1;
-            const int kq = SIGN > 0 ? (odd ? k - 1 : k) : (odd ? k : k - 1);          // pair slot if in 0..2
-            const bool single = odd ? (k == (SIGN > 0 ? 0 : 3)) : (k == (SIGN > 0 ? 3 : 0));
+            const int kq = SIGN > 0 ? (odd ? k - 1 : k) : (odd ? k : k - 1);          // pair slot if in 0..KC-2
+            const bool single = odd ? (k == (SIGN > 0 ? 0 : KC - 1)) : (k == (SIGN > 0 ? KC - 1 : 0));
             float vn, vd;
             if (single) { vn = fns[a][odd]; vd = fds[a][odd]; }
             else { vn = odd ? fnp[a][kq].y : fnp[a][kq].x; vd = odd ? fdp[a][kq].y : fdp[a][kq].x; }
@@ -621,7 +663,7 @@ k_geo_agg_diag(const float* __restrict__ dref, const float* __restrict__ dtgt, c
     }
 }
 
-template <int SIGN, bool BORDER, int NW>
+template <int SIGN, bool BORDER, int NW, int KC>
 static asw_status geo_diag_launch(asw_ctx* ctx, const float* dref, const float* dtgt, const uint32_t* cref, const uint32_t* ctgt,
                                   GeoGeom g, int seg_first, int seg_count, int cand_first, int n_chunks,
                                   unsigned long long* keys, float* agg) {
@@ -629,22 +671,26 @@ static asw_status geo_diag_launch(asw_ctx* ctx, const float* dref, const float* 
     const int h = g.h;
     const int CLW = (GT_X + 2 * h + 7) & ~3, CRW = (GD_DRW + 2 * h + 7) & ~3;
     size_t smem = (2 * (size_t)GT_TC * GT_X + 2 * (size_t)GT_TC * GD_DRW + 8 * (size_t)(CLW + CRW)) * sizeof(float);
-    cudaFuncSetAttribute(k_geo_agg_diag<SIGN, BORDER, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_geo_agg_diag<SIGN, BORDER, NW, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     LAUNCH(ctx, BORDER ? "geo_aggregate_border" : "geo_aggregate",
-           (k_geo_agg_diag<SIGN, BORDER, NW><<<dim3(seg_count, g.H, n_chunks), 32 * NW, smem, ctx->stream>>>(
+           (k_geo_agg_diag<SIGN, BORDER, NW, KC><<<dim3(seg_count, g.H, n_chunks), 32 * NW, smem, ctx->stream>>>(
                                      dref, dtgt, cref, ctgt, g, seg_first, cand_first, keys, agg)));
     return ASW_OK;
 }
-// a range of segments: full chunks of 32 candidates with 8 warps per CTA, the candidate remainder with as many warps
-// as it needs (4 candidates per warp)
+// a range of segments: full chunks of 32 candidates with 4 warps x 8 candidates per thread, the candidate remainder with
+// as many warps as it needs at 4 candidates per thread
 template <int SIGN, bool BORDER>
 static asw_status geo_segments_signed(asw_ctx* ctx, const float* dref, const float* dtgt, const uint32_t* cref,
                                       const uint32_t* ctgt, GeoGeom g, int seg_first, int seg_count,
                                       unsigned long long* keys, float* agg) {
-    const int full = g.n_cand / 32, rem = g.n_cand - full * 32;
-    ASW_TRY((geo_diag_launch<SIGN, BORDER, 8>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, 0, full, keys, agg)));
-    const int nw = (rem + 3) / 4, c1 = full * 32;
-#define GEO_REM(NWV) ASW_TRY((geo_diag_launch<SIGN, BORDER, NWV>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, c1, 1, keys, agg)))
+    const int full = g.n_cand / GEO_FULL_CAND, rem = g.n_cand - full * GEO_FULL_CAND;
+    ASW_TRY((geo_diag_launch<SIGN, BORDER, GEO_FULL_NW, GEO_FULL_KC>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, 0, full, keys, agg)));
+    int nw = (rem + 3) / 4, c1 = full * GEO_FULL_CAND;
+    if (nw > 8) {   // more than 32 left (64-candidate chunks): one 32-candidate launch first
+        ASW_TRY((geo_diag_launch<SIGN, BORDER, 8, 4>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, c1, 1, keys, agg)));
+        c1 += 32; nw -= 8;
+    }
+#define GEO_REM(NWV) ASW_TRY((geo_diag_launch<SIGN, BORDER, NWV, 4>(ctx, dref, dtgt, cref, ctgt, g, seg_first, seg_count, c1, 1, keys, agg)))
     switch (nw) {
         case 1: GEO_REM(1); break;
         case 2: GEO_REM(2); break;
