@@ -44,11 +44,12 @@ __device__ __forceinline__ float4 p4add(float4 a, float4 b) {
     float2 hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
     return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
-// s - old + nw
+// s + (nw - old): the difference does not depend on the running sum, so a sliding run is a chain of ONE packed add per
+// output (the compiler may not reassociate floats itself)
 __device__ __forceinline__ float4 p4slide(float4 s, float4 old, float4 nw) {
     const float2 m1 = make_float2(-1.0f, -1.0f);
-    float2 lo = __fadd2_rn(__ffma2_rn(make_float2(old.x, old.y), m1, make_float2(s.x, s.y)), make_float2(nw.x, nw.y));
-    float2 hi = __fadd2_rn(__ffma2_rn(make_float2(old.z, old.w), m1, make_float2(s.z, s.w)), make_float2(nw.z, nw.w));
+    float2 lo = __fadd2_rn(make_float2(s.x, s.y), __ffma2_rn(make_float2(old.x, old.y), m1, make_float2(nw.x, nw.y)));
+    float2 hi = __fadd2_rn(make_float2(s.z, s.w), __ffma2_rn(make_float2(old.z, old.w), m1, make_float2(nw.z, nw.w)));
     return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
 

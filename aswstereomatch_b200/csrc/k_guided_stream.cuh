@@ -127,16 +127,29 @@ __device__ __forceinline__ float gfs_cost(const FeatF& a, const FeatF& nb, const
     return fmaf(p.reg_r, (float)cci, p.reg * fmaxf(G - p.thr_g, 0.0f));
 }
 
+// sum of K values as a balanced tree (depth ceil(log2 K) instead of a chain of K-1 dependent adds)
+template <int K>
+__device__ __forceinline__ float4 gfs_pair_sum(const float4* w) {
+    float4 t[(K + 1) / 2];
+#pragma unroll
+    for (int i = 0; i < K / 2; i++) t[i] = p4add(w[2 * i], w[2 * i + 1]);
+    if (K & 1) t[K / 2] = w[K - 1];
+#pragma unroll
+    for (int n = (K + 1) / 2; n > 1; n = (n + 1) / 2) {
+#pragma unroll
+        for (int i = 0; i < n / 2; i++) t[i] = p4add(t[2 * i], t[2 * i + 1]);
+        if (n & 1) t[n / 2] = t[n - 1];
+    }
+    return t[0];
+}
+
 // ring step: insert `nw` at slot j (a constant after unrolling) of a K-entry register ring and return the sum of the
 // ring.  Slot 0 restarts the sum from the ring (K-1 adds), the others slide (s - old + new).
 template <int K>
 __device__ __forceinline__ float4 gfs_ring_step(float4 (&r)[K], float4& s, float4 nw, int j) {
     if (j == 0) {
         r[0] = nw;
-        float4 t = p4add(r[0], r[1]);
-#pragma unroll
-        for (int i = 2; i < K; i++) t = p4add(t, r[i]);
-        s = t;
+        s = gfs_pair_sum<K>(r);
     } else {
         s = p4slide(s, r[j], nw);
         r[j] = nw;
@@ -196,12 +209,10 @@ __device__ __forceinline__ void gfs_bulk_g2s(void* dst, const void* src, uint32_
 // Horizontal sliding run of 8 window sums with the loads issued GFS_PF outputs ahead of their use (a filter warp
 // has one other warp per scheduler to hide behind, so the shared-memory latency must be covered inside the thread).
 #define GFS_PF 5
+#define GFS_CPF 2           // cost rows whose feature loads are in flight
 template <int K>
 __device__ __forceinline__ float4 gfs_tree_sum(const float4* w) {
-    float4 t = p4add(w[0], w[1]);
-#pragma unroll
-    for (int i = 2; i < K; i++) t = p4add(t, w[i]);
-    return t;
+    return gfs_pair_sum<K>(w);
 }
 // level 1: window sums of (I c, c) -> (a, b) of A.cpp:2805-2847, a pre-scaled by 1/K^2
 template <int K>
@@ -375,10 +386,16 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
             float4* vs = VS1 + (u & 1) * ROWS * P1 + sl1 * P1 + c1;   // shared-memory row = j * NS + slice
             gfs_mbar_wait(&mbar[u & 1], (u >> 1) & 1);
             if (u >= 2) gfs_bar_sync(GFS_BAR_EMPTY + (u & 1), 2 * GFS_THREADS);   // the filter warps are done with block u-2
+            // the staged rows and VS1 live in the same shared array: the loads are issued GFS_CPF rows ahead by hand
+            // (the compiler will not move a shared load above the previous row's store)
+            FeatF fa_q[GFS_CPF], fb_q[GFS_CPF];
+#pragma unroll
+            for (int j = 0; j < GFS_CPF; j++) { fa_q[j] = rs[j * GFS_IW]; fb_q[j] = ts[j * GFS_TP]; }
 #pragma unroll
             for (int j = 0; j < K; j++) {
-                const FeatF fa = rs[j * GFS_IW];
-                const FeatF fb = ts[j * GFS_TP];
+                const FeatF fa = fa_q[j % GFS_CPF];
+                const FeatF fb = fb_q[j % GFS_CPF];
+                if (j + GFS_CPF < K) { fa_q[j % GFS_CPF] = rs[(j + GFS_CPF) * GFS_IW]; fb_q[j % GFS_CPF] = ts[(j + GFS_CPF) * GFS_TP]; }
                 const float cp = gfs_cost(fa, fb, tp);
                 cmin = fminf(cmin, cp); cmax = fmaxf(cmax, cp);
                 const float cs = cp * inv;
@@ -473,8 +490,11 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
 #pragma unroll
                     for (int i = 0; i <= A; i++) dst[(A + i) * GFS_NS * P2] = gfs_reflect_sum<K>(r2, i, true);
                 } else {
+                    float4 in[K];                       // AB and VS2 alias for the compiler: all loads first
 #pragma unroll
-                    for (int j = 0; j < K; j++) dst[j * GFS_NS * P2] = gfs_ring_step<K>(r2, s2, src[j * GFS_NS * P2], j);
+                    for (int j = 0; j < K; j++) in[j] = src[j * GFS_NS * P2];
+#pragma unroll
+                    for (int j = 0; j < K; j++) dst[j * GFS_NS * P2] = gfs_ring_step<K>(r2, s2, in[j], j);
                 }
             }
             if (!LOADER_FREE || !loader) gfs_bar_sync(GFS_BAR_FILTER2, LOADER_FREE ? GFS_THREADS - 32 : GFS_THREADS);

@@ -351,7 +351,9 @@ def bench_split(ctx, asw, dist, torch, rank, world, local_rank, args):
     download of the map), max over ranks; at N = 1 the same call unsplit."""
     from aswstereomatch_b200 import sharding
     from aswstereomatch_b200.synth import make_pair
-    L, R, _ = make_pair(H, W, D, 1000)
+    L0, R0, _ = make_pair(H, W, D, 1000)
+    L = asw.pinned_empty(L0.shape, np.uint8); R = asw.pinned_empty(R0.shape, np.uint8)     # pinned, like the e2e leg's buffers
+    L[...] = L0; R[...] = R0
     alg = asw.ADAPTIVE_WEIGHT_GUIDED_FILTER_2
     dev = torch.device("cuda", local_rank) if world > 1 else None
 
@@ -384,7 +386,7 @@ def bench_split(ctx, asw, dist, torch, rank, world, local_rank, args):
             ar.append(a)
         times.append(dt)
     res = {"what": f"one {W}x{H} pair, D={D}, GuidedF_2 (dispatcher, left view) disparity-split over {world} rank(s), "
-                   "host buffers in and out, max over ranks", "ms": float(np.median(times)),
+                   "pinned host images in, host map out, max over ranks", "ms": float(np.median(times)),
            "allreduce_ms": float(np.median(ar)) if ar else 0.0, "slices_per_rank": -(-D // world),
            "mde_s": H * W * D / 1e6 / (float(np.median(times)) * 1e-3)}
     if world > 1:
