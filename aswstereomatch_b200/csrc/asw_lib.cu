@@ -398,8 +398,11 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
         }
         return ASW_OK;
     }
-#ifdef ASW_DEV_KERNELS   // the tiled pair of k_guided_fast.cuh: superseded by the streaming kernel
-    if ((win == 5 || win == 7 || win == 9) && !asw_dev("ASW_GF_GENERIC")) {
+    // windows 11, 13, 15 (15 = the reference driver's own call, main.cpp:94): the tiled pair of k_guided_fast.cuh (fixed
+    // 32 x 64 input tile, (a,b) through HBM).  The streaming kernel's shared-memory layout does not fit them (241 KB at 15 with
+    // 2 slices per CTA).  Dev builds can route 5 / 7 / 9 here as well (superseded by the streaming kernel).
+    const bool tiled_big = win == 11 || win == 13 || win == 15;
+    if ((tiled_big || (asw_dev("ASW_GF_TILED") && (win == 5 || win == 7 || win == 9))) && !asw_dev("ASW_GF_GENERIC")) {
         // tuned kernels (k_guided_fast.cuh): fixed 32x64 input tile, register-resident reference-side data
         const int DC1 = 8;
         float4* grd;
@@ -420,13 +423,17 @@ static asw_status dev_guidedf2_keys(asw_ctx* ctx, const uint8_t* dL, const uint8
             int cn = (d_hi - c0 < chunk) ? d_hi - c0 : chunk;
             g.x0_base = v.x0_base + v.x0_step * c0;
             float* agg_c = agg_dev ? agg_dev + (size_t)(c0 - d_lo) * n : nullptr;
-            if (win == 9) ASW_TRY(gff_launch<9>(ctx, fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0, cn, min_d + c0, keys, agg_c));
+            if (win == 15) ASW_TRY(gff_launch<15>(ctx, fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0, cn, min_d + c0, keys, agg_c));
+            else if (win == 13) ASW_TRY(gff_launch<13>(ctx, fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0, cn, min_d + c0, keys, agg_c));
+            else if (win == 11) ASW_TRY(gff_launch<11>(ctx, fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0, cn, min_d + c0, keys, agg_c));
+#ifdef ASW_DEV_KERNELS
+            else if (win == 9) ASW_TRY(gff_launch<9>(ctx, fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0, cn, min_d + c0, keys, agg_c));
             else if (win == 7) ASW_TRY(gff_launch<7>(ctx, fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0, cn, min_d + c0, keys, agg_c));
-            else ASW_TRY(gff_launch<5>(ctx, fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0, cn, min_d + c0, keys, agg_c));
+            else if (win == 5) ASW_TRY(gff_launch<5>(ctx, fref, ftgt, gp.Gi, gp.Gm, grd, g, tp, ab, slice_mm + 2 * c0, cn, min_d + c0, keys, agg_c));
+#endif
         }
         return ASW_OK;
     }
-#endif
     const int DC = 4;
     int chunk = gf_chunk_slices(ctx, n);
     chunk = ((chunk + DC - 1) / DC) * DC;

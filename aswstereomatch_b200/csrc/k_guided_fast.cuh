@@ -31,7 +31,7 @@
 #define GFF_NW 8
 #define GFF_EPT 8              // input positions per thread (32*64 / 256)
 #define GFF_RUN 8              // outputs per sliding run
-#define GFF_MAXK 9
+#define GFF_MAXK 15
 
 struct GffGeom {
     int H, W, Wp, a;
@@ -264,7 +264,7 @@ k_gff_q(const float4* __restrict__ ab, const float4* __restrict__ Gi, GffGeom g,
         if (o < c_len) atomicMin(&keys[pix0 + o * g.W], best[o]);
 }
 
-#ifdef ASW_DEV_KERNELS   // host side of the tiled pair: the product build launches the streaming kernel instead
+// host side of the tiled pair (windows 11, 13, 15 in the product build; 5, 7, 9 take the streaming kernel)
 __global__ void k_reciprocal4(const float4* __restrict__ in, size_t n, float4* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -293,4 +293,3 @@ static asw_status gff_launch(asw_ctx* ctx, const Feat* fref, const Feat* ftgt, c
                             ab, Gi, g, tp.c0, slice_mm, d_label0, dc2, keys, agg)));
     return ASW_OK;
 }
-#endif

@@ -157,6 +157,38 @@ __device__ __forceinline__ float4 gfs_ring_step(float4 (&r)[K], float4& s, float
     return s;
 }
 
+// a - b on a float4 (two packed FMAs with a -1 multiplier)
+__device__ __forceinline__ float4 p4sub(float4 a, float4 b) {
+    const float2 m1 = make_float2(-1.0f, -1.0f);
+    float2 lo = __ffma2_rn(make_float2(b.x, b.y), m1, make_float2(a.x, a.y));
+    float2 hi = __ffma2_rn(make_float2(b.z, b.w), m1, make_float2(a.z, a.w));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+// Window sum over blocks of K elements without a ring of raw values (k_gfs_walk): P[j] holds the PREFIX sum of the
+// previous block's elements 0..j.  Element j of the current block enters: the window = elements j+1..K-1 of the previous
+// block (its total minus its prefix at j) + elements 0..j of this block (this block's prefix at j), and P[j] becomes this
+// block's prefix.  Against a ring (s += new - old; ring[j] = new): the value written back is COMPUTED, so it lands in the
+// slot's home register with no copy, the prefix sums restart every block (nothing accumulates, no periodic re-summation)
+// and the loop-carried chain is one packed add per element.  j is a constant after unrolling.
+template <int K>
+__device__ __forceinline__ float4 gfs_prefix_step(float4 (&P)[K], float4 nw, int j) {
+    if (j == K - 1) {                      // the previous block has fully left the window
+        P[K - 1] = p4add(P[K - 2], nw);
+        return P[K - 1];
+    }
+    const float4 tail = p4sub(P[K - 1], P[j]);
+    P[j] = (j == 0) ? nw : p4add(P[j - 1], nw);
+    return p4add(tail, P[j]);
+}
+// raw elements of the block whose prefix sums are in P
+template <int K>
+__device__ __forceinline__ void gfs_prefix_to_raw(const float4 (&P)[K], float4 (&r)[K]) {
+    r[0] = P[0];
+#pragma unroll
+    for (int j = 1; j < K; j++) r[j] = p4sub(P[j], P[j - 1]);
+}
+
 // REFLECT_101 window sum centred at ring index c over a ring that holds image rows base .. base+K-1, where rows
 // below `lo` (= ring index of image row 0, or -inf) and above `hi` (ring index of row H-1) are reflected.
 template <int K>
@@ -300,7 +332,7 @@ template <int K>
 __global__ void __launch_bounds__(2 * GFS_THREADS, 1)
 k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const float4* __restrict__ Gi,
              const GfsMoments* __restrict__ Gmom, const int* __restrict__ guide_mm, GfsGeom g,
-             TadStream tp, float c0, float* __restrict__ qv, uint32_t* __restrict__ slice_mm) {
+             TadStream tp, float c0, float* __restrict__ qv, uint32_t* __restrict__ slice_mm, int strip0) {
     using L = GfsLayout<K>;
     constexpr int A = L::A, AW = L::AW, QW = L::QW, P1 = L::P1, P2 = L::P2, PQ = L::PQ, ROWS = L::ROWS;
     constexpr int NRUN1 = (AW + GFF_RUN - 1) / GFF_RUN, NRUN2 = (QW + GFF_RUN - 1) / GFF_RUN;
@@ -314,7 +346,7 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
     uint64_t* mbar = (uint64_t*)(sm_gfs + L::oBar);            // [0..1] cost stages, [2..3] filter stages
 
     const int H = g.H, W = g.W;
-    const int x0 = blockIdx.x * QW;                            // first q' column of the strip
+    const int x0 = (blockIdx.x + strip0) * QW;                 // first q' column of the strip
     const int d0 = blockIdx.y * GFS_NS;
     // ---- band geometry ----
     const int nb = g.nbands, band = blockIdx.z;
@@ -518,6 +550,352 @@ k_gfs_filter(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const
     }
 }
 
+#ifdef ASW_DEV_KERNELS
+// ------------------------------------------------------------------------------------------------------------------
+// k_gfs_walk -- the same filter for INTERIOR strips (every (a,b) column of the strip inside the image), K = 9.
+// DEV ONLY (ASW_GFS_WALK=1 in a -DASW_DEV_KERNELS build): bit-compatible with the parity tests, measured SLOWER than the
+// classic kernel (5.57 + 0.33 ms against 5.38 ms per 1080p x 256 view): the walkers carry a third of the CTA's instructions
+// in 4 of its 18 warps at 18 of 32 lanes and issue at IPC 0.26 (ncu: profiles/r02_ncu_gfs.md).
+// The classic kernel moves every level through shared memory twice over: V1 -> [VS1] -> H1 (runs of 8: every value read
+// twice) -> [AB] -> V2 -> [VS2] -> H2 (read twice) -> q'.  ncu (profiles/r02_ncu_gfs.md): the H phases run at the speed of
+// the shared-memory pipe.  Here level 2 runs horizontal-first and ONE thread walks a whole strip row:
+//     cost warps (8)   A / V1 as before                          -> VS1   (16 B stored per evaluation)
+//     walker warps (2) lane = (row of the block, slice): for every column of the row, in registers: level-1 horizontal
+//                      window (prefix sums over blocks of K columns) -> (a,b) epilogue -> level-2 horizontal window
+//                                                                 -> HS    (VS1 read ONCE; no AB, no second H read)
+//     column warps (6) thread = (slice, q' column): level-2 vertical window (prefix sums over the K rows of a block)
+//                      -> q' = abar . I + bbar -> HBM, coalesced along the row
+// Shared-memory traffic per evaluation: 16 + 16 (VS1) + 28 (moments) + 16 + 16 (HS) + 16 (guidance) instead of
+// 16 + 32 + 28 + 16 + 16 + 16 + 32 + 16.  Level 2 borders: rows as in the classic kernel (closed forms on the column
+// prefix sums); columns never (interior strips).  Edge strips and K = 5, 7 run the classic kernel.
+// ------------------------------------------------------------------------------------------------------------------
+#define GFW_WALKERS 128       // 4 warps: (row half) x (half of the block's rows)
+#define GFW_COLS 192          // 6 warps: NS * QW for K = 9
+#define GFW_BAR_FULL 1        // +buf  VS1[buf] written: cost warps arrive, walkers sync
+#define GFW_BAR_EMPTY 3       // +buf  VS1[buf] consumed: walkers arrive, cost warps sync
+#define GFW_BAR_HSFULL 5      // +buf  HS[buf] written: walkers arrive, column warps sync
+#define GFW_BAR_COST 7        // among the cost warps
+#define GFW_BAR_HSEMPTY 8     // +buf  HS[buf] consumed: column warps arrive, walkers sync
+#define GFW_BAR_COLS 10       // among the column warps
+#define GFW_BAR_WALK 11       // among the walkers
+#define GFW_PF 2              // columns the walker's loads run ahead
+// 5 warpgroups: 2 cost, 1 walkers, 2 column (6 of its 8 warps have work).  640 threads start with 96 registers each; the
+// roles then re-divide the register file (setmaxnreg, per warpgroup): 256 x 88 + 128 x 128 + 256 x 88 = 640 x 96
+#define GFW_THREADS 640
+#define GFW_REG_COST 88
+#define GFW_REG_WALK 128
+#define GFW_REG_COLS 88
+#define GFW_STR2(x) #x
+#define GFW_STR(x) GFW_STR2(x)
+
+template <int K>
+struct GfwLayout {
+    static constexpr int A = K / 2;
+    static constexpr int AW = GFS_IW - (K - 1), QW = GFS_IW - 2 * (K - 1);
+    static constexpr int P1 = GFS_IW + 1, P2 = AW | 1, PQ = QW | 1;
+    static constexpr int ROWS = GFS_NS * K;
+    static constexpr int oVS1 = 0;                             // [2][ROWS][P1]
+    static constexpr int oHS = oVS1 + 2 * ROWS * P1;           // [2][ROWS][PQ]  level-2 horizontal sums
+    static constexpr int oRef = oHS + 2 * ROWS * PQ;           // staging as in GfsLayout
+    static constexpr int oTgt = oRef + 2 * K * GFS_IW;
+    static constexpr int oGM = oTgt + 2 * K * GFS_TP;
+    static constexpr int oIQ = oGM + 2 * K * P2 * 2;
+    static constexpr int oBar = oIQ + 2 * K * PQ;
+    static constexpr size_t bytes = (size_t)(oBar + 3) * sizeof(float4);   // 6 mbarriers
+};
+
+// NSTEPS columns t0 .. t0+NSTEPS-1 of a walker's row (t0 a multiple of K, so the prefix slot of column t0+j is j).
+// MODE 0: the first K columns (only the last one completes a level-1 window), 1: the next K (only the last two complete
+// a level-2 window), 2: steady state.  Every queue slot is assigned unconditionally (clamped indices), so that only the
+// GFW_PF slots in flight are live.
+// 16-byte shared store as two 8-byte stores: the two halves of a packed result sit in two register pairs, and a
+// 16-byte store would first move them into an aligned quad (4 MOVs)
+__device__ __forceinline__ void gfs_sts_pairs(float4* p, float4 v) {
+    const uint32_t a = gfs_smem_u32(p);
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};\n\tst.shared.v2.f32 [%0+8], {%3, %4};"
+                 ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+template <int K, int MODE, int NSTEPS, int NCOLS>
+__device__ __forceinline__ void gfw_steps(const float4* __restrict__ src, const GfsMoments* __restrict__ gm, float4* __restrict__ dst,
+                                          int t0, float inv, float4 (&Pa)[K], float4 (&Pb)[K], float4 (&vq)[K], float4 (&nmq)[K],
+                                          float2 (&rdq)[K]) {
+    constexpr int AW = NCOLS - (K - 1);
+#pragma unroll
+    for (int j = 0; j < NSTEPS; j++) {
+        const int t = t0 + j;                                  // column of the walk (VS1 index relative to its first column)
+        // loads of column t + PF: issued before this column's store (ptxas keeps shared loads behind shared stores)
+        const int tn = min(t + GFW_PF, NCOLS - 1);
+        const int cn = min(max(tn - (K - 1), 0), AW - 1);
+        vq[(j + GFW_PF) % K] = src[tn];
+        nmq[(j + GFW_PF) % K] = gm[cn].nm;
+        rdq[(j + GFW_PF) % K] = *(const float2*)&gm[cn].rd;
+        const float4 s = gfs_prefix_step<K>(Pa, vq[j], j);     // sum of VS1 columns t-K+1 .. t
+        if (MODE > 0 || j >= K - 1) {
+            const float4 nm = nmq[j];
+            const float2 rd = rdq[j];
+            const float mP = s.w;
+            // cov = corr_Ip - mean_I * mean_p ; a = cov / (var + eps) ; b = mean_p - a . mean_I      (A.cpp:2805-2847)
+            const float2 cov01 = __ffma2_rn(make_float2(nm.x, nm.y), make_float2(mP, mP), make_float2(s.x, s.y));
+            const float2 a01 = __fmul2_rn(cov01, rd);
+            const float a2 = fmaf(nm.z, mP, s.z) * nm.w;
+            const float b = fmaf(a01.x, nm.x, fmaf(a01.y, nm.y, fmaf(a2, nm.z, mP * inv)));
+            const float4 s2 = gfs_prefix_step<K>(Pb, make_float4(a01.x, a01.y, a2, b), (j + 1) % K);
+            if (MODE == 2 || (MODE == 1 && j >= K - 2)) gfs_sts_pairs(dst + t - 2 * (K - 1), s2);
+        }
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(GFW_THREADS, 1)
+k_gfs_walk(const FeatF* __restrict__ ref, const FeatF* __restrict__ tgt, const float4* __restrict__ Gi,
+           const GfsMoments* __restrict__ Gmom, const int* __restrict__ guide_mm, GfsGeom g,
+           TadStream tp, float c0, float* __restrict__ qv, uint32_t* __restrict__ slice_mm, int strip0) {
+    using L = GfwLayout<K>;
+    constexpr int A = L::A, AW = L::AW, QW = L::QW, P1 = L::P1, P2 = L::P2, PQ = L::PQ, ROWS = L::ROWS;
+    static_assert(GFS_NS * QW == GFW_COLS && ROWS <= 64 && ROWS % 2 == 0 && QW % 2 == 0, "role sizes");
+    constexpr int NCW = GFS_THREADS + GFW_WALKERS;             // participants of the cost <-> walker barriers
+    constexpr int NWC = GFW_WALKERS + GFW_COLS;                // participants of the walker <-> column barriers
+    extern __shared__ float4 sm_gfs[];
+    float4* VS1 = sm_gfs + L::oVS1;
+    float4* HS = sm_gfs + L::oHS;
+    uint64_t* mbar = (uint64_t*)(sm_gfs + L::oBar);            // [0..1] cost stages, [2..3] moment stages, [4..5] guidance stages
+
+    const int H = g.H, W = g.W;
+    const int x0 = (blockIdx.x + strip0) * QW;                 // first q' column of the strip
+    const int d0 = blockIdx.y * GFS_NS;
+    const int nb = g.nbands, band = blockIdx.z;
+    const int yb0 = (int)(((long long)H * band) / nb), yb1 = (int)(((long long)H * (band + 1)) / nb);
+    const bool top = band == 0, bottom = band == nb - 1;
+    int a0, U;                                                 // first (a,b) row of block 1, number of (a,b) blocks
+    if (bottom) { U = (H - yb0 + A + K - 1) / K; a0 = H - K * U; }
+    else { a0 = top ? 0 : yb0 - A; U = (yb1 + A - a0 + K - 1) / K; }
+    const int n_iter = U + (bottom ? 1 : 0);
+    const float inv = 1.0f / (float)(K * K);
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 6; i++) gfs_mbar_init(&mbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    FeatF* sRef = (FeatF*)(sm_gfs + L::oRef);
+    FeatF* sTgt = (FeatF*)(sm_gfs + L::oTgt);
+    GfsMoments* sGM = (GfsMoments*)(sm_gfs + L::oGM);
+    float4* sIQ = sm_gfs + L::oIQ;
+
+    if (threadIdx.x < GFS_THREADS) {
+        // =========================== cost warps: A / V1, thread = (slice, column) ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " GFW_STR(GFW_REG_COST) ";");   // 96 at launch
+        int sxmin, sxmax;
+        {   // source columns of the strip (see k_gfs_filter)
+            const int lo = x0 - 2 * A, hi = lo + GFS_IW - 1, per = W - 1;
+            sxmin = min(border_idx(lo, W, 1), border_idx(hi, W, 1));
+            sxmax = max(border_idx(lo, W, 1), border_idx(hi, W, 1));
+            int k = lo >= 0 ? (lo + per - 1) / per : -((-lo) / per);
+            for (; k * per <= hi; k++) {
+                if (k & 1) sxmax = W - 1; else sxmin = 0;
+            }
+        }
+        const int nref = sxmax - sxmin + 1;
+        const int xo_a = g.x0_base + g.x0_step * d0, xo_b = g.x0_base + g.x0_step * min(d0 + GFS_NS - 1, g.D - 1);
+        const int xomin = min(xo_a, xo_b), ntgt = nref + abs(xo_a - xo_b);
+        const int tid = threadIdx.x;
+        const int sl1 = tid >> 6, c1 = tid & 63;
+        const int di1 = min(d0 + sl1, g.D - 1);
+        const int sx1 = border_idx(x0 - 2 * A + c1, W, 1);
+        const int ia = sx1 - sxmin;
+        const int it = ia + (g.x0_base + g.x0_step * di1) - xomin;
+        float gsf, ghf;
+        minmax_scale_shift((double)guide_mm[0], (double)guide_mm[1], &gsf, &ghf);
+        const uint32_t tx_cost = (uint32_t)(K * (nref + ntgt) * 16);
+        auto issue_cost = [&](int u) {
+            const int st = u & 1;
+            gfs_mbar_expect_tx(&mbar[st], tx_cost);
+            const int p0 = a0 - A - 1 + K * u;
+#pragma unroll 1
+            for (int j = 0; j < K; j++) {
+                const int sy = gfs_reflect1(p0 + j, H);
+                gfs_bulk_g2s(sRef + (st * K + j) * GFS_IW, ref + (size_t)sy * W + sxmin, nref * 16, &mbar[st]);
+                gfs_bulk_g2s(sTgt + (st * K + j) * GFS_TP, tgt + (size_t)sy * g.Wp + sxmin + xomin, ntgt * 16, &mbar[st]);
+            }
+        };
+        if (tid == 0) issue_cost(0);
+        float4 r1[K], s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < K; j++) r1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float cmin = 3.0e38f, cmax = -3.0e38f;
+        for (int u = 0; u <= U; u++) {
+            gfs_bar_sync(GFW_BAR_COST, GFS_THREADS);
+            if (tid == 0 && u + 1 <= U) issue_cost(u + 1);
+            const FeatF* rs = sRef + ((u & 1) * K) * GFS_IW + ia;
+            const FeatF* ts = sTgt + ((u & 1) * K) * GFS_TP + it;
+            float4* vs = VS1 + (u & 1) * ROWS * P1 + sl1 * P1 + c1;
+            gfs_mbar_wait(&mbar[u & 1], (u >> 1) & 1);
+            if (u >= 2) gfs_bar_sync(GFW_BAR_EMPTY + (u & 1), NCW);
+            FeatF fa_q[GFS_CPF], fb_q[GFS_CPF];
+#pragma unroll
+            for (int j = 0; j < GFS_CPF; j++) { fa_q[j] = rs[j * GFS_IW]; fb_q[j] = ts[j * GFS_TP]; }
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const FeatF fa = fa_q[j % GFS_CPF];
+                const FeatF fb = fb_q[j % GFS_CPF];
+                if (j + GFS_CPF < K) { fa_q[j % GFS_CPF] = rs[(j + GFS_CPF) * GFS_IW]; fb_q[j % GFS_CPF] = ts[(j + GFS_CPF) * GFS_TP]; }
+                const float cp = gfs_cost(fa, fb, tp);
+                cmin = fminf(cmin, cp); cmax = fmaxf(cmax, cp);
+                const float cs = cp * inv;
+                const float I0 = fmaf((float)(fa.bgr & 0xFF), gsf, ghf), I1 = fmaf((float)((fa.bgr >> 8) & 0xFF), gsf, ghf);
+                const float I2 = fmaf((float)((fa.bgr >> 16) & 0xFF), gsf, ghf);
+                const float2 p01 = __fmul2_rn(make_float2(I0, I1), make_float2(cs, cs));
+                const float4 nw = make_float4(p01.x, p01.y, I2 * cs, cs);
+                vs[j * GFS_NS * P1] = gfs_ring_step<K>(r1, s1, nw, j);
+            }
+            __threadfence_block();
+            gfs_bar_arrive(GFW_BAR_FULL + (u & 1), NCW);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            cmin = fminf(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+            cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+        }
+        if ((tid & 31) == 0 && d0 + sl1 < g.D) {
+            atomicMin(&slice_mm[2 * di1], orderable_u32(__fadd_rn(c0, cmin)));
+            atomicMax(&slice_mm[2 * di1 + 1], orderable_u32(__fadd_rn(c0, cmax)));
+        }
+    } else if (threadIdx.x < GFS_THREADS + GFW_WALKERS) {
+        // =========================== walkers: H1 -> (a,b) -> H2 along one strip row ===========================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 " GFW_STR(GFW_REG_WALK) ";");
+        // a walker = (row of the block, slice, half of the row): the left half turns VS1 columns 0 .. QW/2+2(K-1)-1 into
+        // q' columns 0 .. QW/2-1, the right half starts QW/2 columns further (the 2(K-1) columns in between are walked twice:
+        // four warps instead of two on the critical path of the CTA)
+        const int wt = threadIdx.x - GFS_THREADS;
+        constexpr int TPW = ROWS / 2;                          // rows per walker warp
+        constexpr int NCOLS = QW / 2 + 2 * (K - 1);            // columns a walker reads
+        const int ww = wt >> 5, wl = wt & 31;
+        const bool w_on = wl < TPW;
+        const int task = min((ww & 1) * TPW + wl, ROWS - 1);   // shared-memory row = j * NS + slice
+        const int c_off = (ww >> 1) * (QW / 2);
+        const int hj = task / GFS_NS;
+        // the walkers stage their own operand (the moment records of the block's K rows) two blocks ahead: a stage is refilled
+        // as soon as every walker is done with it
+        const uint32_t tx_gm = (uint32_t)(K * AW * 32);
+        auto issue_gm = [&](int u) {
+            const int st = u & 1;
+            gfs_mbar_expect_tx(&mbar[2 + st], tx_gm);
+            const int abase = a0 + K * (u - 1);
+#pragma unroll 1
+            for (int j = 0; j < K; j++) {
+                const int ya = min(max(abase + j, 0), H - 1);
+                gfs_bulk_g2s(sGM + (st * K + j) * P2, Gmom + (size_t)ya * W + (x0 - A), AW * 32, &mbar[2 + st]);
+            }
+        };
+        if (wt == 0) { issue_gm(1); if (2 <= U) issue_gm(2); }
+        for (int u = 0; u <= U; u++) {
+            gfs_bar_sync(GFW_BAR_FULL + (u & 1), NCW);         // VS1[u & 1] written
+            if (u >= 1) {
+                gfs_mbar_wait(&mbar[2 + (u & 1)], ((u - 1) >> 1) & 1);           // moments of block u
+                if (u >= 3) gfs_bar_sync(GFW_BAR_HSEMPTY + (u & 1), NWC);        // column warps done with HS[u & 1] (block u-2)
+                if (w_on) {
+                    const float4* src = VS1 + (u & 1) * ROWS * P1 + task * P1 + c_off;
+                    const GfsMoments* gm = sGM + ((u & 1) * K + hj) * P2 + c_off;   // interior strip: staged index = (a,b) column
+                    float4* dst = HS + (u & 1) * ROWS * PQ + task * PQ + c_off;
+                    float4 Pa[K], Pb[K];                       // prefix sums of the previous K columns: level 1, level 2
+#pragma unroll
+                    for (int j = 0; j < K; j++) { Pa[j] = make_float4(0.f, 0.f, 0.f, 0.f); Pb[j] = Pa[j]; }
+                    float4 vq[K], nmq[K];
+                    float2 rdq[K];
+#pragma unroll
+                    for (int j = 0; j < GFW_PF; j++) {
+                        vq[j] = src[j];
+                        nmq[j] = gm[0].nm; rdq[j] = *(const float2*)&gm[0].rd;
+                    }
+                    constexpr int NFULL = NCOLS / K, REM = NCOLS - NFULL * K;
+                    static_assert(NFULL >= 2, "walk shorter than two blocks");
+                    gfw_steps<K, 0, K, NCOLS>(src, gm, dst, 0, inv, Pa, Pb, vq, nmq, rdq);
+                    gfw_steps<K, 1, K, NCOLS>(src, gm, dst, K, inv, Pa, Pb, vq, nmq, rdq);
+#pragma unroll 1
+                    for (int m = 2; m < NFULL; m++) gfw_steps<K, 2, K, NCOLS>(src, gm, dst, m * K, inv, Pa, Pb, vq, nmq, rdq);
+                    if (REM > 0) gfw_steps<K, 2, REM, NCOLS>(src, gm, dst, NFULL * K, inv, Pa, Pb, vq, nmq, rdq);
+                }
+                __threadfence_block();
+                gfs_bar_arrive(GFW_BAR_HSFULL + (u & 1), NWC);
+                if (u + 2 <= U) {
+                    gfs_bar_sync(GFW_BAR_WALK, GFW_WALKERS);   // every walker is done with the moment stage of block u
+                    if (wt == 0) issue_gm(u + 2);
+                }
+            }
+            if (u + 2 <= U) { __threadfence_block(); gfs_bar_arrive(GFW_BAR_EMPTY + (u & 1), NCW); }
+        }
+    } else {
+        // =========================== column warps: V2 + q', thread = (slice, q' column) ===========================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " GFW_STR(GFW_REG_COLS) ";");
+        const int tid = threadIdx.x - GFS_THREADS - GFW_WALKERS;
+        if (tid >= GFW_COLS) return;                           // the warpgroup's two spare warps
+        const int sl2 = tid / QW, cq = tid - sl2 * QW;
+        const int d = d0 + sl2;
+        const bool d_ok = d < g.D;
+        const int niq = min(W, x0 + QW) - x0;
+        const uint32_t tx_iq = (uint32_t)(K * niq * 16);
+        auto issue_iq = [&](int u) {        // guidance rows of block u -> guidance stage u & 1
+            const int st = u & 1;
+            gfs_mbar_expect_tx(&mbar[4 + st], tx_iq);
+            const int abase = a0 + K * (u - 1);
+#pragma unroll 1
+            for (int j = 0; j < K; j++) {
+                const int rq = min(max(abase - A + j, 0), H - 1);
+                gfs_bulk_g2s(sIQ + (st * K + j) * PQ, Gi + (size_t)rq * W + x0, niq * 16, &mbar[4 + st]);
+            }
+        };
+        if (tid == 0) { issue_iq(1); if (2 <= n_iter) issue_iq(2); }
+        float4 r2[K];                                          // column prefix sums of the previous block
+#pragma unroll
+        for (int j = 0; j < K; j++) r2[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 1; u <= n_iter; u++) {
+            const int abase = a0 + K * (u - 1);
+            if (u <= U) gfs_bar_sync(GFW_BAR_HSFULL + (u & 1), NWC);             // walkers done with block u
+            gfs_mbar_wait(&mbar[4 + (u & 1)], ((u - 1) >> 1) & 1);               // guidance rows of block u
+            const float4* src = HS + (u & 1) * ROWS * PQ + sl2 * PQ + cq;        // + j * NS * PQ
+            const float4* iq = sIQ + ((u & 1) * K) * PQ + min(cq, niq - 1);
+            float* qrow = qv + ((size_t)(abase - A) * g.D + d) * g.Wq + x0 + cq;  // output row of block row 0
+            const size_t qpitch = (size_t)g.D * g.Wq;
+            auto emit = [&](int j, float4 o) {                 // q' = abar . I + bbar (A.cpp:2852)
+                const int rq = abase - A + j;
+                if (rq >= yb0 && rq < yb1 && d_ok) {
+                    const float4 I = iq[j * PQ];
+                    qrow[(size_t)j * qpitch] = fmaf(o.x, I.x, fmaf(o.y, I.y, fmaf(o.z, I.z, o.w)));
+                }
+            };
+            if (u == U + 1) {
+                // bottom of the image: the last block = rows H-K .. H-1; output rows H-a .. H-1 (block rows 0 .. a-1)
+                float4 raw[K];
+                gfs_prefix_to_raw<K>(r2, raw);
+#pragma unroll
+                for (int i = 0; i < A; i++) emit(i, gfs_reflect_sum<K>(raw, K - A + i, false));
+            } else {
+                float4 in[K];
+#pragma unroll
+                for (int j = 0; j < K; j++) in[j] = src[j * GFS_NS * PQ];
+                if (u + 2 <= U) { __threadfence_block(); gfs_bar_arrive(GFW_BAR_HSEMPTY + (u & 1), NWC); }   // HS[u & 1] consumed
+                if (top && u == 1) {
+                    // top of the image: rows 0 .. K-1; output rows 0 .. a (block rows a .. K-1)
+#pragma unroll
+                    for (int i = 0; i <= A; i++) emit(A + i, gfs_reflect_sum<K>(in, i, true));
+                    r2[0] = in[0];
+#pragma unroll
+                    for (int j = 1; j < K; j++) r2[j] = p4add(r2[j - 1], in[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < K; j++) emit(j, gfs_prefix_step<K>(r2, in[j], j));
+                }
+            }
+            gfs_bar_sync(GFW_BAR_COLS, GFW_COLS);              // every column thread is done with the stage of block u
+            if (tid == 0 && u + 2 <= n_iter) issue_iq(u + 2);
+        }
+    }
+}
+
+#endif  // ASW_DEV_KERNELS
+
 // per-slice affine of cv::normalize (A.cpp:2775) applied after the (linear) filter: q = sf * q' + (c0 * sf + hf)
 __global__ void k_gfs_affine(const uint32_t* __restrict__ slice_mm, int D, float c0, float2* __restrict__ aff) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
@@ -595,8 +973,32 @@ static asw_status gfs_launch(asw_ctx* ctx, const FeatF* fref, const FeatF* ftgt,
     TadStream ts;
     ts.thr_c = (int)floorf(tp.thr_c); ts.add_c = (int)rintf(tp.add_c); ts.thr_g = tp.thr_g;
     ts.reg_r = (float)tp.reg_r; ts.reg = (float)tp.reg;
-    LAUNCH(ctx, "gfs_filter", (k_gfs_filter<K><<<dim3(strips, groups, nb), 2 * GFS_THREADS, smem, ctx->stream>>>(
-                                  fref, ftgt, Gi, Gmom, guide_mm, g, ts, tp.c0, qv, slice_mm)));
+    // dev builds: interior strips (every (a,b) column x0-A .. x0-A+AW-1 inside the image) can take the walker kernel
+    int s_lo = 0, s_hi = 0;
+#ifdef ASW_DEV_KERNELS
+    if (K == 9 && asw_dev("ASW_GFS_WALK")) {
+        constexpr int A = K / 2, AW = GfsLayout<K>::AW;
+        s_lo = 1;
+        s_hi = s_lo;
+        while (s_hi < strips && s_hi * QW - A + AW - 1 <= g.W - 1) s_hi++;
+    }
+#endif
+    if (s_hi > s_lo) {
+#ifdef ASW_DEV_KERNELS
+        const size_t smem_w = GfwLayout<9>::bytes;
+        cudaFuncSetAttribute(k_gfs_walk<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+        LAUNCH(ctx, "gfs_filter", (k_gfs_walk<9><<<dim3(s_hi - s_lo, groups, nb), GFW_THREADS, smem_w, ctx->stream>>>(
+                                      fref, ftgt, Gi, Gmom, guide_mm, g, ts, tp.c0, qv, slice_mm, s_lo)));
+        LAUNCH(ctx, "gfs_filter_edge", (k_gfs_filter<K><<<dim3(s_lo, groups, nb), 2 * GFS_THREADS, smem, ctx->stream>>>(
+                                      fref, ftgt, Gi, Gmom, guide_mm, g, ts, tp.c0, qv, slice_mm, 0)));
+        if (strips > s_hi)
+            LAUNCH(ctx, "gfs_filter_edge", (k_gfs_filter<K><<<dim3(strips - s_hi, groups, nb), 2 * GFS_THREADS, smem, ctx->stream>>>(
+                                          fref, ftgt, Gi, Gmom, guide_mm, g, ts, tp.c0, qv, slice_mm, s_hi)));
+#endif
+    } else {
+        LAUNCH(ctx, "gfs_filter", (k_gfs_filter<K><<<dim3(strips, groups, nb), 2 * GFS_THREADS, smem, ctx->stream>>>(
+                                      fref, ftgt, Gi, Gmom, guide_mm, g, ts, tp.c0, qv, slice_mm, 0)));
+    }
     LAUNCH(ctx, "gfs_affine", (k_gfs_affine<<<cdiv(cn, 128), 128, 0, ctx->stream>>>(slice_mm, cn, tp.c0, aff)));
     const dim3 wgrid(cdiv(cdiv(g.W, 4), 128), g.H);
     if (disp_direct && agg) {

@@ -71,7 +71,11 @@ def test_guided_filter_stage_golden(ctx):
 
 
 @pytest.mark.parametrize("H,W,D,win,eps,seed", [(40, 56, 8, 5, 1e-4, 7), (96, 128, 16, 9, 1e-4, 3),
-                                                 (75, 101, 12, 9, 1e-6, 9), (64, 64, 7, 15, 1e-4, 11)])
+                                                 (75, 101, 12, 9, 1e-6, 9), (64, 64, 7, 15, 1e-4, 11),
+                                                 # windows 11 / 13 / 15: the tiled pair (15 = the reference driver's own call,
+                                                 # aswStereoMatch.cpp:94), image not a multiple of the 18 x 50 output tile
+                                                 (70, 131, 9, 11, 1e-4, 12), (53, 90, 6, 13, 1e-4, 13), (97, 161, 10, 15, 1e-4, 14),
+                                                 (33, 40, 5, 17, 1e-4, 15)])
 def test_guidedf2_left(ctx, H, W, D, win, eps, seed):
     L, R, _ = make_pair(H, W, D, seed)
     d, q = ctx.computeAdaptiveWeight_GuidedF_2(L, R, 0, eps, win, 0, D, agg=True, strict=True)
