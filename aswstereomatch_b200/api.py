@@ -53,7 +53,7 @@ EXPORTS = [
     "asw_adaptive_weight_direct8", "asw_adaptive_weight_geodesic", "asw_adaptive_weight_bilateral_grid", "asw_adaptive_weight_blo1",
     "asw_adaptive_weight_guidedf", "asw_adaptive_weight_guidedf_2", "asw_adaptive_weight_guidedf_3", "asw_ncc", "asw_cost_ncc", "asw_adaptive_weight_weighted_median",
     "asw_capture_aggregated", "asw_cost_tad_cg", "asw_cost_sad_box", "asw_wta", "asw_guided_filter",
-    "asw_geodesic_dist", "asw_lr_check", "asw_fill_invalid", "asw_wmedian_refine", "asw_guidedf2_lr_refine", "asw_disparity_to_u8",
+    "asw_geodesic_dist", "asw_lr_check", "asw_fill_invalid", "asw_wmedian_refine", "asw_guidedf2_lr_refine", "asw_disparity_to_u8", "asw_preprocess", "asw_batch_upload_raw",
     "asw_batch_create", "asw_batch_destroy", "asw_batch_set_active", "asw_batch_upload", "asw_batch_run_guidedf2_lr_refine",
     "asw_batch_run_method", "asw_batch_download", "asw_split_local_keys", "asw_keys_alloc", "asw_keys_download",
     "asw_keys_upload", "asw_keys_min_merge", "asw_keys_to_disparity", "asw_keys_flip_sign", "asw_pool_create",
@@ -112,6 +112,8 @@ def load_library():
         "asw_wmedian_refine": (ci, [vp, pu8, pf32, pmask, ci, cd, cd, pf32]),
         "asw_guidedf2_lr_refine": (ci, [vp, pu8, pu8, pf32, cd, ci, ci, ci, cf, cd, cd, pf32, pf32, pmask]),
         "asw_disparity_to_u8": (ci, [vp, pf32, pmask]),
+        "asw_preprocess": (ci, [vp, pu8, pu8]),
+        "asw_batch_upload_raw": (ci, [vp, ci, pu8, pu8]),
         "asw_batch_create": (ci, [vp, ci, ci, ci, C.POINTER(vp)]),
         "asw_batch_destroy": (None, [vp]),
         "asw_batch_set_active": (ci, [vp, ci]),
@@ -413,6 +415,15 @@ class Context:
         self._chk(self.lib.asw_disparity_to_u8(self.h, C.byref(as_), C.byref(ms)))
         return m
 
+    def preprocess(self, img, width=640, height=360):
+        """the driver's per-image pre-processing (aswStereoMatch.cpp:30-31, 67-89): resize to width x height + V-channel
+        bilateral detail boost, CV_8UC3 -> CV_8UC3"""
+        a, as_ = _u8(img)
+        out = np.empty((int(height), int(width), 3), np.uint8)
+        _, os_ = _u8(out)
+        self._chk(self.lib.asw_preprocess(self.h, C.byref(as_), C.byref(os_)))
+        return out
+
     # ---- disparity split ----
     def split_local_keys(self, L, R, algorithm, disp_type, win, min_d, num_d, d_begin, d_end):
         La, Ls = _u8(L)
@@ -541,6 +552,12 @@ class Batch:
         La, Ls = _u8(L)
         Ra, Rs = _u8(R)
         self.ctx._chk(self.ctx.lib.asw_batch_upload(self.h, i, C.byref(Ls), C.byref(Rs)))
+
+    def upload_raw(self, i, L, R):
+        """raw frames of any size: uploaded once, pre-processed on the device (Context.preprocess) into slot i"""
+        La, Ls = _u8(L)
+        Ra, Rs = _u8(R)
+        self.ctx._chk(self.ctx.lib.asw_batch_upload_raw(self.h, i, C.byref(Ls), C.byref(Rs)))
 
     def set_active(self, n_pairs=None):
         """the run calls process pairs [0, n_pairs) (None: the whole batch)"""

@@ -67,7 +67,7 @@ struct asw_ctx {
     // tuning knobs (asw_set_tuning; 0 = the built-in choice)
     int tune[ASW_TUNE_COUNT] = {0};
     // host-built tables are cached per parameter set: nothing is uploaded (and nothing synchronises) on a repeated call
-    std::string table_key[8];
+    std::string table_key[12];                         // 6 per workspace bank
 };
 
 // workspace slots
@@ -103,7 +103,7 @@ static inline asw_status asw_fail(asw_ctx* ctx, asw_status st, const char* fmt, 
 static inline bool table_cached(asw_ctx* ctx, int ks, int ws_slot, const char* what) {
     char key[160];
     snprintf(key, sizeof(key), "%u|%s", ctx->bufs[ws_slot + ctx->ws_bank * WS_COUNT].gen, what);
-    ks += 4 * ctx->ws_bank;
+    ks += 6 * ctx->ws_bank;
     if (ctx->table_key[ks] == key) return true;
     ctx->table_key[ks] = key;
     return false;

@@ -720,5 +720,6 @@ static asw_status dev_guidedf2_lr_refine(asw_ctx* ctx, const uint8_t* dL, const 
 #include "k_grid.cuh"
 #include "k_blo1.cuh"
 #include "k_wmedian.cuh"
+#include "k_preproc.cuh"
 #include "asw_methods.inl"
 #include "asw_pool.inl"

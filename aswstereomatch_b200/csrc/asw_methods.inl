@@ -176,6 +176,22 @@ extern "C" asw_status asw_disparity_to_u8(asw_ctx* ctx, const asw_f32_image* dis
     return ASW_OK;
 }
 
+// driver pre-processing (aswStereoMatch.cpp:30-31, 67-89): resize to dst's size + V-channel bilateral detail boost
+extern "C" asw_status asw_preprocess(asw_ctx* ctx, const asw_u8_image* src, asw_u8_image* dst) {
+    if (!ctx) return ASW_ERR_BAD_ARG;
+    ASW_TRY(check_u8(ctx, src, 3)); ASW_TRY(check_u8(ctx, dst, 3));
+    ASW_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint8_t *raw, *out;
+    ASW_TRY(ws_get(ctx, WS_IMG_L, (size_t)src->rows * src->cols * 3, &raw));
+    ASW_TRY(ws_get(ctx, WS_IMG_R, (size_t)dst->rows * dst->cols * 3, &out));
+    ASW_TRY(upload_u8(ctx, src, raw));
+    ASW_TRY(dev_preprocess(ctx, raw, src->rows, src->cols, out, dst->rows, dst->cols));
+    const size_t rowb = (size_t)dst->cols * 3;
+    ASW_CUDA(ctx, cudaMemcpy2DAsync(const_cast<uint8_t*>(dst->data), dst->step, out, rowb, rowb, dst->rows, cudaMemcpyDeviceToHost, ctx->stream));
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ASW_OK;
+}
+
 static bool valid_disp_args(int disp_type, int min_d, int num_d) {
     return (disp_type == 0 || disp_type == 1) && min_d >= 0 && num_d > 0;
 }
@@ -384,6 +400,8 @@ struct asw_batch {
     uint8_t* imgs;     // [n][2][H][W][3]
     float* disp;       // [n][H][W]
     std::vector<cudaEvent_t> uploaded, computed, downloaded;
+    // asw_batch_upload_raw: staging for one raw pair (any size) + the event after which it may be overwritten
+    uint8_t* raw = nullptr; size_t raw_cap = 0; cudaEvent_t raw_free = nullptr;
 };
 static asw_status batch_pair_begin(asw_batch* b, int i) {
     asw_ctx* ctx = b->ctx;
@@ -425,6 +443,8 @@ extern "C" void asw_batch_destroy(asw_batch* b) {
         cudaEventDestroy(b->uploaded[i]); cudaEventDestroy(b->computed[i]); cudaEventDestroy(b->downloaded[i]);
     }
     cudaFree(b->imgs); cudaFree(b->disp);
+    if (b->raw) cudaFree(b->raw);
+    if (b->raw_free) cudaEventDestroy(b->raw_free);
     delete b;
 }
 extern "C" asw_status asw_batch_set_active(asw_batch* b, int n_active) {
@@ -444,6 +464,36 @@ extern "C" asw_status asw_batch_upload(asw_batch* b, int i, const asw_u8_image* 
     ASW_CUDA(ctx, cudaMemcpy2DAsync(b->imgs + (size_t)i * 2 * n3, rowb, L->data, L->step, rowb, b->H, cudaMemcpyHostToDevice, ctx->h2d_stream));
     ASW_CUDA(ctx, cudaMemcpy2DAsync(b->imgs + (size_t)i * 2 * n3 + n3, rowb, R->data, R->step, rowb, b->H, cudaMemcpyHostToDevice, ctx->h2d_stream));
     ASW_CUDA(ctx, cudaEventRecord(b->uploaded[i], ctx->h2d_stream));
+    return ASW_OK;
+}
+// raw frames (any size, CV_8UC3) -> the driver's pre-processing on the device -> the batch slot.  The raw pair is staged in
+// one buffer per batch: the next raw upload waits until the previous pre-processing has read it.
+extern "C" asw_status asw_batch_upload_raw(asw_batch* b, int i, const asw_u8_image* L, const asw_u8_image* R) {
+    if (!b || i < 0 || i >= b->n) return ASW_ERR_BAD_ARG;
+    asw_ctx* ctx = b->ctx;
+    ASW_TRY(check_pair(ctx, L, R, nullptr));
+    ASW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t raw3 = (size_t)L->rows * L->cols * 3, n3 = (size_t)b->H * b->W * 3;
+    if (!b->raw_free) ASW_CUDA(ctx, cudaEventCreateWithFlags(&b->raw_free, cudaEventDisableTiming));
+    if (b->raw_cap < 2 * raw3) {
+        ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ASW_CUDA(ctx, cudaStreamSynchronize(ctx->h2d_stream));
+        if (b->raw) cudaFree(b->raw);
+        b->raw = nullptr; b->raw_cap = 0;
+        if (cudaMalloc(&b->raw, 2 * raw3) != cudaSuccess) return asw_fail(ctx, ASW_ERR_NOMEM, "raw staging allocation failed%s%s");
+        b->raw_cap = 2 * raw3;
+    }
+    ASW_CUDA(ctx, cudaStreamWaitEvent(ctx->h2d_stream, b->raw_free, 0));          // the previous pair's pre-processing
+    const size_t rowb = (size_t)L->cols * 3;
+    ASW_CUDA(ctx, cudaMemcpy2DAsync(b->raw, rowb, L->data, L->step, rowb, L->rows, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    ASW_CUDA(ctx, cudaMemcpy2DAsync(b->raw + raw3, rowb, R->data, R->step, rowb, R->rows, cudaMemcpyHostToDevice, ctx->h2d_stream));
+    ASW_CUDA(ctx, cudaEventRecord(ctx->ev_copy, ctx->h2d_stream));
+    ASW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_copy, 0));
+    ASW_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, b->computed[i], 0));           // ordered anyway (same stream); explicit
+    ASW_TRY(dev_preprocess(ctx, b->raw, L->rows, L->cols, b->imgs + (size_t)i * 2 * n3, b->H, b->W));
+    ASW_TRY(dev_preprocess(ctx, b->raw + raw3, R->rows, R->cols, b->imgs + (size_t)i * 2 * n3 + n3, b->H, b->W));
+    ASW_CUDA(ctx, cudaEventRecord(b->raw_free, ctx->stream));
+    ASW_CUDA(ctx, cudaEventRecord(b->uploaded[i], ctx->stream));
     return ASW_OK;
 }
 extern "C" asw_status asw_batch_run_guidedf2_lr_refine(asw_batch* b, double eps, int win, int min_d, int num_d, float tol,

@@ -171,6 +171,11 @@ asw_status asw_guidedf2_lr_refine(asw_ctx* ctx, const asw_u8_image* left, const 
 /* driver post-processing (aswStereoMatch.cpp:97-98): disparityMap.convertTo(CV_8UC1) + normalize(0, 255, NORM_MINMAX) */
 asw_status asw_disparity_to_u8(asw_ctx* ctx, const asw_f32_image* disparity, asw_mask_image* out_u8);
 
+/* driver pre-processing (aswStereoMatch.cpp:30-31, 67-89): resize(src, Size(dst->cols, dst->rows)) [the driver: 640 x 360] +
+ * cvtColor(BGR2HSV) + bilateralFilter(V, 7, 10, 3, BORDER_REFLECT) + V = V + 2 (V - blur) + cvtColor(HSV2BGR), CV_8UC3.
+ * OpenCV 4.13's 8-bit arithmetic (resize / BGR2HSV bit-exact; HSV2BGR as cv2's vector body: see oracle/preproc.py) */
+asw_status asw_preprocess(asw_ctx* ctx, const asw_u8_image* src, asw_u8_image* dst);
+
 /* ---- device-resident batches (config 5; inputs live in HBM between upload and run) ---- */
 typedef struct asw_batch asw_batch;
 asw_status asw_batch_create(asw_ctx* ctx, int n_pairs, int rows, int cols, asw_batch** out);
@@ -178,6 +183,8 @@ void asw_batch_destroy(asw_batch* b);
 /* the run calls below process pairs [0, n_active) (default: all n_pairs) */
 asw_status asw_batch_set_active(asw_batch* b, int n_active);
 asw_status asw_batch_upload(asw_batch* b, int index, const asw_u8_image* left, const asw_u8_image* right);
+/* raw frames of any size: uploaded once, pre-processed on the device (asw_preprocess) into the pair's slot */
+asw_status asw_batch_upload_raw(asw_batch* b, int index, const asw_u8_image* left_raw, const asw_u8_image* right_raw);
 /* asynchronous on the ctx stream: every pair through asw_guidedf2_lr_refine's pipeline */
 asw_status asw_batch_run_guidedf2_lr_refine(asw_batch* b, double eps, int win_size, int min_disparity,
                                             int num_disparity, float lr_tol, double rate_s, double rate_r);
