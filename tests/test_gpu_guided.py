@@ -109,6 +109,20 @@ def test_guidedf2_config2_full_size(ctx):
     assert np.mean(np.abs(out - gt) <= 1) > 0.9
 
 
+@pytest.mark.parametrize("win,seed", [(11, 31), (15, 32)])
+def test_guidedf2_lr_refine_large_windows(ctx, win, seed):
+    """both views + LR + refine with the tiled pair (windows 11 / 13 / 15), the driver's own size and range (main.cpp:30, 94)"""
+    L, R, _ = make_pair(360, 640, 64, seed)
+    out, parts = ctx.guidedf2_lr_refine(L, R, 1e-4, win, 0, 64, parts=True)
+    ref, rparts = orc.guidedf2_lr_refine(L, R, 1e-4, win, 0, 64)
+    assert (parts["dl"] == rparts["dl"]).mean() >= AGREE
+    assert (parts["dr"] == rparts["dr"]).mean() >= AGREE
+    v = orc.lr_check(parts["dl"], parts["dr"], 0.0)
+    assert np.array_equal(parts["valid"], v)
+    assert np.array_equal(out, orc.wmedian_refine(L, orc.fill_invalid(parts["dl"], v), v, win, 10, 10))
+    assert (out == ref).mean() >= 0.995
+
+
 def test_stage4_pieces_bit_exact(ctx):
     rng = np.random.default_rng(5)
     L, R, _ = make_pair(60, 90, 16, 6)
