@@ -277,7 +277,7 @@ __global__ void k_init_slice_mm(uint32_t* mm, int D) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < D) { mm[2 * i] = 0xFFFFFFFFu; mm[2 * i + 1] = 0u; }
 }
-__global__ void k_init_mm_u8(int* mm) { mm[0] = 255; mm[1] = 0; }
+__global__ void k_init_mm_u8(int* mm) { mm[2 * threadIdx.x] = 255; mm[2 * threadIdx.x + 1] = 0; }   // one pair per thread
 // both of the above in one launch (streaming guided path)
 __global__ void k_gfs_init(uint32_t* slice_mm, int D, int* guide_mm) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -482,11 +482,65 @@ static asw_status dev_gf_generic_slice(asw_ctx* ctx, const GuidePrep& gp, const 
     LAUNCH(ctx, "init_slice_mm", (k_init_slice_mm<<<1, 32, 0, ctx->stream>>>(mm, 1)));
     LAUNCH(ctx, "minmax_f32", (k_minmax_f32_slices<<<dim3(ctx->sm_count * 2, 1), 256, 0, ctx->stream>>>(cost, n, mm)));
     unsigned nb = (unsigned)((n + 255) / 256);
-    LAUNCH(ctx, "gfg_products", (k_gfg_products<<<nb, 256, 0, ctx->stream>>>(cost, mm, gp.I, n, C, planes)));
+    LAUNCH(ctx, "gfg_products", (k_gfg_products<<<nb, 256, 0, ctx->stream>>>(cost, mm, gp.I, n, C, planes, 0)));
     ASW_TRY(launch_box_f32(ctx, planes, boxed, H, W, r, 1 + C, n));
-    LAUNCH(ctx, "gfg_ab", (k_gfg_ab<<<nb, 256, 0, ctx->stream>>>(boxed, gp.mI, gp.den, n, C)));
+    LAUNCH(ctx, "gfg_ab", (k_gfg_ab<<<nb, 256, 0, ctx->stream>>>(boxed, gp.mI, gp.den, n, C, 0)));
     ASW_TRY(launch_box_f32(ctx, boxed, planes, H, W, r, 1 + C, n));
-    LAUNCH(ctx, "gfg_q", (k_gfg_q<<<nb, 256, 0, ctx->stream>>>(planes, gp.I, n, C, q)));
+    LAUNCH(ctx, "gfg_q", (k_gfg_q<<<nb, 256, 0, ctx->stream>>>(planes, gp.I, n, C, q, 0)));
+    return ASW_OK;
+}
+
+// The generic guided filter of `ns` consecutive slices in ONE set of 13 launches per chunk (the per-slice form costs 13 launches
+// a slice: 839 launches / 12.5 ms for 64 slices of 640 x 360).  Slice s filters cost[s] -> q[s].  merge = true: 6-channel guidance
+// merge(ref, tpad cropped at column x0_first + s * x0_step), prepared per slice (GuidedF A.cpp:2905-2912, GuidedF_3 LEFT
+// A.cpp:3090-3097); merge = false: the 3-channel image `ref` guides every slice (GuidedF_3 RIGHT, A.cpp:3104).
+static asw_status dev_gf_generic_batch(asw_ctx* ctx, bool merge, const uint8_t* ref, const uint8_t* tpad, int H, int W, int Wp,
+                                       int ref_first, int x0_first, int x0_step, int ns, int win, double eps, const float* cost, float* q) {
+    const size_t n = (size_t)H * W;
+    const int C = merge ? 6 : 3;
+    const size_t per_slice = n * ((merge ? 6 + 4 * 2 * C * 2 : 0) + 4 * 2 * (1 + C));
+    int sb = (int)std::max<size_t>(1, std::min<size_t>((size_t)ns, ((size_t)3 << 30) / per_slice));
+    sb = std::min(sb, 1024);                                          // init_mm: one thread per slice
+    GuidePrep gp;
+    uint8_t* guide6 = nullptr;
+    float *gplanes = nullptr, *gboxed = nullptr, *planes, *boxed;
+    int* gmm = nullptr; uint32_t* smm;
+    if (merge) {
+        ASW_TRY(ws_get(ctx, WS_GUIDE6, n * 6 * sb, &guide6));
+        ASW_TRY(ws_get(ctx, WS_TMP0, n * 2 * C * sb, &gplanes));
+        ASW_TRY(ws_get(ctx, WS_TMP1, n * 2 * C * sb, &gboxed));
+        ASW_TRY(ws_get(ctx, WS_MISC0, (size_t)2 * sb + 64, &gmm));
+    } else {
+        ASW_TRY(prep_guide(ctx, ref, H, W, 3, win, eps, &gp));
+    }
+    ASW_TRY(ws_get(ctx, WS_TMP2, n * (1 + C) * sb, &planes));
+    ASW_TRY(ws_get(ctx, WS_TMP3, n * (1 + C) * sb, &boxed));
+    ASW_TRY(ws_get(ctx, WS_MISC1, (size_t)2 * sb + 64, &smm));
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    for (int s0 = 0; s0 < ns; s0 += sb) {
+        const int cn = std::min(sb, ns - s0);
+        const float *I, *mI, *den; size_t gstride;
+        if (merge) {
+            LAUNCH(ctx, "merge_guide6", (k_merge_guide6<<<dim3(cdiv(W, 128), H, cn), 128, 0, ctx->stream>>>(
+                                            ref, tpad, H, W, Wp, x0_first + s0 * x0_step, ref_first, guide6, x0_step)));
+            LAUNCH(ctx, "init_mm", (k_init_mm_u8<<<1, cn, 0, ctx->stream>>>(gmm)));
+            LAUNCH(ctx, "minmax_u8", (k_minmax_u8<<<dim3(std::max(1, ctx->sm_count * 4 / cn), cn), 256, 0, ctx->stream>>>(guide6, n * 6, gmm)));
+            LAUNCH(ctx, "guide_normalize", (k_guide_normalize<<<dim3(nb, cn), 256, 0, ctx->stream>>>(guide6, n, C, gmm, gplanes, nullptr)));
+            ASW_TRY(launch_box_f32(ctx, gplanes, gboxed, H, W, win, 2 * C * cn, n));
+            LAUNCH(ctx, "guide_finish", (k_guide_finish<<<dim3(nb, cn), 256, 0, ctx->stream>>>(gboxed, n, C, (float)eps, nullptr, nullptr)));
+            I = gplanes; mI = gboxed; den = gboxed + n * C; gstride = n * 2 * C;
+        } else {
+            I = gp.I; mI = gp.mI; den = gp.den; gstride = 0;
+        }
+        const float* c = cost + (size_t)s0 * n;
+        LAUNCH(ctx, "init_slice_mm", (k_init_slice_mm<<<cdiv(cn, 128), 128, 0, ctx->stream>>>(smm, cn)));
+        LAUNCH(ctx, "minmax_f32", (k_minmax_f32_slices<<<dim3(std::max(1, ctx->sm_count * 2 / cn), cn), 256, 0, ctx->stream>>>(c, n, smm)));
+        LAUNCH(ctx, "gfg_products", (k_gfg_products<<<dim3(nb, cn), 256, 0, ctx->stream>>>(c, smm, I, n, C, planes, gstride)));
+        ASW_TRY(launch_box_f32(ctx, planes, boxed, H, W, win, (1 + C) * cn, n));
+        LAUNCH(ctx, "gfg_ab", (k_gfg_ab<<<dim3(nb, cn), 256, 0, ctx->stream>>>(boxed, mI, den, n, C, gstride)));
+        ASW_TRY(launch_box_f32(ctx, boxed, planes, H, W, win, (1 + C) * cn, n));
+        LAUNCH(ctx, "gfg_q", (k_gfg_q<<<dim3(nb, cn), 256, 0, ctx->stream>>>(planes, I, n, C, q + (size_t)s0 * n, gstride)));
+    }
     return ASW_OK;
 }
 
@@ -543,21 +597,15 @@ static asw_status dev_guidedf(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR
     ASW_TRY(dev_cost_sad_box(ctx, dL, dR, H, W, disp_type, win, min_d, num_d, cost, nullptr, nullptr));
     ViewGeom v = make_view(dL, dR, H, W, disp_type, min_d, num_d);
     // padded target BGR image for the 6-channel guide (A.cpp:2877-2878)
-    uint8_t *tpad, *guide6;
+    uint8_t* tpad;
     ASW_TRY(ws_get(ctx, WS_MISC2, (size_t)H * v.Wp * 3, &tpad));
-    ASW_TRY(ws_get(ctx, WS_MISC3, n * 6, &guide6));
     LAUNCH(ctx, "pad_bgr", (k_pad_cols_bgr<<<dim3(cdiv(v.Wp, 128), H), 128, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, tpad)));
     float* q = agg_dev;
     if (!q) ASW_TRY(ws_get(ctx, WS_VOL1, n * num_d, &q));   // the |L-R| planes in WS_VOL1 are dead after dev_cost_sad_box
-    for (int i = 0; i < num_d; i++) {
-        // LEFT: Rect(numDisparity - i - 1, ..) (A.cpp:2909); RIGHT: Rect(i + minDisparity, ..) (A.cpp:2926)
-        int x0 = disp_type == ASW_DISPARITY_LEFT ? num_d - i - 1 : i + min_d;
-        LAUNCH(ctx, "merge_guide6", (k_merge_guide6<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(
-                                        v.ref, tpad, H, W, v.Wp, x0, disp_type == ASW_DISPARITY_LEFT ? 1 : 0, guide6)));
-        GuidePrep gp;
-        ASW_TRY(prep_guide(ctx, guide6, H, W, 6, win, eps, &gp));
-        ASW_TRY(dev_gf_generic_slice(ctx, gp, cost + (size_t)i * n, H, W, 6, win, q + (size_t)i * n));
-    }
+    // slice i: LEFT crops at Rect(numDisparity - i - 1, ..) (A.cpp:2909); RIGHT at Rect(i + minDisparity, ..) (A.cpp:2926)
+    const bool left = disp_type == ASW_DISPARITY_LEFT;
+    ASW_TRY(dev_gf_generic_batch(ctx, true, v.ref, tpad, H, W, v.Wp, left ? 1 : 0, left ? num_d - 1 : min_d, left ? -1 : 1,
+                                 num_d, win, eps, cost, q));
     unsigned long long* keys;
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));
     ASW_TRY(init_keys(ctx, keys, n));
@@ -627,20 +675,12 @@ static asw_status dev_guidedf3(asw_ctx* ctx, const uint8_t* dL, const uint8_t* d
     if (!q) ASW_TRY(ws_get(ctx, WS_VOL1, n * num_d, &q));
     if (disp_type == ASW_DISPARITY_LEFT) {
         ViewGeom v = make_view(dL, dR, H, W, disp_type, min_d, num_d);
-        uint8_t *tpad, *guide6;
+        uint8_t* tpad;
         ASW_TRY(ws_get(ctx, WS_IMG_PAD, (size_t)H * v.Wp * 3, &tpad));
-        ASW_TRY(ws_get(ctx, WS_GUIDE6, n * 6, &guide6));
         LAUNCH(ctx, "pad_bgr", (k_pad_cols_bgr<<<dim3(cdiv(v.Wp, 128), H), 128, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, tpad)));
-        for (int i = 0; i < num_d; i++) {
-            LAUNCH(ctx, "merge_guide6", (k_merge_guide6<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(v.ref, tpad, H, W, v.Wp, num_d - i - 1, 1, guide6)));
-            GuidePrep gp;
-            ASW_TRY(prep_guide(ctx, guide6, H, W, 6, win, eps, &gp));
-            ASW_TRY(dev_gf_generic_slice(ctx, gp, cost + (size_t)i * n, H, W, 6, win, q + (size_t)i * n));
-        }
+        ASW_TRY(dev_gf_generic_batch(ctx, true, v.ref, tpad, H, W, v.Wp, 1, num_d - 1, -1, num_d, win, eps, cost, q));
     } else {
-        GuidePrep gp;
-        ASW_TRY(prep_guide(ctx, dR, H, W, 3, win, eps, &gp));
-        for (int i = 0; i < num_d; i++) ASW_TRY(dev_gf_generic_slice(ctx, gp, cost + (size_t)i * n, H, W, 3, win, q + (size_t)i * n));
+        ASW_TRY(dev_gf_generic_batch(ctx, false, dR, nullptr, H, W, 0, 0, 0, 0, num_d, win, eps, cost, q));
     }
     unsigned long long* keys;
     ASW_TRY(ws_get(ctx, WS_KEYS, n, &keys));

@@ -24,6 +24,8 @@ __global__ void k_guide_normalize(const uint8_t* __restrict__ img, size_t n, int
                                   float* __restrict__ planes, float4* __restrict__ Gi) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    // blockIdx.y = slice of a batch (GuidedF / GuidedF_3: one guidance image per slice), every array slice-major
+    img += (size_t)blockIdx.y * n * C; mm += 2 * blockIdx.y; planes += (size_t)blockIdx.y * 2 * C * n;
     float sf, hf;
     minmax_scale_shift((double)mm[0], (double)mm[1], &sf, &hf);
     float v[6];
@@ -40,6 +42,7 @@ __global__ void k_guide_finish(float* __restrict__ boxed, size_t n, int C, float
                                float4* __restrict__ Gd) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    boxed += (size_t)blockIdx.y * 2 * C * n;                        // slice of a batch
     float m[6], dn[6];
     for (int c = 0; c < C; c++) {
         m[c] = boxed[(size_t)c * n + i];
@@ -57,10 +60,14 @@ __global__ void k_guide_finish(float* __restrict__ boxed, size_t n, int C, float
 // generic (plane) path kernels
 // ------------------------------------------------------------------------------------------------
 // p = normalize(cost) per slice; planes[0] = p, planes[1+c] = I_c * p          (A.cpp:2775, 2787-2792)
+// blockIdx.y = slice of a batch: cost / mm / planes are slice-major, the guidance arrays advance by gstride floats per slice
+// (0: one guidance image for every slice)
 __global__ void k_gfg_products(const float* __restrict__ cost, const uint32_t* __restrict__ mm_slice,
-                               const float* __restrict__ I, size_t n, int C, float* __restrict__ planes) {
+                               const float* __restrict__ I, size_t n, int C, float* __restrict__ planes, size_t gstride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    cost += (size_t)blockIdx.y * n; mm_slice += 2 * blockIdx.y; I += (size_t)blockIdx.y * gstride;
+    planes += (size_t)blockIdx.y * (1 + C) * n;
     float sf, hf;
     minmax_scale_shift((double)from_orderable(mm_slice[0]), (double)from_orderable(mm_slice[1]), &sf, &hf);
     float p = fmaf(cost[i], sf, hf);
@@ -69,9 +76,10 @@ __global__ void k_gfg_products(const float* __restrict__ cost, const uint32_t* _
 }
 // in: boxed[0] = mean_p, boxed[1+c] = corr_Ip_c; out: boxed[0] = b, boxed[1+c] = a_c   (A.cpp:2805-2847)
 __global__ void k_gfg_ab(float* __restrict__ boxed, const float* __restrict__ mI, const float* __restrict__ den,
-                         size_t n, int C) {
+                         size_t n, int C, size_t gstride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    boxed += (size_t)blockIdx.y * (1 + C) * n; mI += (size_t)blockIdx.y * gstride; den += (size_t)blockIdx.y * gstride;
     float mP = boxed[i];
     float dot = 0.0f;
     for (int c = 0; c < C; c++) {
@@ -86,9 +94,10 @@ __global__ void k_gfg_ab(float* __restrict__ boxed, const float* __restrict__ mI
 }
 // q = sum_c abar_c * I_c + bbar                                                 (A.cpp:2852)
 __global__ void k_gfg_q(const float* __restrict__ boxed, const float* __restrict__ I, size_t n, int C,
-                        float* __restrict__ q) {
+                        float* __restrict__ q, size_t gstride) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    boxed += (size_t)blockIdx.y * (1 + C) * n; I += (size_t)blockIdx.y * gstride; q += (size_t)blockIdx.y * n;
     float dot = 0.0f;
     for (int c = 0; c < C; c++) {
         float t = __fmul_rn(boxed[(size_t)(1 + c) * n + i], I[(size_t)c * n + i]);
@@ -97,10 +106,12 @@ __global__ void k_gfg_q(const float* __restrict__ boxed, const float* __restrict
     q[i] = __fadd_rn(dot, boxed[i]);
 }
 // 6-channel guidance for GuidedF: L (+) crop of padded R (A.cpp:2905-2912)
+// blockIdx.z = slice of a batch: crop column x0 + blockIdx.z * x0_step, output slice-major
 __global__ void k_merge_guide6(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt_pad, int H, int W,
-                               int Wp, int x0, int ref_first, uint8_t* __restrict__ out) {
+                               int Wp, int x0, int ref_first, uint8_t* __restrict__ out, int x0_step) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
+    x0 += (int)blockIdx.z * x0_step; out += (size_t)blockIdx.z * H * W * 6;
     const uint8_t* a = ref + ((size_t)y * W + x) * 3;
     const uint8_t* b = tgt_pad + ((size_t)y * Wp + x0 + x) * 3;
     uint8_t* o = out + ((size_t)y * W + x) * 6;

@@ -86,7 +86,9 @@ __global__ void k_bgr2gray_pad(const uint8_t* __restrict__ img, int H, int W, in
 }
 
 // min / max of a u8 buffer -> mm[0] = min, mm[1] = max (ints, pre-initialised to 255 / 0)
+// blockIdx.y = slice of a batch (n bytes per slice, one min / max pair per slice)
 __global__ void k_minmax_u8(const uint8_t* __restrict__ src, size_t n, int* __restrict__ mm) {
+    src += (size_t)blockIdx.y * n; mm += 2 * blockIdx.y;
     int mn = 255, mx = 0;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         int v = src[i];
@@ -168,8 +170,52 @@ __global__ void k_box_f32(const float* __restrict__ src, float* __restrict__ dst
     }
 }
 
+// Streaming form of the same filter (the default): one thread per halo column of a 128-column strip walks down a band of
+// rows with the vertical window sum in a double register (one row in, one row out), the horizontal sums run over shared
+// memory.  Sums of <= k^2 floats are exact in double for any data whose exponents span < 29 bits, so the summation order
+// does not change the rounded float (same argument as k_gfs_guide_moments); 2 global loads and k + 2 double adds per output
+// instead of the tiled kernel's ~4 k, and no (k-1)-row halo per 8 output rows.
+#define BOXS_COLS 128
+__global__ void __launch_bounds__(BOXS_COLS)
+k_box_f32_stream(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int k, size_t plane_stride, int band_rows) {
+    __shared__ double vs[2][BOXS_COLS];
+    const int a = k / 2, SW = BOXS_COLS - (k - 1);
+    const int cx = threadIdx.x, x0 = blockIdx.x * SW;
+    const int sx = border_idx(x0 - a + cx, W, 1);
+    const float* s = src + (size_t)blockIdx.z * plane_stride + sx;
+    float* o = dst + (size_t)blockIdx.z * plane_stride;
+    const int y_begin = blockIdx.y * band_rows, y_end = min(H, y_begin + band_rows);
+    double V = 0.0;
+    for (int j = -a; j < a; j++) V += (double)s[(size_t)border_idx(y_begin + j, H, 1) * W];
+    const double scale = 1.0 / ((double)k * k);
+    const int xo = x0 + cx;
+    const bool writer = cx < SW && xo < W;
+    int buf = 0;
+    for (int y = y_begin; y < y_end; y++) {
+        V += (double)s[(size_t)border_idx(y + a, H, 1) * W];
+        vs[buf][cx] = V;
+        V -= (double)s[(size_t)border_idx(y - a, H, 1) * W];
+        __syncthreads();
+        if (writer) {
+            double acc = 0.0;
+            for (int j = 0; j < k; j++) acc += vs[buf][cx + j];
+            o[(size_t)y * W + xo] = (float)(acc * scale);
+        }
+        buf ^= 1;
+    }
+}
+
 static inline asw_status launch_box_f32(asw_ctx* ctx, const float* src, float* dst, int H, int W, int k,
                                         int planes, size_t plane_stride) {
+    if (k - 1 <= BOXS_COLS / 2 && !asw_dev("ASW_BOX_TILED")) {
+        const int strips = cdiv(W, BOXS_COLS - (k - 1));
+        // bands: a band is entered once (k - 1 warm-up rows); as few as fill the GPU ~4 times over
+        int bands = std::max(1, std::min(cdiv(H, 4 * k), cdiv(4 * ctx->sm_count * 8, std::max(1, strips * planes))));
+        const int band_rows = cdiv(H, bands);
+        dim3 grid(strips, cdiv(H, band_rows), planes);
+        LAUNCH(ctx, "box_f32", (k_box_f32_stream<<<grid, BOXS_COLS, 0, ctx->stream>>>(src, dst, H, W, k, plane_stride, band_rows)));
+        return ASW_OK;
+    }
     const int TW = 32, TH = 8;
     size_t smem = ((size_t)(TH + k - 1) * (TW + k - 1) + (size_t)(TH + k - 1) * TW) * sizeof(double);
     if (smem > 200 * 1024) return asw_fail(ctx, ASW_ERR_UNSUPPORTED, "box window too large%s%s");
