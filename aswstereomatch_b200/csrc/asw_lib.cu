@@ -641,8 +641,14 @@ static asw_status dev_cost_ncc(asw_ctx* ctx, const uint8_t* dL, const uint8_t* d
     uint32_t* mm;
     ASW_TRY(ws_get(ctx, WS_SLICE_MM, (size_t)2 * num_d, &mm));
     LAUNCH(ctx, "init_slice_mm", (k_init_slice_mm<<<cdiv(num_d, 128), 128, 0, ctx->stream>>>(mm, num_d)));
-    LAUNCH(ctx, "ncc_cost", (k_ncc_cost<false><<<dim3(cdiv(W, 128), H, num_d), 128, 0, ctx->stream>>>(
-                                s.ref, s.mr, s.sr, s.tgt, s.mt, s.st, H, W, s.v.Wp, win, s.v.x0_base, s.v.x0_step, 0, min_d, vol, nullptr)));
+    if (ncc_tile_smem(win) <= 160 * 1024 && !asw_dev("ASW_NCC_DIRECT")) {
+        cudaFuncSetAttribute(k_ncc_cost_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ncc_tile_smem(win));
+        LAUNCH(ctx, "ncc_cost", (k_ncc_cost_tile<false><<<dim3(cdiv(W, NCC_COLS), H, cdiv(num_d, NCC_DC)), NCC_COLS, ncc_tile_smem(win), ctx->stream>>>(
+                                    s.ref, s.mr, s.sr, s.tgt, s.mt, s.st, H, W, s.v.Wp, win, s.v.x0_base, s.v.x0_step, num_d, min_d, vol, nullptr)));
+    } else {
+        LAUNCH(ctx, "ncc_cost", (k_ncc_cost<false><<<dim3(cdiv(W, 128), H, num_d), 128, 0, ctx->stream>>>(
+                                    s.ref, s.mr, s.sr, s.tgt, s.mt, s.st, H, W, s.v.Wp, win, s.v.x0_base, s.v.x0_step, 0, min_d, vol, nullptr)));
+    }
     LAUNCH(ctx, "minmax_f32", (k_minmax_f32_slices<<<dim3(std::max(1, ctx->sm_count * 2 / num_d), num_d), 256, 0, ctx->stream>>>(vol, n, mm)));
     LAUNCH(ctx, "normalize_slices", (k_normalize_slices<<<dim3((unsigned)((n + 255) / 256), num_d), 256, 0, ctx->stream>>>(vol, n, mm)));
     return ASW_OK;
@@ -658,8 +664,14 @@ static asw_status dev_ncc(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, in
     if (disp_type == ASW_DISPARITY_LEFT && num_d > 1) {
         NccDev s;
         ASW_TRY(dev_ncc_setup(ctx, dL, dR, H, W, disp_type, win, min_d, num_d, &s));
-        LAUNCH(ctx, "ncc_cost", (k_ncc_cost<true><<<dim3(cdiv(W, 128), H, num_d - 1), 128, 0, ctx->stream>>>(
-                                    s.ref, s.mr, s.sr, s.tgt, s.mt, s.st, H, W, s.v.Wp, win, s.v.x0_base, s.v.x0_step, 0, min_d, nullptr, keys)));
+        if (ncc_tile_smem(win) <= 160 * 1024 && !asw_dev("ASW_NCC_DIRECT")) {
+            cudaFuncSetAttribute(k_ncc_cost_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ncc_tile_smem(win));
+            LAUNCH(ctx, "ncc_cost", (k_ncc_cost_tile<true><<<dim3(cdiv(W, NCC_COLS), H, cdiv(num_d - 1, NCC_DC)), NCC_COLS, ncc_tile_smem(win), ctx->stream>>>(
+                                        s.ref, s.mr, s.sr, s.tgt, s.mt, s.st, H, W, s.v.Wp, win, s.v.x0_base, s.v.x0_step, num_d - 1, min_d, nullptr, keys)));
+        } else {
+            LAUNCH(ctx, "ncc_cost", (k_ncc_cost<true><<<dim3(cdiv(W, 128), H, num_d - 1), 128, 0, ctx->stream>>>(
+                                        s.ref, s.mr, s.sr, s.tgt, s.mt, s.st, H, W, s.v.Wp, win, s.v.x0_base, s.v.x0_step, 0, min_d, nullptr, keys)));
+        }
     }
     return keys_to_disp(ctx, keys, n, disp_dev);
 }

@@ -69,6 +69,64 @@ k_ncc_cost(const uint8_t* __restrict__ ref, const float* __restrict__ mr, const 
     else raw[(size_t)blockIdx.z * H * W + p] = (float)c;
 }
 
+// The same cost with the window rows staged in shared memory: one CTA = one image row x 128 columns x NCC_DC candidates.  The
+// REFLECT indices are resolved once when a row is staged (the direct kernel evaluates two of them per tap), the taps then read
+// floats at immediate offsets.  Identical float / double operations in the identical (window row-major) order: bit-identical
+// results; 3.4 -> ~1 ms at 640 x 360 x 64, window 15.
+#define NCC_COLS 128
+#define NCC_DC 8
+template <bool KEYS>
+__global__ void __launch_bounds__(NCC_COLS)
+k_ncc_cost_tile(const uint8_t* __restrict__ ref, const float* __restrict__ mr, const double* __restrict__ sr,
+                const uint8_t* __restrict__ tgt, const float* __restrict__ mt, const double* __restrict__ st, int H, int W, int Wt,
+                int win, int x0_base, int x0_step, int n_cand, int d_label0, float* __restrict__ raw, unsigned long long* __restrict__ keys) {
+    extern __shared__ float sm_ncc[];
+    const int h = win / 2, RW = NCC_COLS + 2 * h, TW = NCC_COLS + 2 * h + NCC_DC - 1;
+    float* RA = sm_ncc;                 // [win][RW]  reference rows, cell c <-> column x0 - h + c (REFLECT)
+    float* RB = sm_ncc + win * RW;      // [win][TW]  target rows, cell c <-> padded-target column t0 - h + c (REFLECT)
+    const int x0 = blockIdx.x * NCC_COLS, y = blockIdx.y, c0 = blockIdx.z * NCC_DC;
+    const int nc = min(NCC_DC, n_cand - c0);
+    // target window centres of the chunk: x + x0_base + x0_step * ci, ci = c0 .. c0 + nc - 1
+    const int ta = x0 + x0_base + x0_step * c0, tb = x0 + x0_base + x0_step * (c0 + nc - 1);
+    const int t0 = min(ta, tb);
+    for (int i = threadIdx.x; i < win * RW; i += NCC_COLS) {
+        const int j = i / RW, c = i - j * RW;
+        RA[i] = (float)ref[(size_t)border_idx(y - h + j, H, 0) * W + border_idx(x0 - h + c, W, 0)];
+    }
+    for (int i = threadIdx.x; i < win * TW; i += NCC_COLS) {
+        const int j = i / TW, c = i - j * TW;
+        RB[i] = (float)tgt[(size_t)border_idx(y - h + j, H, 0) * Wt + border_idx(t0 - h + c, Wt, 0)];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= W) return;
+    const float m0 = mr[(size_t)y * W + x];
+    const double s0 = sr[(size_t)y * W + x];
+    const size_t p = (size_t)y * W + x;
+    unsigned long long best = WTA_KEY_EMPTY;
+    for (int k = 0; k < nc; k++) {
+        const int ci = c0 + k;
+        const int xt = x + x0_base + x0_step * ci;                // window centre in the padded target
+        const float m1 = mt[(size_t)y * Wt + xt];
+        const float* a = RA + threadIdx.x;                        // cell of column x - h
+        const float* b = RB + (xt - t0);                          // cell of column xt - h
+        double sxy = 0.0;
+        for (int j = 0; j < win; j++) {
+#pragma unroll 5
+            for (int i = 0; i < win; i++) {
+                const float u = __fadd_rn(a[j * RW + i], -m0);
+                const float v = __fadd_rn(b[j * TW + i], -m1);
+                sxy += (double)__fmul_rn(u, v);
+            }
+        }
+        const double c = sxy / (s0 * st[(size_t)y * Wt + xt]);
+        if (KEYS) best = min(best, wta_key_d(c, d_label0 + ci));
+        else raw[(size_t)ci * H * W + p] = (float)c;
+    }
+    if (KEYS) atomicMin(&keys[p], best);
+}
+static inline size_t ncc_tile_smem(int win) { return (size_t)win * (2 * NCC_COLS + 4 * (win / 2) + NCC_DC - 1) * sizeof(float); }
+
 // normalize(slice, 0, 1, NORM_MINMAX) in place (A.cpp:974-976), one slice per blockIdx.y
 __global__ void k_normalize_slices(float* __restrict__ vol, size_t n, const uint32_t* __restrict__ mm) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

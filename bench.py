@@ -261,11 +261,12 @@ def main():
     split = None
     if not args.no_split:
         split = bench_split(ctx, asw, dist, torch, rank, world, local_rank, args)
-    cfgs = None
+    cfgs = methods = None
     if rank == 0 and world == 1 and not args.no_configs:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_configs
         cfgs = bench_configs.run_configs(ctx, reps=3, warmup=3, brief=True)
+        methods = bench_configs.run_driver_methods(ctx)
 
     # sanity: the last e2e result is a plausible disparity map (guards against timing a no-op)
     ok = bool(np.isfinite(map0).all() and map0.max() <= D - 1 and map0.std() > 0)
@@ -313,6 +314,9 @@ def main():
             line["split"] = split
         if cfgs:
             line["configs"] = cfgs
+        if methods:
+            # every dispatcher value of the hot path with the driver's own literals (640x360, win 15, D 64), kernel-only ms
+            line["driver_methods"] = methods
         if name in ALG_LANE_INSTR:
             # secondary view: the kernel moves far fewer HBM bytes than the 3-pass model, its own bound is the FP32
             # issue rate (148 SMs x 128 lanes x SM clock)

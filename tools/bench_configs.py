@@ -92,6 +92,37 @@ def run_configs(ctx, reps=3, warmup=3, only="", brief=False):
     return lines
 
 
+def run_driver_methods(ctx, reps=3, warmup=2):
+    """every value of the reference's dispatcher that belongs to the hot path (aswMethods.cpp:46-88), called the way the
+    reference's own driver calls it (aswStereoMatch.cpp:30, 94): 640x360, DISPARITY_LEFT, winSize 15, minDisparity 0,
+    numDisparity 64.  Kernel-only time with the pair resident, L2 flushed before every repetition."""
+    H, W, D, WIN = 360, 640, 64, 15
+    L, R, _ = make_pair(H, W, D, 9)
+    b = asw.Batch(ctx, 1, H, W)
+    b.upload(0, L, R)
+    names = {getattr(asw, k): k for k in ("ADAPTIVE_WEIGHT", "ADAPTIVE_WEIGHT_8DIRECT", "ADAPTIVE_WEIGHT_GEODESIC",
+                                          "ADAPTIVE_WEIGHT_BILATERAL_GRID", "ADAPTIVE_WEIGHT_BLO1", "ADAPTIVE_WEIGHT_GUIDED_FILTER",
+                                          "ADAPTIVE_WEIGHT_GUIDED_FILTER_2", "ADAPTIVE_WEIGHT_GUIDED_FILTER_3",
+                                          "ADAPTIVE_WEIGHT_MEDIAN", "NCC")}
+    out = []
+    for alg in sorted(names):
+        for _ in range(warmup):
+            b.run_method(alg, 0, WIN, 0, D)
+        ctx.sync()
+        ts = []
+        for _ in range(reps):
+            ctx.flush_l2()
+            ctx.timer_start()
+            b.run_method(alg, 0, WIN, 0, D)
+            ts.append(ctx.timer_stop())
+        n0 = ctx.launch_count()
+        b.run_method(alg, 0, WIN, 0, D)
+        ctx.sync()
+        out.append({"algorithm": names[alg], "ms": round(float(np.median(ts)), 4), "launches": int(ctx.launch_count() - n0)})
+    b.close()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=3)
