@@ -183,6 +183,161 @@ k_wm_aggregate2(const float* __restrict__ WL, const float* __restrict__ WR, cons
     atomicMin(&keys[p], wta_key(result, d_label0 + off));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Warp-per-evaluation path (the default).  The heap kernel keeps a 225-entry heap per THREAD in shared memory: 86 KB per
+// 32-thread CTA, two warps per SM.  Here one warp owns one pixel and walks its candidates; the win^2 (cost bits << 32 | window
+// index) keys sit 8 per lane in registers and are sorted with a 256-element bitonic network (21 in-lane stages, 15 shuffle
+// stages) -- the index in the low bits makes the keys distinct, so the order is the reference's stable ascending order.  The
+// weights (wL * spatial) * wR go to a per-warp shared array and are gathered in sorted order; their running sum is a per-lane
+// prefix + a warp scan in double, and the first element whose partial sum exceeds half the total selects its predecessor
+// (A.cpp:3276-3304).  Weight planes are pixel-major ([y][x][tap]) so that a warp reads one pixel's window contiguously.
+// 301 -> ~35 ms at 640 x 360 x 64, window 15.
+// ---------------------------------------------------------------------------------------------
+#define WM3_WARPS 4
+// out[(y * Wout + xo) * n + t]
+__global__ void k_wm_weights_px(const uint32_t* __restrict__ img, int H, int W, int Wout, int pad, int win, double alpha_r,
+                                float* __restrict__ out) {
+    const int n = win * win;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)H * Wout * n) return;
+    const int t = (int)(i % n);
+    const size_t pix = i / n;
+    const int xo = (int)(pix % Wout), y = (int)(pix / Wout);
+    const int h = win / 2, wy = t / win, wx = t - wy * win;
+    const uint32_t c = img[(size_t)y * W + border_idx(xo - pad, W, 0)];
+    const int sy = border_idx(y - h + wy, H, 0);
+    const int xb = border_idx(xo - h + wx, Wout, 0);
+    const uint32_t q = img[(size_t)sy * W + border_idx(xb - pad, W, 0)];
+    float d0 = (float)abs((int)(q & 0xFF) - (int)(c & 0xFF)), d1 = (float)abs((int)((q >> 8) & 0xFF) - (int)((c >> 8) & 0xFF));
+    float d2 = (float)abs((int)((q >> 16) & 0xFF) - (int)((c >> 16) & 0xFF));
+    out[i] = (float)exp((double)(float)fma((double)__fadd_rn(d0, d1), alpha_r, __dmul_rn((double)d2, alpha_r)));
+}
+
+__device__ __forceinline__ void wm3_cx(unsigned long long& a, unsigned long long& b, bool asc) {   // in-lane compare-exchange
+    const unsigned long long lo = min(a, b), hi = max(a, b);
+    a = asc ? lo : hi; b = asc ? hi : lo;
+}
+// 256 keys, 8 per lane (element e = lane * 8 + r), ascending
+__device__ __forceinline__ void wm3_sort256(unsigned long long (&k)[8], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 256; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 8) {
+                const int lm = stride >> 3;                                // partner lane = lane ^ lm
+                const bool asc = size == 256 ? true : ((lane & (size >> 3)) == 0);
+                const bool lower = (lane & lm) == 0;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[r], lm);
+                    k[r] = (lower == asc) ? min(k[r], o) : max(k[r], o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    if ((r & stride) == 0) {
+                        const bool asc = size >= 16 ? (size == 256 ? true : ((lane & (size >> 3)) == 0))
+                                                    : (size == 8 ? ((lane & 1) == 0) : ((r & size) == 0));
+                        wm3_cx(k[r], k[r | stride], asc);
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32 * WM3_WARPS)
+k_wm_aggregate3(const float* __restrict__ WL, const float* __restrict__ WR, const float* __restrict__ cost, WmGeom g,
+                float alpha_s, int d_label0, unsigned long long* __restrict__ keys, float* __restrict__ agg) {
+    __shared__ float wsm[WM3_WARPS][256];
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    const int win = g.win, h = g.h, n = win * win, W = g.W, H = g.H, Wr = W + g.max_off;
+    const int x = blockIdx.x * WM3_WARPS + wp, y = blockIdx.y;
+    if (x >= W) return;
+    const size_t p = (size_t)y * W + x, sl = (size_t)H * W;
+    // per lane: its 8 window elements t = lane * 8 + r: cost offset inside a slice, wL * spatial (candidate-independent)
+    int coff[8];
+    float wls[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int t = lane * 8 + r;
+        if (t < n) {
+            const int wy = t / win, wx = t - wy * win;
+            coff[r] = border_idx(y - h + wy, H, 0) * W + border_idx(x - h + wx, W, 0);
+            const float dist2 = __fadd_rn((float)((wx - h) * (wx - h)), (float)((wy - h) * (wy - h)));
+            const float wsp = (float)exp((double)__fmul_rn(dist2, alpha_s));                 // A.cpp:3219-3225
+            wls[r] = __fmul_rn(__ldg(&WL[p * n + t]), wsp);                                  // wL.mul(dist)
+        } else { coff[r] = 0; wls[r] = 0.0f; }
+    }
+    unsigned long long best = WTA_KEY_EMPTY;
+    for (int off = 0; off < g.D; off++) {
+        const int xr = x - off + g.D - 1;                         // weightWinsR[y][x - offset + numDisparity - 1]
+        const float* wr = WR + ((size_t)y * Wr + xr) * n;
+        const float* cs = cost + (size_t)off * sl;
+        unsigned long long k[8];
+        double lsum = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int t = lane * 8 + r;
+            if (t < n) {
+                const float w = __fmul_rn(wls[r], __ldg(&wr[t]));                            // .mul(wR)
+                wsm[wp][t] = w;
+                lsum += (double)w;
+                k[r] = ((unsigned long long)__float_as_uint(cs[coff[r]]) << 32) | (unsigned)t;   // costs >= 0: bit order = value order
+            } else {
+                wsm[wp][t] = 0.0f;
+                k[r] = 0xFFFFFFFFFFFFFFFFull;
+            }
+        }
+        double total = lsum;                                       // cv::sum of the weights, double
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+        const double half = total / 2;
+        __syncwarp();
+        wm3_sort256(k, lane);
+        // running weight sums in sorted order
+        double pre[8];
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) { acc += (double)wsm[wp][(int)(k[r] & 0xFFu)]; pre[r] = acc; }
+        double scan = acc;                                         // inclusive scan of the lane totals
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = __shfl_up_sync(0xffffffffu, scan, o);
+            if (lane >= o) scan += up;
+        }
+        const double base = scan - acc;                            // sum of every element before this lane's
+        int cross = 8;
+#pragma unroll
+        for (int r = 7; r >= 0; r--) if (base + pre[r] > half) cross = r;
+        const unsigned ball = __ballot_sync(0xffffffffu, cross < 8);
+        const unsigned prev_last = __shfl_up_sync(0xffffffffu, (unsigned)(k[7] >> 32), 1);   // previous lane's largest value
+        float result = 0.0f;
+        if (ball) {
+            const int src = __ffs(ball) - 1;                       // lane that holds the first crossing element
+            unsigned vb = 0;
+            if (lane == src) {
+                // the element BEFORE the crossing one; the very first element of the order selects itself (A.cpp:3296-3302)
+                if (cross == 0) {
+                    vb = (src == 0) ? (unsigned)(k[0] >> 32) : prev_last;
+                } else {
+                    vb = (unsigned)(k[0] >> 32);
+#pragma unroll
+                    for (int r = 1; r < 7; r++) if (cross - 1 == r) vb = (unsigned)(k[r] >> 32);
+                }
+            }
+            vb = __shfl_sync(0xffffffffu, vb, src);
+            result = __uint_as_float(vb);
+        }
+        __syncwarp();                                              // wsm is rewritten by the next candidate
+        if (lane == 0) {
+            if (agg) agg[(size_t)off * sl + p] = result;
+            best = min(best, wta_key(result, d_label0 + off));
+        }
+    }
+    if (lane == 0) atomicMin(&keys[p], best);
+}
+
 static asw_status dev_weighted_median(asw_ctx* ctx, const uint8_t* dL, const uint8_t* dR, int H, int W, int win,
                                       double rate_s, double rate_r, int min_d, int num_d, float* disp_dev, float* agg_dev) {
     if (win > WM_MAXWIN)
@@ -215,6 +370,16 @@ static asw_status dev_weighted_median(asw_ctx* ctx, const uint8_t* dL, const uin
     float alpha_s = (float)((1.0 / rate_s) * (-1));
     const int nn = win * win, Wr = W + v.max_off;
     const size_t planes = (size_t)nn * H * ((size_t)W + Wr) * sizeof(float);
+    if (!asw_dev("ASW_WM_SCAN") && !asw_dev("ASW_WM_HEAP") && planes <= ((size_t)6 << 30) && nn <= 256) {
+        float *WLp, *WRp;
+        ASW_TRY(ws_get(ctx, WS_GEO_L, (size_t)nn * H * W, &WLp));
+        ASW_TRY(ws_get(ctx, WS_GEO_R, (size_t)nn * H * Wr, &WRp));
+        LAUNCH(ctx, "wm_weights", (k_wm_weights_px<<<(unsigned)(((size_t)nn * H * W + 255) / 256), 256, 0, ctx->stream>>>(pl, H, W, W, 0, win, alpha_r, WLp)));
+        LAUNCH(ctx, "wm_weights", (k_wm_weights_px<<<(unsigned)(((size_t)nn * H * Wr + 255) / 256), 256, 0, ctx->stream>>>(pr, H, W, Wr, v.max_off, win, alpha_r, WRp)));
+        LAUNCH(ctx, "wm_aggregate", (k_wm_aggregate3<<<dim3(cdiv(W, WM3_WARPS), H), 32 * WM3_WARPS, 0, ctx->stream>>>(
+                                        WLp, WRp, cost, g, alpha_s, min_d, keys, agg_dev)));
+        return keys_to_disp(ctx, keys, n, disp_dev);
+    }
     if (!asw_dev("ASW_WM_SCAN") && planes <= ((size_t)6 << 30)) {
         float *WLp, *WRp;
         ASW_TRY(ws_get(ctx, WS_GEO_L, (size_t)nn * H * W, &WLp));
