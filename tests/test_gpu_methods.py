@@ -266,6 +266,40 @@ def test_weighted_median_method(ctx, H, W, D, win, seed):
     assert (d == d_ref).mean() >= AGREE
 
 
+@pytest.mark.parametrize("H,W,D,win,seed", [(33, 47, 5, 15, 4), (21, 30, 3, 13, 5), (17, 9, 2, 3, 6)])
+def test_weighted_median_warp_kernel_edges(ctx, H, W, D, win, seed):
+    """the warp-per-pixel selection kernel: the largest window (225 of its 256 key slots), windows larger than the image
+    in one direction, widths that are not a multiple of the 4 pixels of a CTA, a 9-element window"""
+    L, R, _ = make_pair(H, W, D, seed)
+    d, q = ctx.computeAdaptiveWeight_WeightedMedian(L, R, 0, win, 10, 10, 0, D, agg=True, strict=True)
+    d_ref, q_ref = orc.asw_weighted_median(L, R, 0, win, 10, 10, 0, D, agg=True)
+    assert (q == q_ref).mean() >= 0.999
+    assert (d == d_ref).mean() >= AGREE
+
+
+@pytest.mark.parametrize("H,W,D,win,seed", [(30, 150, 11, 9, 7), (40, 131, 3, 21, 8)])
+def test_ncc_tile_kernel_edges(ctx, H, W, D, win, seed):
+    """k_ncc_cost_tile: candidate counts that are not a multiple of its 8-candidate chunks, a second 128-column strip that
+    is partly outside the image, a window wider than its candidate chunk; bit-compatible with the direct kernel's order"""
+    L, R, _ = make_pair(H, W, D, seed)
+    for dt in (0, 1):
+        v = ctx.computeNCC_volume(L, R, dt, win, 0, D)
+        assert np.abs(v - orc.cost_ncc(L, R, 0, D, win, dt)).max() <= 1e-6
+        assert (ctx.computeNCC(L, R, dt, win, 0, D, strict=True) == orc.asw_ncc(L, R, dt, win, 0, D)).mean() >= AGREE
+
+
+@pytest.mark.parametrize("D", [2, 5])
+def test_guidedf_batched_slices(ctx, D):
+    """GuidedF (6-channel guidance per slice) runs every slice of a chunk in one set of launches: two slices, several slices,
+    both views, against the per-slice oracle"""
+    L, R, _ = make_pair(37, 52, max(D, 2), 9)
+    for dt in (0, 1):
+        d, q = ctx.computeAdaptiveWeight_GuidedF(L, R, dt, 1e-6, 7, 0, D, agg=True, strict=True)
+        d_ref, q_ref = orc.asw_guidedf(L, R, dt, 1e-6, 7, 0, D, agg=True)
+        assert rel_err(q, q_ref) <= REL_TOL
+        assert (d == d_ref).mean() >= AGREE
+
+
 def test_weighted_median_dispatcher_and_limits(ctx):
     L, R, _ = make_pair(32, 44, 6, 3)
     d = ctx.stereoMatching(L, R, 0, asw.ADAPTIVE_WEIGHT_MEDIAN, 7, 0, 6, strict=True)
