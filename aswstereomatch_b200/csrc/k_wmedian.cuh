@@ -186,8 +186,8 @@ k_wm_aggregate2(const float* __restrict__ WL, const float* __restrict__ WR, cons
 // ---------------------------------------------------------------------------------------------
 // Warp-per-evaluation path (the default).  The heap kernel keeps a 225-entry heap per THREAD in shared memory: 86 KB per
 // 32-thread CTA, two warps per SM.  Here one warp owns one pixel and walks its candidates; the win^2 (cost bits << 32 | window
-// index) keys sit 8 per lane in registers and are sorted with a 256-element bitonic network (21 in-lane stages, 15 shuffle
-// stages) -- the index in the low bits makes the keys distinct, so the order is the reference's stable ascending order.  The
+// index) keys sit 2 / 4 / 8 per lane in registers (64 / 128 / 256 slots for windows up to 7 / 11 / 15) and are sorted with a bitonic
+// network (256 slots: 21 in-lane stages, 15 shuffle stages) -- the index in the low bits makes the keys distinct, so the order is the reference's stable ascending order.  The
 // weights (wL * spatial) * wR go to a per-warp shared array and are gathered in sorted order; their running sum is a per-lane
 // prefix + a warp scan in double, and the first element whose partial sum exceeds half the total selects its predecessor
 // (A.cpp:3276-3304).  Weight planes are pixel-major ([y][x][tap]) so that a warp reads one pixel's window contiguously.
@@ -217,27 +217,29 @@ __device__ __forceinline__ void wm3_cx(unsigned long long& a, unsigned long long
     const unsigned long long lo = min(a, b), hi = max(a, b);
     a = asc ? lo : hi; b = asc ? hi : lo;
 }
-// 256 keys, 8 per lane (element e = lane * 8 + r), ascending
-__device__ __forceinline__ void wm3_sort256(unsigned long long (&k)[8], int lane) {
+// 32 * E keys, E per lane (element e = lane * E + r), ascending; E = 2, 4, 8
+template <int E>
+__device__ __forceinline__ void wm3_sort(unsigned long long (&k)[E], int lane) {
+    constexpr int N = 32 * E;
 #pragma unroll
-    for (int size = 2; size <= 256; size <<= 1) {
+    for (int size = 2; size <= N; size <<= 1) {
 #pragma unroll
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= 8) {
-                const int lm = stride >> 3;                                // partner lane = lane ^ lm
-                const bool asc = size == 256 ? true : ((lane & (size >> 3)) == 0);
+            if (stride >= E) {
+                const int lm = stride / E;                                 // partner lane = lane ^ lm
+                const bool asc = size == N ? true : ((lane & (size / E)) == 0);
                 const bool lower = (lane & lm) == 0;
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
+                for (int r = 0; r < E; r++) {
                     const unsigned long long o = __shfl_xor_sync(0xffffffffu, k[r], lm);
                     k[r] = (lower == asc) ? min(k[r], o) : max(k[r], o);
                 }
             } else {
 #pragma unroll
-                for (int r = 0; r < 8; r++) {
+                for (int r = 0; r < E; r++) {
                     if ((r & stride) == 0) {
-                        const bool asc = size >= 16 ? (size == 256 ? true : ((lane & (size >> 3)) == 0))
-                                                    : (size == 8 ? ((lane & 1) == 0) : ((r & size) == 0));
+                        // direction bit of element e = lane * E + r for this merge size
+                        const bool asc = size == N ? true : (size >= E ? ((lane & (size / E)) == 0) : ((r & size) == 0));
                         wm3_cx(k[r], k[r | stride], asc);
                     }
                 }
@@ -246,21 +248,23 @@ __device__ __forceinline__ void wm3_sort256(unsigned long long (&k)[8], int lane
     }
 }
 
+// E = key slots per lane: 2 for windows up to 7 (n <= 64), 4 up to 11 (n <= 128), 8 up to 15 (n <= 256)
+template <int E>
 __global__ void __launch_bounds__(32 * WM3_WARPS)
 k_wm_aggregate3(const float* __restrict__ WL, const float* __restrict__ WR, const float* __restrict__ cost, WmGeom g,
                 float alpha_s, int d_label0, unsigned long long* __restrict__ keys, float* __restrict__ agg) {
-    __shared__ float wsm[WM3_WARPS][256];
+    __shared__ float wsm[WM3_WARPS][32 * E];
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     const int win = g.win, h = g.h, n = win * win, W = g.W, H = g.H, Wr = W + g.max_off;
     const int x = blockIdx.x * WM3_WARPS + wp, y = blockIdx.y;
     if (x >= W) return;
     const size_t p = (size_t)y * W + x, sl = (size_t)H * W;
-    // per lane: its 8 window elements t = lane * 8 + r: cost offset inside a slice, wL * spatial (candidate-independent)
-    int coff[8];
-    float wls[8];
+    // per lane: its E window elements t = lane * E + r: cost offset inside a slice, wL * spatial (candidate-independent)
+    int coff[E];
+    float wls[E];
 #pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const int t = lane * 8 + r;
+    for (int r = 0; r < E; r++) {
+        const int t = lane * E + r;
         if (t < n) {
             const int wy = t / win, wx = t - wy * win;
             coff[r] = border_idx(y - h + wy, H, 0) * W + border_idx(x - h + wx, W, 0);
@@ -274,11 +278,11 @@ k_wm_aggregate3(const float* __restrict__ WL, const float* __restrict__ WR, cons
         const int xr = x - off + g.D - 1;                         // weightWinsR[y][x - offset + numDisparity - 1]
         const float* wr = WR + ((size_t)y * Wr + xr) * n;
         const float* cs = cost + (size_t)off * sl;
-        unsigned long long k[8];
+        unsigned long long k[E];
         double lsum = 0.0;
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int t = lane * 8 + r;
+        for (int r = 0; r < E; r++) {
+            const int t = lane * E + r;
             if (t < n) {
                 const float w = __fmul_rn(wls[r], __ldg(&wr[t]));                            // .mul(wR)
                 wsm[wp][t] = w;
@@ -294,12 +298,12 @@ k_wm_aggregate3(const float* __restrict__ WL, const float* __restrict__ WR, cons
         for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
         const double half = total / 2;
         __syncwarp();
-        wm3_sort256(k, lane);
+        wm3_sort<E>(k, lane);
         // running weight sums in sorted order
-        double pre[8];
+        double pre[E];
         double acc = 0.0;
 #pragma unroll
-        for (int r = 0; r < 8; r++) { acc += (double)wsm[wp][(int)(k[r] & 0xFFu)]; pre[r] = acc; }
+        for (int r = 0; r < E; r++) { acc += (double)wsm[wp][(int)(k[r] & (unsigned)(32 * E - 1))]; pre[r] = acc; }
         double scan = acc;                                         // inclusive scan of the lane totals
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -307,11 +311,11 @@ k_wm_aggregate3(const float* __restrict__ WL, const float* __restrict__ WR, cons
             if (lane >= o) scan += up;
         }
         const double base = scan - acc;                            // sum of every element before this lane's
-        int cross = 8;
+        int cross = E;
 #pragma unroll
-        for (int r = 7; r >= 0; r--) if (base + pre[r] > half) cross = r;
-        const unsigned ball = __ballot_sync(0xffffffffu, cross < 8);
-        const unsigned prev_last = __shfl_up_sync(0xffffffffu, (unsigned)(k[7] >> 32), 1);   // previous lane's largest value
+        for (int r = E - 1; r >= 0; r--) if (base + pre[r] > half) cross = r;
+        const unsigned ball = __ballot_sync(0xffffffffu, cross < E);
+        const unsigned prev_last = __shfl_up_sync(0xffffffffu, (unsigned)(k[E - 1] >> 32), 1);   // previous lane's largest value
         float result = 0.0f;
         if (ball) {
             const int src = __ffs(ball) - 1;                       // lane that holds the first crossing element
@@ -323,7 +327,7 @@ k_wm_aggregate3(const float* __restrict__ WL, const float* __restrict__ WR, cons
                 } else {
                     vb = (unsigned)(k[0] >> 32);
 #pragma unroll
-                    for (int r = 1; r < 7; r++) if (cross - 1 == r) vb = (unsigned)(k[r] >> 32);
+                    for (int r = 1; r < E - 1; r++) if (cross - 1 == r) vb = (unsigned)(k[r] >> 32);
                 }
             }
             vb = __shfl_sync(0xffffffffu, vb, src);
@@ -376,8 +380,10 @@ static asw_status dev_weighted_median(asw_ctx* ctx, const uint8_t* dL, const uin
         ASW_TRY(ws_get(ctx, WS_GEO_R, (size_t)nn * H * Wr, &WRp));
         LAUNCH(ctx, "wm_weights", (k_wm_weights_px<<<(unsigned)(((size_t)nn * H * W + 255) / 256), 256, 0, ctx->stream>>>(pl, H, W, W, 0, win, alpha_r, WLp)));
         LAUNCH(ctx, "wm_weights", (k_wm_weights_px<<<(unsigned)(((size_t)nn * H * Wr + 255) / 256), 256, 0, ctx->stream>>>(pr, H, W, Wr, v.max_off, win, alpha_r, WRp)));
-        LAUNCH(ctx, "wm_aggregate", (k_wm_aggregate3<<<dim3(cdiv(W, WM3_WARPS), H), 32 * WM3_WARPS, 0, ctx->stream>>>(
-                                        WLp, WRp, cost, g, alpha_s, min_d, keys, agg_dev)));
+        const dim3 wgrid(cdiv(W, WM3_WARPS), H);
+        if (nn <= 64) LAUNCH(ctx, "wm_aggregate", (k_wm_aggregate3<2><<<wgrid, 32 * WM3_WARPS, 0, ctx->stream>>>(WLp, WRp, cost, g, alpha_s, min_d, keys, agg_dev)));
+        else if (nn <= 128) LAUNCH(ctx, "wm_aggregate", (k_wm_aggregate3<4><<<wgrid, 32 * WM3_WARPS, 0, ctx->stream>>>(WLp, WRp, cost, g, alpha_s, min_d, keys, agg_dev)));
+        else LAUNCH(ctx, "wm_aggregate", (k_wm_aggregate3<8><<<wgrid, 32 * WM3_WARPS, 0, ctx->stream>>>(WLp, WRp, cost, g, alpha_s, min_d, keys, agg_dev)));
         return keys_to_disp(ctx, keys, n, disp_dev);
     }
     if (!asw_dev("ASW_WM_SCAN") && planes <= ((size_t)6 << 30)) {
