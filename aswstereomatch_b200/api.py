@@ -52,7 +52,7 @@ EXPORTS = [
     "asw_set_tuning", "asw_host_alloc", "asw_host_free", "asw_stereo_matching", "asw_method_candidates", "asw_adaptive_weight",
     "asw_adaptive_weight_direct8", "asw_adaptive_weight_geodesic", "asw_adaptive_weight_bilateral_grid", "asw_adaptive_weight_blo1",
     "asw_adaptive_weight_guidedf", "asw_adaptive_weight_guidedf_2", "asw_adaptive_weight_guidedf_3", "asw_ncc", "asw_cost_ncc", "asw_adaptive_weight_weighted_median",
-    "asw_capture_aggregated", "asw_cost_tad_cg", "asw_cost_sad_box", "asw_wta", "asw_guided_filter",
+    "asw_capture_aggregated", "asw_cost_tad_cg", "asw_cost_tad_cg_padded", "asw_cost_sad_box", "asw_wta", "asw_guided_filter",
     "asw_geodesic_dist", "asw_lr_check", "asw_fill_invalid", "asw_wmedian_refine", "asw_guidedf2_lr_refine", "asw_disparity_to_u8", "asw_preprocess", "asw_batch_upload_raw",
     "asw_batch_create", "asw_batch_destroy", "asw_batch_set_active", "asw_batch_upload", "asw_batch_run_guidedf2_lr_refine",
     "asw_batch_run_method", "asw_batch_download", "asw_split_local_keys", "asw_keys_alloc", "asw_keys_download",
@@ -111,6 +111,7 @@ def load_library():
         "asw_fill_invalid": (ci, [vp, pf32, pmask, pf32]),
         "asw_wmedian_refine": (ci, [vp, pu8, pf32, pmask, ci, cd, cd, pf32]),
         "asw_guidedf2_lr_refine": (ci, [vp, pu8, pu8, pf32, cd, ci, ci, ci, cf, cd, cd, pf32, pf32, pmask]),
+        "asw_cost_tad_cg_padded": (ci, [vp, pu8, pu8, vp, cd, cd, cd, ci, ci, ci, ci]),
         "asw_disparity_to_u8": (ci, [vp, pf32, pmask]),
         "asw_preprocess": (ci, [vp, pu8, pu8]),
         "asw_batch_upload_raw": (ci, [vp, ci, pu8, pu8]),
@@ -323,6 +324,19 @@ class Context:
                              int(minDisparity), int(numDisparity)), numDisparity, agg, strict)
 
     # ---- stage level ----
+    def computeSimilarity_padded(self, leftImg, rightImg, regularity, thresC, thresG, dispType, winSize, minDisparity,
+                                 numDisparity):
+        """computeSimilarity 8-arg (A.h:115-117): the [D][H + 2h][W + 2h] float volume, every slice REFLECT-padded by winSize / 2."""
+        La, Ls = _u8(leftImg)
+        Ra, Rs = _u8(rightImg)
+        H, W = La.shape[:2]
+        h = int(winSize) // 2
+        vol = np.empty((numDisparity, H + 2 * h, W + 2 * h), np.float32)
+        self._chk(self.lib.asw_cost_tad_cg_padded(self.h, C.byref(Ls), C.byref(Rs), vol.ctypes.data, float(regularity),
+                                                  float(thresC), float(thresG), int(dispType), int(winSize),
+                                                  int(minDisparity), int(numDisparity)))
+        return vol
+
     def computeSimilarity(self, leftImg, rightImg, regularity, thresC, thresG, dispType, minDisparity,
                           numDisparity):
         """computeSimilarity 7-arg (A.h:112-114): returns the [D][H][W] float volume (cost_d_imgs)."""

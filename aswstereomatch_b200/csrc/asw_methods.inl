@@ -30,6 +30,42 @@ extern "C" asw_status asw_cost_tad_cg(asw_ctx* ctx, const asw_u8_image* L, const
     return ASW_OK;
 }
 
+// copyMakeBorder(slice, h, h, h, h, BORDER_REFLECT) of every cost slice (A.cpp:651-668): out [D][H + 2h][W + 2h]
+__global__ void k_pad_reflect_slices(const float* __restrict__ vol, int H, int W, int h, float* __restrict__ out) {
+    const int Wp = W + 2 * h, Hp = H + 2 * h;
+    const int xp = blockIdx.x * blockDim.x + threadIdx.x, yp = blockIdx.y, d = blockIdx.z;
+    if (xp >= Wp) return;
+    out[((size_t)d * Hp + yp) * Wp + xp] = vol[((size_t)d * H + border_idx(yp - h, H, 0)) * W + border_idx(xp - h, W, 0)];
+}
+extern "C" asw_status asw_cost_tad_cg_padded(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, float* host_volume,
+                                             double regularity, double thres_c, double thres_g, int disp_type,
+                                             int win, int min_d, int num_d) {      // the reference's order (A.h:112-114)
+    ASW_TRY(check_pair(ctx, L, R, nullptr));
+    if (!host_volume || num_d <= 0 || min_d < 0 || (disp_type != 0 && disp_type != 1) || win <= 0 || win % 2 == 0)
+        return asw_fail(ctx, ASW_ERR_BAD_ARG, "bad cost arguments%s%s");
+    ASW_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int H = L->rows, W = L->cols, h = win / 2;
+    const size_t n = (size_t)H * W, np_ = (size_t)(H + 2 * h) * (W + 2 * h);
+    uint8_t *dL, *dR;
+    ASW_TRY(upload_pair(ctx, L, R, &dL, &dR));
+    ViewGeom v = make_view(dL, dR, H, W, disp_type, min_d, num_d);
+    Feat *fref, *ftgt;
+    float *vol, *padded;
+    ASW_TRY(ws_get(ctx, WS_FEAT_REF, n, &fref));
+    ASW_TRY(ws_get(ctx, WS_FEAT_TGT, (size_t)H * v.Wp, &ftgt));
+    ASW_TRY(ws_get(ctx, WS_VOL0, n * num_d, &vol));
+    ASW_TRY(ws_get(ctx, WS_VOL1, np_ * num_d, &padded));
+    LAUNCH(ctx, "features", (k_features<<<dim3(cdiv(W, 128), H), 128, 0, ctx->stream>>>(v.ref, H, W, 0, 0, fref)));
+    LAUNCH(ctx, "features", (k_features<<<dim3(cdiv(v.Wp, 128), H), 128, 0, ctx->stream>>>(v.tgt, H, W, v.pad_l, v.pad_r, ftgt)));
+    TadParams tp = make_tad_params(regularity, thres_c, thres_g);
+    LAUNCH(ctx, "cost_tad_volume", (k_cost_tad_volume<<<dim3(cdiv(W, 128), H, num_d), 128, 0, ctx->stream>>>(
+                                       fref, ftgt, H, W, v.Wp, v.x0_base, v.x0_step, tp, vol)));
+    LAUNCH(ctx, "pad_reflect", (k_pad_reflect_slices<<<dim3(cdiv(W + 2 * h, 128), H + 2 * h, num_d), 128, 0, ctx->stream>>>(vol, H, W, h, padded)));
+    ASW_CUDA(ctx, cudaMemcpyAsync(host_volume, padded, np_ * num_d * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    ASW_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return ASW_OK;
+}
+
 extern "C" asw_status asw_cost_sad_box(asw_ctx* ctx, const asw_u8_image* L, const asw_u8_image* R, float* host_volume,
                                        int disp_type, int win, int min_d, int num_d) {
     ASW_TRY(check_pair(ctx, L, R, nullptr));

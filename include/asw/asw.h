@@ -133,10 +133,15 @@ asw_status asw_adaptive_weight_weighted_median(asw_ctx* ctx, const asw_u8_image*
 asw_status asw_capture_aggregated(asw_ctx* ctx, float* host_volume, size_t capacity_floats);
 
 /* ---- stage level ---- */
-/* computeSimilarity 7-arg (A.h:112-114, A.cpp:415-487): volume [num_disparity][rows][cols] */
+/* computeSimilarity 7-arg (A.h:109-111, A.cpp:415-487): volume [num_disparity][rows][cols] */
 asw_status asw_cost_tad_cg(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
                            float* host_volume, double regularity, double thres_c, double thres_g,
                            int disp_type, int min_disparity, int num_disparity);
+/* computeSimilarity 8-arg (A.h:112-114, A.cpp:488-668): the same cost, every slice padded by win_size / 2 with BORDER_REFLECT
+ * (what the weighted-median method consumes): volume [num_disparity][rows + 2h][cols + 2h] */
+asw_status asw_cost_tad_cg_padded(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
+                                  float* host_volume, double regularity, double thres_c, double thres_g,
+                                  int disp_type, int win_size, int min_disparity, int num_disparity);
 /* getCostSAD_d for every d (A.h:157, A.cpp:2442-2503 as called at A.cpp:2524-2536) */
 asw_status asw_cost_sad_box(asw_ctx* ctx, const asw_u8_image* left, const asw_u8_image* right,
                             float* host_volume, int disp_type, int win_size, int min_disparity,

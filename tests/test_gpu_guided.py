@@ -32,6 +32,15 @@ def test_cost_tad_cg_bit_exact(ctx, H, W, D, seed, disp_type):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("H,W,D,win,disp_type", [(40, 56, 8, 9, 0), (33, 47, 5, 15, 0), (21, 30, 4, 35, 0), (40, 56, 8, 7, 1)])
+def test_cost_tad_cg_padded_bit_exact(ctx, H, W, D, win, disp_type):
+    """row a-2: computeSimilarity 8-arg (A.cpp:651-668): every slice REFLECT-padded by win / 2, also windows wider than the image"""
+    L, R, _ = make_pair(H, W, D, 17)
+    got = ctx.computeSimilarity_padded(L, R, 0.4, 10, 50, disp_type, win, 0, D)
+    ref = orc.cost_tad_cg_padded(L, R, 0, D, win, disp_type)
+    assert got.shape == ref.shape and np.array_equal(got, ref)
+
+
 def test_cost_tad_cg_golden(ctx):
     g = np.load("tests/golden/cv2_stages_40x56_d8.npz")
     got = ctx.computeSimilarity(g["L"], g["R"], 0.4, 10, 50, 0, 0, 8)
