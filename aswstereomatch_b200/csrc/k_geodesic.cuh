@@ -4,7 +4,10 @@
 //   from the BORDER_REFLECT-padded image (A.cpp:1404).  Pass schedule of the reference: iterations 0 and 1
 //   are the BACKWARD raster (neighbours R, BR, B, BL), iteration 2 the FORWARD raster (L, UL, U, UR) because
 //   the test is iterCount/2 (A.cpp:1341, 1365).  The second backward sweep is provably a no-op (every cell
-//   already equals the min over its final predecessors), so two sweeps are run.  Distances are exact
+//   already equals the min over its final predecessors), so two sweeps are run.  The backward raster only looks right
+//   and down, so it leaves every window row BELOW the centre row at its initial FLT_MAX: those rows are neither swept,
+//   written nor re-read (the forward sweep starts them from "infinity"): 18 instead of 35 backward rows at 35 x 35 and
+//   a third less traffic through the distance volume.  Distances are exact
 //   integers (L1 colour steps; < 2^24) so integer arithmetic is bit-identical to the reference's floats.
 //   One thread per pixel; the window is stored plane-major dist[tap][y][x] so that both the DP's global
 //   traffic and the aggregation's loads are coalesced across threads.
@@ -37,8 +40,9 @@ k_geo_dist(const uint32_t* __restrict__ ext, int H, int W, int win, float* __res
     int prev[GEO_MAXW + 2], cur[GEO_MAXW + 2];
     uint32_t pprev[GEO_MAXW + 2], pcur[GEO_MAXW + 2];
     // ---- backward sweep: rows win..1, cols win..1; neighbours (r,c+1), (r+1,c+1), (r+1,c), (r+1,c-1) ----
-    for (int c = 0; c <= win + 1; c++) { prev[c] = GEO_INF; pprev[c] = ext[(size_t)(y + win + 1) * Wp + x + c]; }
-    for (int r = win; r >= 1; r--) {
+    // rows win .. h+2 stay "infinite" (no finite neighbour to the right or below): start at the centre row
+    for (int c = 0; c <= win + 1; c++) { prev[c] = GEO_INF; pprev[c] = ext[(size_t)(y + h + 2) * Wp + x + c]; }
+    for (int r = h + 1; r >= 1; r--) {
         const uint32_t* row = ext + (size_t)(y + r) * Wp + x;
         for (int c = 0; c <= win + 1; c++) pcur[c] = row[c];
         cur[win + 1] = GEO_INF; cur[0] = GEO_INF;
@@ -61,7 +65,7 @@ k_geo_dist(const uint32_t* __restrict__ ext, int H, int W, int win, float* __res
         for (int c = 0; c <= win + 1; c++) pcur[c] = row[c];
         cur[0] = GEO_INF; cur[win + 1] = GEO_INF;
         for (int c = 1; c <= win; c++) {
-            int v = (int)dist[(size_t)((r - 1) * win + (c - 1)) * n + p];  // value left by the backward sweep
+            int v = r <= h + 1 ? (int)dist[(size_t)((r - 1) * win + (c - 1)) * n + p] : GEO_INF;  // value left by the backward sweep
             uint32_t me = pcur[c];
             v = min(v, cur[c - 1] + (int)__vsadu4(pcur[c - 1], me));      // left
             v = min(v, prev[c - 1] + (int)__vsadu4(pprev[c - 1], me));    // up-left
@@ -88,9 +92,10 @@ k_geo_dist_t(const uint32_t* __restrict__ ext, int H, int W, float* __restrict__
     uint32_t pprev[WIN + 2], pcur[WIN + 2];
     // ---- backward sweep: rows WIN..1, cols WIN..1; neighbours (r,c+1), (r+1,c+1), (r+1,c), (r+1,c-1) ----
 #pragma unroll
-    for (int c = 0; c <= WIN + 1; c++) { d[c] = GEO_INF; pprev[c] = ext[(size_t)(y + WIN + 1) * Wp + x + c]; }
+    for (int c = 0; c <= WIN + 1; c++) { d[c] = GEO_INF; pprev[c] = ext[(size_t)(y + h + 2) * Wp + x + c]; }
+    // rows WIN .. h+2 stay "infinite" (no finite neighbour to the right or below): the sweep starts at the centre row
 #pragma unroll 1
-    for (int r = WIN; r >= 1; r--) {
+    for (int r = h + 1; r >= 1; r--) {
         const uint32_t* row = ext + (size_t)(y + r) * Wp + x;
 #pragma unroll
         for (int c = 0; c <= WIN + 1; c++) pcur[c] = row[c];
@@ -120,9 +125,14 @@ k_geo_dist_t(const uint32_t* __restrict__ ext, int H, int W, float* __restrict__
 #pragma unroll 1
     for (int r = 1; r <= WIN; r++) {
         const uint32_t* row = ext + (size_t)(y + r) * Wp + x;
-        float back[WIN];
+        float back[WIN];                                            // left by the backward sweep (rows up to the centre row)
+        if (r <= h + 1) {
 #pragma unroll
-        for (int c = 0; c < WIN; c++) back[c] = dist[(size_t)((r - 1) * WIN + c) * n + p];   // left by the backward sweep
+            for (int c = 0; c < WIN; c++) back[c] = dist[(size_t)((r - 1) * WIN + c) * n + p];
+        } else {
+#pragma unroll
+            for (int c = 0; c < WIN; c++) back[c] = (float)GEO_INF;
+        }
 #pragma unroll
         for (int c = 0; c <= WIN + 1; c++) pcur[c] = row[c];
         int old_left = d[0];
