@@ -80,8 +80,14 @@ k_geo_dist(const uint32_t* __restrict__ ext, int H, int W, int win, float* __res
 
 // Window size as a template constant: the DP row (distances + the colours of the previous and the current window
 // row) lives in registers instead of local memory; the row update runs in place with one saved neighbour.
+// 4 resident CTAs per SM (128 registers, 32 bytes of spills at 35 x 35): the DP is a chain of dependent min / add steps,
+// the fourth CTA hides more of it than the spills cost (measured at 1280 x 720, two images: 3.83 ms; 3 CTAs / 168 registers
+// 4.09, unconstrained 140 registers 4.04, 5 CTAs / 96 registers 5.20 ms)
+#ifndef GEO_DIST_MINB
+#define GEO_DIST_MINB 4
+#endif
 template <int WIN>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, GEO_DIST_MINB)
 k_geo_dist_t(const uint32_t* __restrict__ ext, int H, int W, float* __restrict__ dist) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
