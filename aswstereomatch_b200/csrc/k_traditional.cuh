@@ -123,9 +123,21 @@ k_trad_aggregate(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tg
 // both as u8 (weight-table index) and as float (cost samples), the exact weight-table rows of one window row
 // staged in shared memory per group of `win` taps.  Thread = pixel, TR_Q candidates in registers.
 // ------------------------------------------------------------------------------------------------
+// Tile 32 x 4 pixels, 17 candidates per thread, 4 CTAs of 128 threads per SM (128 registers, no spills).  17 candidates = the
+// D + 1 = 17 of config 1 in one chunk, and the per-tap work that does not depend on the candidate (tap record, reference
+// exponent, reference sample) is shared by 17 evaluations instead of 9.  Measured (trad_aggregate, ms; 384x288x16 win 35 /
+// 640x360x64 win 15 / 1280x720x64 win 35): 32x8, Q 9, 3 CTAs (round 1-2) 0.96 / 1.31 / 26.3; 32x8, Q 17, 2 CTAs 0.92 / 1.19 / 22.8;
+// 32x4, Q 17, 4 CTAs 0.88 / 1.17 / 22.8; 32x4, Q 22, 3 CTAs 1.13 / 1.14 / 22.1; 32x4, Q 13 1.50 / 1.20 / 23.7; 32x2, Q 17 1.03 / 1.20 / 25.7
 #define TR_TW 32
-#define TR_TH 8
-#define TR_Q 9
+#ifndef TR_TH
+#define TR_TH 4
+#endif
+#ifndef TR_Q
+#define TR_Q 17
+#endif
+#ifndef TR_MINB
+#define TR_MINB 4
+#endif
 
 template <bool INTERIOR>
 __device__ __forceinline__ void trad_tile_body(const uint8_t* __restrict__ refU, const float* __restrict__ refF,
@@ -457,7 +469,7 @@ __device__ __forceinline__ void trad_lin_body(const float* __restrict__ RF, cons
 }
 
 template <int SIGN>
-__global__ void __launch_bounds__(TR_TW * TR_TH, 3)
+__global__ void __launch_bounds__(TR_TW * TR_TH, TR_MINB)
 k_trad_lin(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ tgt, const float* __restrict__ c2, float a2,
            TradGeom g, unsigned long long* __restrict__ keys, float* __restrict__ agg) {
     extern __shared__ __align__(16) float sm_tr[];
