@@ -89,11 +89,22 @@ __global__ void k_bgr2gray_pad(const uint8_t* __restrict__ img, int H, int W, in
 // blockIdx.y = slice of a batch (n bytes per slice, one min / max pair per slice)
 __global__ void k_minmax_u8(const uint8_t* __restrict__ src, size_t n, int* __restrict__ mm) {
     src += (size_t)blockIdx.y * n; mm += 2 * blockIdx.y;
-    int mn = 255, mx = 0;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        int v = src[i];
-        mn = min(mn, v); mx = max(mx, v);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+    // 16 bytes per load, byte-wise min / max on packed words; the unaligned head and the tail byte by byte
+    size_t head = (16 - ((size_t)(uintptr_t)src & 15)) & 15;
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / 16;
+    const uint4* v = (const uint4*)(src + head);
+    unsigned int mn4 = 0xFFFFFFFFu, mx4 = 0u;
+    for (size_t i = tid; i < nvec; i += nt) {
+        const uint4 q = __ldg(&v[i]);
+        mn4 = __vminu4(mn4, __vminu4(__vminu4(q.x, q.y), __vminu4(q.z, q.w)));
+        mx4 = __vmaxu4(mx4, __vmaxu4(__vmaxu4(q.x, q.y), __vmaxu4(q.z, q.w)));
     }
+    int mn = (int)min(min(mn4 & 0xFF, (mn4 >> 8) & 0xFF), min((mn4 >> 16) & 0xFF, mn4 >> 24));
+    int mx = (int)max(max(mx4 & 0xFF, (mx4 >> 8) & 0xFF), max((mx4 >> 16) & 0xFF, mx4 >> 24));
+    for (size_t i = tid; i < head; i += nt) { const int b = src[i]; mn = min(mn, b); mx = max(mx, b); }
+    for (size_t i = head + nvec * 16 + tid; i < n; i += nt) { const int b = src[i]; mn = min(mn, b); mx = max(mx, b); }
     for (int o = 16; o > 0; o >>= 1) {
         mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -191,15 +202,26 @@ k_box_f32_stream(const float* __restrict__ src, float* __restrict__ dst, int H, 
     const int xo = x0 + cx;
     const bool writer = cx < SW && xo < W;
     int buf = 0;
+    // the row entering / leaving the window is requested one row ahead of its use; the horizontal sum runs as four
+    // independent chains (every partial sum is exact in double, so the grouping does not change the result)
+    float nin = s[(size_t)border_idx(y_begin + a, H, 1) * W], nout = s[(size_t)border_idx(y_begin - a, H, 1) * W];
     for (int y = y_begin; y < y_end; y++) {
-        V += (double)s[(size_t)border_idx(y + a, H, 1) * W];
+        const float cin = nin, cout = nout;
+        if (y + 1 < y_end) {
+            nin = s[(size_t)border_idx(y + 1 + a, H, 1) * W];
+            nout = s[(size_t)border_idx(y + 1 - a, H, 1) * W];
+        }
+        V += (double)cin;
         vs[buf][cx] = V;
-        V -= (double)s[(size_t)border_idx(y - a, H, 1) * W];
+        V -= (double)cout;
         __syncthreads();
         if (writer) {
-            double acc = 0.0;
-            for (int j = 0; j < k; j++) acc += vs[buf][cx + j];
-            o[(size_t)y * W + xo] = (float)(acc * scale);
+            const double* w = &vs[buf][cx];
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            int j = 0;
+            for (; j + 4 <= k; j += 4) { a0 += w[j]; a1 += w[j + 1]; a2 += w[j + 2]; a3 += w[j + 3]; }
+            for (; j < k; j++) a0 += w[j];
+            o[(size_t)y * W + xo] = (float)(((a0 + a1) + (a2 + a3)) * scale);
         }
         buf ^= 1;
     }
