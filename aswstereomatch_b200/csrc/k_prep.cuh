@@ -118,10 +118,16 @@ __global__ void k_minmax_f32_slices(const float* __restrict__ vol, size_t n, uin
     int d = blockIdx.y;
     const float* s = vol + (size_t)d * n;
     uint32_t mn = 0xFFFFFFFFu, mx = 0u;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float v = s[i];
-        if (v == v) { uint32_t o = orderable_u32(v); mn = min(mn, o); mx = max(mx, o); }
-    }
+    auto take = [&](float v) { if (v == v) { uint32_t o = orderable_u32(v); mn = min(mn, o); mx = max(mx, o); } };
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+    // 16-byte loads over the aligned body of the slice, the unaligned head and the tail element by element
+    size_t head = ((16 - ((size_t)(uintptr_t)s & 15)) & 15) / 4;
+    if (head > n) head = n;
+    const size_t nvec = (n - head) / 4;
+    const float4* v4 = (const float4*)(s + head);
+    for (size_t i = tid; i < nvec; i += nt) { const float4 q = __ldg(&v4[i]); take(q.x); take(q.y); take(q.z); take(q.w); }
+    for (size_t i = tid; i < head; i += nt) take(s[i]);
+    for (size_t i = head + nvec * 4 + tid; i < n; i += nt) take(s[i]);
     for (int o = 16; o > 0; o >>= 1) {
         mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
         mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
