@@ -194,10 +194,11 @@ __global__ void k_box_f32(const float* __restrict__ src, float* __restrict__ dst
 // instead of the tiled kernel's ~4 k, and no (k-1)-row halo per 8 output rows.
 #define BOXS_COLS 128
 #define BOXS_RUN 7
+#define BOXS_ROWS 4
 __global__ void __launch_bounds__(BOXS_COLS)
 k_box_f32_stream(const float* __restrict__ src, float* __restrict__ dst, int H, int W, int k, size_t plane_stride, int band_rows) {
-    __shared__ double vs[2][BOXS_COLS];
-    __shared__ float os[2][BOXS_COLS];
+    __shared__ double vs[2][BOXS_ROWS][BOXS_COLS];
+    __shared__ float os[2][BOXS_ROWS][BOXS_COLS];
     const int a = k / 2, SW = BOXS_COLS - (k - 1);
     const int cx = threadIdx.x, x0 = blockIdx.x * SW;
     const int sx = border_idx(x0 - a + cx, W, 1);
@@ -210,45 +211,54 @@ k_box_f32_stream(const float* __restrict__ src, float* __restrict__ dst, int H, 
     const int xo = x0 + cx;
     const bool writer = cx < SW && xo < W;
     int buf = 0;
-    // Horizontal sums: thread t slides over BOXS_RUN = 7 adjacent outputs (k - 1 + 7 loads for 7 outputs instead of 7 k; an odd
-    // run keeps the 8-byte loads of a half-warp on distinct banks); every partial sum is exact in double, so neither the
-    // grouping nor the sliding update changes a result.  The 7 results of a thread go through shared memory and are
-    // written to global memory one row later by the column threads (coalesced), after the next row's barrier.
-    // The row entering / leaving the vertical window is requested one row ahead of its use.
-    float nin = s[(size_t)border_idx(y_begin + a, H, 1) * W], nout = s[(size_t)border_idx(y_begin - a, H, 1) * W];
-    for (int y = y_begin; y < y_end; y++) {
-        const float cin = nin, cout = nout;
-        if (y + 1 < y_end) {
-            nin = s[(size_t)border_idx(y + 1 + a, H, 1) * W];
-            nout = s[(size_t)border_idx(y + 1 - a, H, 1) * W];
+    // BOXS_ROWS = 4 rows per barrier.  Vertical: a thread advances its column sum over the 4 rows (their 8 loads are issued
+    // together).  Horizontal: warp r takes row r; lane l slides over BOXS_RUN = 7 adjacent outputs (k - 1 + 7 loads for 7 outputs;
+    // an odd run keeps the 8-byte loads of a half-warp on distinct banks).  Every partial sum is exact in double, so neither the
+    // grouping nor the sliding update changes a result.  The results go through shared memory and are written to global memory
+    // by the column threads (coalesced) after the next group's barrier.
+    const int hr = cx >> 5, c0 = (cx & 31) * BOXS_RUN;
+    for (int y = y_begin; y < y_end; y += BOXS_ROWS) {
+        float fin[BOXS_ROWS], fout[BOXS_ROWS];
+#pragma unroll
+        for (int r = 0; r < BOXS_ROWS; r++) {
+            fin[r] = s[(size_t)border_idx(y + r + a, H, 1) * W];
+            fout[r] = s[(size_t)border_idx(y + r - a, H, 1) * W];
         }
-        V += (double)cin;
-        vs[buf][cx] = V;
-        V -= (double)cout;
+#pragma unroll
+        for (int r = 0; r < BOXS_ROWS; r++) {
+            V += (double)fin[r];
+            vs[buf][r][cx] = V;
+            V -= (double)fout[r];
+        }
         __syncthreads();
-        if (y > y_begin && writer) o[(size_t)(y - 1) * W + xo] = os[buf ^ 1][cx];
-        // the active lanes stay in one warp: spread over the four warps every warp would issue the whole phase (measured 3.5 vs 2.2 ms)
-        const int c0 = cx * BOXS_RUN;
-        if (c0 < SW) {
-            const double* w = &vs[buf][c0];
+        if (y > y_begin && writer) {
+#pragma unroll
+            for (int r = 0; r < BOXS_ROWS; r++) o[(size_t)(y - BOXS_ROWS + r) * W + xo] = os[buf ^ 1][r][cx];
+        }
+        if (hr < BOXS_ROWS && y + hr < y_end && c0 < SW) {
+            const double* w = &vs[buf][hr][c0];
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             int j = 0;
             for (; j + 4 <= k; j += 4) { a0 += w[j]; a1 += w[j + 1]; a2 += w[j + 2]; a3 += w[j + 3]; }
             for (; j < k; j++) a0 += w[j];
             double sum = (a0 + a1) + (a2 + a3);
-            os[buf][c0] = (float)(sum * scale);
+            os[buf][hr][c0] = (float)(sum * scale);
 #pragma unroll
             for (int g = 1; g < BOXS_RUN; g++) {
                 if (c0 + g < SW) {
                     sum += w[k - 1 + g] - w[g - 1];
-                    os[buf][c0 + g] = (float)(sum * scale);
+                    os[buf][hr][c0 + g] = (float)(sum * scale);
                 }
             }
         }
         buf ^= 1;
     }
     __syncthreads();
-    if (y_end > y_begin && writer) o[(size_t)(y_end - 1) * W + xo] = os[buf ^ 1][cx];
+    if (y_end > y_begin && writer) {
+        const int ylast = y_begin + ((y_end - y_begin - 1) / BOXS_ROWS) * BOXS_ROWS;     // first row of the last group
+#pragma unroll
+        for (int r = 0; r < BOXS_ROWS; r++) if (ylast + r < y_end) o[(size_t)(ylast + r) * W + xo] = os[buf ^ 1][r][cx];
+    }
 }
 
 static inline asw_status launch_box_f32(asw_ctx* ctx, const float* src, float* dst, int H, int W, int k,
